@@ -1,0 +1,156 @@
+/*
+ * vl2.h — C-ABI of libvl2.so, the B200 (sm_100a) kernel library behind the VideoLLaMA2 video->text prefill path.
+ *
+ * The reference (DAMO-NLP-SG/VideoLLaMA2) is pure Python on top of HF transformers / timm / torch; it has no FFI.
+ * Each entry point below therefore replaces a *library call site* of the reference hot path; the citation after
+ * each declaration is the reference line (relative to /root/reference, or HF: = transformers/models) whose
+ * arithmetic the call performs.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers + sizes; no torch types.  All data pointers are DEVICE pointers unless named host_*.
+ *  - bf16 storage (`uint16_t`-sized), fp32 accumulate.  Row-major, leading dimensions in ELEMENTS.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls enqueue work and return; they never synchronise, never
+ *    allocate device memory, and are CUDA-graph capturable.
+ *  - Every call returns 0 on success or a negative VL2_E_* code; vl2_last_error() gives a thread-local message.
+ *  - There is no CPU fallback: on a machine without an sm_100 device the calls fail with VL2_E_CUDA.
+ */
+#ifndef VL2_H_
+#define VL2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VL2_VERSION 100
+
+enum {
+  VL2_OK = 0,
+  VL2_E_BADSHAPE = -1,
+  VL2_E_BADDTYPE = -2,
+  VL2_E_BADALIGN = -3,
+  VL2_E_CUDA = -4,
+  VL2_E_NCCL = -5,
+  VL2_E_UNSUPPORTED = -6
+};
+
+/* GEMM epilogue activations. */
+enum {
+  VL2_ACT_NONE = 0,
+  VL2_ACT_QUICK_GELU = 1, /* x*sigmoid(1.702x)          HF:clip/modeling_clip.py:339-351 (quick_gelu)      */
+  VL2_ACT_SILU = 2,       /* x*sigmoid(x)               projector.py:173 (nn.SiLU), timm LayerNormAct2d     */
+  VL2_ACT_GELU_ERF = 3,   /* 0.5x(1+erf(x/sqrt2))       projector.py:128 (nn.GELU)                          */
+  VL2_ACT_SWIGLU = 4      /* out[:,j] = silu(acc[:,2j])*acc[:,2j+1]  HF:mistral/modeling_mistral.py:46-48   */
+};
+
+int vl2_version(void);
+const char* vl2_last_error(void);
+/* Number of kernel launches issued by this library in this process (bench.py's gpu_launches counter). */
+int64_t vl2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense bf16 GEMM on tcgen05 tensor cores:  C[M,Nout] = epi( A[M,K] * W[N,K]^T ).
+ *   epi(acc) = act( acc * row_scale[m] + bias[n] ) + residual[m,n]        (each term optional)
+ *   VL2_ACT_SWIGLU: W rows interleave gate/up (row 2j = gate_j, row 2j+1 = up_j); Nout = N/2; residual unsupported.
+ * Replaces nn.Linear / 1x1 nn.Conv2d / (after im2col) nn.Conv2d and nn.Conv3d call sites:
+ *   HF:clip/modeling_clip.py:294-311,339-351 ; projector.py:153-187 (timm RegStage 1x1 convs, Conv3d, readout MLP) ;
+ *   HF:mistral/modeling_mistral.py:35-48,122-177,402-470.
+ * Requirements: K % 8 == 0, N % 8 == 0, lda/ldw/ldc/ldr % 8 == 0, pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vl2_gemm_args {
+  const void* A;   /* bf16 [M,K]  */
+  const void* W;   /* bf16 [N,K]  */
+  void* C;         /* bf16 [M,Nout] (or fp32 if out_f32) */
+  const float* bias;      /* fp32 [N] or NULL  */
+  const void* residual;   /* bf16 [M,Nout] or NULL */
+  const float* row_scale; /* fp32 [M] or NULL */
+  int64_t lda, ldw, ldc, ldr;
+  int32_t M, N, K;
+  int32_t act;
+  int32_t out_f32;
+  int32_t reserved;
+} vl2_gemm_args;
+int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
+
+/* Skinny GEMM (M <= 32 rows, HBM-bound weight streaming): C[M,N] = act(A[M,K] W[N,K]^T + bias).
+ * Used for the SE excitation MLP of the RegStage blocks (timm SEModule, projector.py:153-161) and the last-position
+ * lm_head GEMV (HF:mistral/modeling_mistral.py:463-466 with logits_to_keep=1).  act_out: VL2_ACT_NONE/SILU or
+ * 100 = sigmoid.  C is fp32 if out_f32 else bf16. A is fp32 if a_f32 else bf16. */
+int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, void* C, int out_f32, int M, int N,
+                    int K, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused attention (FlashAttention-style, tcgen05 QK^T / PV with TMEM accumulators, TMA-staged K/V).
+ *   q: bf16 [B*S, ldq] with head h at columns [q_off + h*D, +D)   (likewise k, v with kv head h / (Hq/Hkv))
+ *   out: bf16 [B*S, ldo], head h at columns [h*D, +D).  softmax scale applied to logits in fp32.
+ * causal = 0: HF:clip/modeling_clip.py:282-336 (CLIPAttention, 16 heads x 64).
+ * causal = 1: HF:mistral/modeling_mistral.py:122-177 / qwen2/modeling_qwen2.py:187-246 (GQA, D=128).
+ * D in {64, 128}.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vl2_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int64_t ldq, ldk, ldv, ldo; /* row strides in elements */
+  int32_t B, S, Hq, Hkv, D;
+  int32_t causal;
+  float scale;
+  int32_t reserved;
+} vl2_attn_args;
+int vl2_attention(const vl2_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Row-wise normalisations (HBM-bound, one pass).
+ * vl2_layernorm: y = act( LN(x; gamma, beta, eps) [+ residual] )  over the last dim C (bf16 in/out, fp32 math).
+ *   act in {NONE, SILU}; with residual the order is act(LN(x) + residual)   (timm Bottleneck: act3(conv3(..)+shortcut)).
+ *   HF:clip/modeling_clip.py:363-385 (layer_norm1/2, pre_layrnorm) ; timm LayerNormAct2d inside RegStage.
+ * vl2_rmsnorm:   y = bf16( x * rsqrt(mean(x^2)+eps) ) * gamma     HF:mistral/modeling_mistral.py:182-199.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vl2_layernorm(const void* x, const void* gamma, const void* beta, const void* residual, void* y, int64_t rows,
+                  int C, float eps, int act, void* stream);
+int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t rows, int C, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CLIP patch embedding front/back ends (HF:clip/modeling_clip.py:202-218).
+ * vl2_patch_im2col: pixels bf16 [F,3,H,W] (NCHW) -> A bf16 [F*(H/P)*(W/P), Kpad], column = c*P*P + i*P + j, zero
+ *   padded to Kpad (Kpad % 64 == 0) so the patch conv becomes vl2_gemm_bf16 against weight[1024, Kpad].
+ * vl2_clip_embed_finish: tok[f, 0] = cls + pos[0]; tok[f, 1+p] = patch[f*np+p] + pos[1+p]; then pre_layrnorm.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vl2_patch_im2col(const void* pixels, void* A, int F, int H, int W, int P, int Kpad, void* stream);
+int vl2_clip_embed_finish(const void* patch, const void* cls, const void* pos, const void* gamma, const void* beta,
+                          void* tok, int F, int np, int C, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * STC connector pieces (projector.py:133-215; timm regnet.Bottleneck), channels-last [F,H,W,C].
+ * vl2_dwconv3x3_ln_silu: y = SiLU(LN_c(depthwise3x3(x; w[9,C]))); if pooled != NULL it must hold F*C + F*H*C floats:
+ *   pooled[0 : F*C] receives mean_{h,w} y[f,h,w,c] (the SE squeeze), the rest is workspace for per-row partial sums
+ *   (deterministic two-step reduction, no atomics).
+ * vl2_se_scale: y[f,p,c] *= s[f,c]  (s fp32 [F,C]).
+ * vl2_conv3d_im2col: A[(t',h',w'), tap*C + c] = x[2t'-1+dt+pad.., ...] for the k=s=2 Conv3d with padding `pad`
+ *   (1 for stc_connector, 0 for stc_connector_v35); OOB taps are zero.  Then vl2_gemm_bf16 with W[C, 8C].
+ * ---------------------------------------------------------------------------------------------------------- */
+int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void* gamma, const void* beta, void* y, float* pooled,
+                          int F, int H, int W, int C, float eps, void* stream);
+int vl2_se_scale(void* y, const float* s, int F, int HW, int C, void* stream);
+int vl2_conv3d_im2col(const void* x, void* A, int T, int H, int W, int C, int pad, int To, int Ho, int Wo,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Decoder glue.
+ * vl2_rope_inplace: rotate-half RoPE on q and k heads inside a fused [S, ld] QKV buffer, positions pos0..pos0+S-1.
+ *   HF:mistral/modeling_mistral.py:51-82,262-323 (cos/sin in fp32 from inv_freq = theta^(-2i/D)).
+ * vl2_embed_splice: inputs_embeds[dst_row[i]] = table[ids[i]] for text positions (ids >= 0); visual rows are written
+ *   directly by the readout GEMM.  videollama2_arch.py:198-220.
+ * ---------------------------------------------------------------------------------------------------------- */
+int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off, int k_off, int pos0,
+                     const float* inv_freq /* fp32 [D/2], device */, void* stream);
+int vl2_embed_splice(const int64_t* ids, const int32_t* dst_row, int n, const void* table, int64_t vocab, void* out,
+                     int H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VL2_H_ */

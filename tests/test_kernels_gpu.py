@@ -1,0 +1,237 @@
+"""Kernel-level parity on the GPU: every libvl2 entry point against a plain PyTorch fp32 restatement of the same op
+(inputs bf16-rounded, math fp32).  Tolerances are written per test; integer/index work is exact."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def rnd(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+ACTS = {
+    0: lambda x: x,
+    1: lambda x: x * torch.sigmoid(1.702 * x),
+    2: torch.nn.functional.silu,
+    3: lambda x: torch.nn.functional.gelu(x),
+}
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 256, 64), (128, 128, 128), (256, 64, 192), (200, 264, 136), (1, 8, 8), (577, 1024, 1024),
+    (1776, 4096, 1024), (1521, 512, 2048), (333, 3072, 640),
+])
+def test_gemm_plain(cuda, M, N, K):
+    from videollama2_b200 import ops
+    a = rnd((M, K), cuda, seed=1)
+    w = rnd((N, K), cuda, 0.05, seed=2)
+    out = ops.gemm(a, w)
+    ref = a.float() @ w.float().t()
+    assert relerr(out, ref) < 6e-3, (M, N, K)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_gemm_epilogue(cuda, act, with_res):
+    from videollama2_b200 import ops
+    M, N, K = 300, 520, 256
+    a = rnd((M, K), cuda, seed=3)
+    w = rnd((N, K), cuda, 0.08, seed=4)
+    bias = torch.randn(N, device=cuda)
+    res = rnd((M, N), cuda, seed=5) if with_res else None
+    rs = torch.rand(M, device=cuda) + 0.5
+    out = ops.gemm(a, w, bias=bias, act=act, residual=res, row_scale=rs)
+    ref = ACTS[act]((a.float() @ w.float().t()) * rs[:, None] + bias)
+    if with_res:
+        ref = ref + res.float()
+    assert relerr(out, ref) < 6e-3
+    out32 = ops.gemm(a, w, bias=bias, act=act, residual=res, row_scale=rs, out_dtype=torch.float32)
+    assert out32.dtype == torch.float32 and relerr(out32, ref) < 2e-3
+
+
+def test_gemm_swiglu_and_strided(cuda):
+    from videollama2_b200 import ops
+    M, I, K = 260, 384, 128
+    a_full = rnd((M, K + 64), cuda, seed=6)
+    a = a_full[:, 32:32 + K]  # strided view, 64-byte aligned start
+    gate = rnd((I, K), cuda, 0.1, seed=7)
+    up = rnd((I, K), cuda, 0.1, seed=8)
+    w = torch.stack([gate, up], dim=1).reshape(2 * I, K).contiguous()
+    out = ops.gemm(a, w, act=ops.ACT_SWIGLU)
+    ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    assert out.shape == (M, I) and relerr(out, ref) < 8e-3
+
+
+def test_gemm_rejects_bad_args(cuda):
+    from videollama2_b200 import ops
+    a = rnd((16, 12), cuda)
+    w = rnd((8, 12), cuda)
+    with pytest.raises(ValueError):
+        ops.gemm(a, w)  # K % 8 != 0
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,D,causal", [
+    (2, 577, 4, 4, 64, False), (1, 128, 2, 2, 64, False), (3, 45, 2, 2, 64, False),
+    (1, 300, 4, 2, 128, True), (1, 1776, 8, 2, 128, True), (1, 128, 2, 1, 128, True), (2, 260, 2, 2, 64, True),
+])
+def test_attention(cuda, B, S, Hq, Hkv, D, causal):
+    from videollama2_b200 import ops
+    qkv = rnd((B * S, (Hq + 2 * Hkv) * D), cuda, 1.0, seed=9)
+    q = qkv[:, : Hq * D]
+    k = qkv[:, Hq * D: (Hq + Hkv) * D]
+    v = qkv[:, (Hq + Hkv) * D:]
+    scale = 1.0 / math.sqrt(D)
+    out = ops.attention(q, k, v, B=B, S=S, Hq=Hq, Hkv=Hkv, D=D, causal=causal, scale=scale)
+    qf = q.float().view(B, S, Hq, D).transpose(1, 2)
+    kf = k.float().view(B, S, Hkv, D).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    vf = v.float().view(B, S, Hkv, D).transpose(1, 2).repeat_interleave(Hq // Hkv, dim=1)
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    if causal:
+        s = s.masked_fill(torch.ones(S, S, device=cuda, dtype=torch.bool).triu(1), float("-inf"))
+    ref = (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(B * S, Hq * D)
+    assert relerr(out, ref) < 8e-3, (B, S, Hq, Hkv, D, causal)
+
+
+@pytest.mark.parametrize("rows,C", [(9232, 1024), (1521, 4096), (7, 128), (33, 3584)])
+@pytest.mark.parametrize("act,with_res", [(0, False), (2, False), (2, True)])
+def test_layernorm(cuda, rows, C, act, with_res):
+    from videollama2_b200 import ops
+    x = rnd((rows, C), cuda, 2.0, seed=10) + 0.5
+    g = rnd((C,), cuda, 0.1, seed=11) + 1.0
+    b = rnd((C,), cuda, 0.1, seed=12)
+    res = rnd((rows, C), cuda, seed=13) if with_res else None
+    y = ops.layernorm(x, g, b, 1e-5, act=act, residual=res)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5)
+    if with_res:
+        ref = ref + res.float()
+    if act == 2:
+        ref = torch.nn.functional.silu(ref)
+    assert relerr(y, ref) < 4e-3
+
+
+@pytest.mark.parametrize("rows,C", [(1776, 4096), (5, 128), (64, 3584)])
+def test_rmsnorm(cuda, rows, C):
+    from videollama2_b200 import ops
+    x = rnd((rows, C), cuda, 3.0, seed=14)
+    g = rnd((C,), cuda, 0.1, seed=15) + 1.0
+    y = ops.rmsnorm(x, g, 1e-5)
+    xf = x.float()
+    ref = g.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5))
+    assert relerr(y, ref) < 4e-3
+
+
+@pytest.mark.parametrize("F,H,P,C", [(2, 336, 14, 1024), (3, 56, 14, 64)])
+def test_patch_embed_path(cuda, F, H, P, C):
+    from videollama2_b200 import ops
+    px = rnd((F, 3, H, H), cuda, seed=16)
+    wconv = rnd((C, 3, P, P), cuda, 0.05, seed=17)
+    K = 3 * P * P
+    Kpad = (K + 63) // 64 * 64
+    A = ops.patch_im2col(px, P, Kpad)
+    ref_A = torch.nn.functional.unfold(px.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(-1, K)
+    assert torch.equal(A[:, :K].float(), ref_A) and A[:, K:].abs().max().item() == 0  # pure data movement: exact
+    wpad = torch.zeros((C, Kpad), device=cuda, dtype=torch.bfloat16)
+    wpad[:, :K] = wconv.reshape(C, K)
+    patch = ops.gemm(A, wpad)
+    ref_patch = torch.nn.functional.conv2d(px.float(), wconv.float(), stride=P).flatten(2).transpose(1, 2).reshape(-1, C)
+    assert relerr(patch, ref_patch) < 6e-3
+    np_ = (H // P) ** 2
+    cls = rnd((C,), cuda, seed=18)
+    pos = rnd((np_ + 1, C), cuda, seed=19)
+    g = rnd((C,), cuda, 0.1, seed=20) + 1
+    b = rnd((C,), cuda, 0.1, seed=21)
+    tok = ops.clip_embed_finish(patch, cls, pos, g, b, F, 1e-5)
+    emb = torch.cat([cls.float().expand(F, 1, C), patch.float().view(F, np_, C)], 1) + pos.float()
+    ref_tok = torch.nn.functional.layer_norm(emb, (C,), g.float(), b.float(), 1e-5).reshape(-1, C)
+    assert relerr(tok, ref_tok) < 4e-3
+
+
+@pytest.mark.parametrize("F,H,W,C", [(2, 24, 24, 4096), (3, 13, 13, 512), (1, 4, 5, 64)])
+def test_dwconv_ln_silu_pool_scale(cuda, F, H, W, C):
+    from videollama2_b200 import ops
+    x = rnd((F, H, W, C), cuda, seed=22)
+    wd = rnd((C, 1, 3, 3), cuda, 0.3, seed=23)
+    g = rnd((C,), cuda, 0.1, seed=24) + 1
+    b = rnd((C,), cuda, 0.1, seed=25)
+    w9c = wd.reshape(C, 9).t().contiguous()
+    y, pooled = ops.dwconv3x3_ln_silu(x, w9c, g, b, 1e-5)
+    conv = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wd.float(), padding=1, groups=C).permute(0, 2, 3, 1)
+    ref = torch.nn.functional.silu(torch.nn.functional.layer_norm(conv, (C,), g.float(), b.float(), 1e-5))
+    assert relerr(y, ref) < 5e-3
+    assert relerr(pooled, y.float().mean(dim=(1, 2))) < 1e-5  # pooling of what was written: fp32-exact up to order
+    s = torch.rand((F, C), device=cuda)
+    y2 = ops.se_scale(y.clone(), s)
+    assert relerr(y2, y.float() * s[:, None, None, :]) < 4e-3
+
+
+@pytest.mark.parametrize("pad", [1, 0])
+@pytest.mark.parametrize("T,H,W,C", [(4, 6, 6, 64), (16, 24, 24, 128), (3, 5, 7, 8)])
+def test_conv3d_path(cuda, pad, T, H, W, C):
+    from videollama2_b200 import ops
+    x = rnd((T, H, W, C), cuda, seed=26)
+    wc = rnd((C, C, 2, 2, 2), cuda, 0.1, seed=27)
+    bias = torch.randn(C, device=cuda)
+    A = ops.conv3d_im2col(x, pad)
+    wk = wc.permute(0, 2, 3, 4, 1).reshape(C, 8 * C).contiguous()
+    out = ops.gemm(A, wk, bias=bias, act=ops.ACT_SILU)
+    ref = torch.nn.functional.conv3d(x.float().permute(3, 0, 1, 2)[None], wc.float(), bias, stride=2, padding=pad)
+    ref = torch.nn.functional.silu(ref)[0].permute(1, 2, 3, 0).reshape(-1, C)
+    assert out.shape == ref.shape and relerr(out, ref) < 6e-3
+
+
+def test_skinny_gemm(cuda):
+    from videollama2_b200 import ops
+    a = torch.randn((16, 4096), device=cuda)
+    w = rnd((1024, 4096), cuda, 0.05, seed=28)
+    bias = torch.randn(1024, device=cuda)
+    for act, fn in ((ops.ACT_NONE, lambda t: t), (ops.ACT_SILU, torch.nn.functional.silu), (ops.ACT_SIGMOID, torch.sigmoid)):
+        out = ops.gemm_skinny(a, w, bias=bias, act=act)
+        assert relerr(out, fn(a @ w.float().t() + bias)) < 1e-4
+    ab = rnd((1, 4096), cuda, seed=29)
+    out = ops.gemm_skinny(ab, w, out_dtype=torch.bfloat16)
+    assert relerr(out, ab.float() @ w.float().t()) < 4e-3
+
+
+def test_rope(cuda):
+    from videollama2_b200 import ops
+    S, Hq, Hkv, D = 300, 4, 2, 128
+    qkv = rnd((S, (Hq + 2 * Hkv) * D), cuda, seed=30)
+    orig = qkv.clone()
+    inv_freq = 1.0 / (1e6 ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    ops.rope_inplace(qkv, S, Hq, Hkv, D, 0, Hq * D, 7, inv_freq.to(cuda))
+    pos = torch.arange(7, 7 + S, dtype=torch.float32)
+    fr = torch.outer(pos, inv_freq)
+    emb = torch.cat([fr, fr], -1)
+    cos, sin = emb.cos().to(cuda), emb.sin().to(cuda)
+
+    def rot(x):
+        return torch.cat([-x[..., D // 2:], x[..., : D // 2]], -1)
+
+    qk = orig[:, : (Hq + Hkv) * D].float().view(S, Hq + Hkv, D)
+    ref = qk * cos[:, None, :] + rot(qk) * sin[:, None, :]
+    assert relerr(qkv[:, : (Hq + Hkv) * D], ref.reshape(S, -1)) < 5e-3
+    assert torch.equal(qkv[:, (Hq + Hkv) * D:], orig[:, (Hq + Hkv) * D:])  # V untouched: exact
+
+
+def test_embed_splice_exact(cuda):
+    from videollama2_b200 import ops
+    V, H = 1000, 256
+    table = rnd((V, H), cuda, seed=31)
+    ids = torch.tensor([5, 999, -201, 0, 17], dtype=torch.int64, device=cuda)
+    dst = torch.tensor([0, 1, 2, 50, 51], dtype=torch.int32, device=cuda)
+    out = torch.full((52, H), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.embed_splice(ids, dst, table, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], table[5]) and torch.equal(out[1], table[999])
+    assert torch.equal(out[50], table[0]) and torch.equal(out[51], table[17])
+    assert (out[2:50] == 7.0).all()  # placeholder row and untouched rows stay as they were

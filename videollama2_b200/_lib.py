@@ -1,0 +1,91 @@
+"""ctypes binding of libvl2.so (include/vl2.h).  There is NO fallback: if the library is missing the import of any
+compute entry point raises, and on a box without an sm_100 GPU every compute call returns VL2_E_CUDA."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvl2.so")
+
+# Every symbol include/vl2.h declares (tests/test_abi.py checks the header against this list and the .so).
+SYMBOLS = [
+    "vl2_version", "vl2_last_error", "vl2_launch_count",
+    "vl2_gemm_bf16", "vl2_gemm_skinny", "vl2_attention",
+    "vl2_layernorm", "vl2_rmsnorm",
+    "vl2_patch_im2col", "vl2_clip_embed_finish",
+    "vl2_dwconv3x3_ln_silu", "vl2_se_scale", "vl2_conv3d_im2col",
+    "vl2_rope_inplace", "vl2_embed_splice",
+]
+
+ACT_NONE, ACT_QUICK_GELU, ACT_SILU, ACT_GELU_ERF, ACT_SWIGLU = 0, 1, 2, 3, 4
+ACT_SIGMOID = 100  # vl2_gemm_skinny only
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("C", C.c_void_p),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("row_scale", C.c_void_p),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ldc", C.c_int64), ("ldr", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("act", C.c_int32), ("out_f32", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+        ("B", C.c_int32), ("S", C.c_int32), ("Hq", C.c_int32), ("Hkv", C.c_int32), ("D", C.c_int32),
+        ("causal", C.c_int32), ("scale", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+class Vl2Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libvl2.so or raise.  Never falls back to another implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Vl2Error(
+            f"{LIB_PATH} is missing: build it with `python -m videollama2_b200.build` (nvcc, sm_100a). "
+            "videollama2_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.vl2_version.restype = C.c_int
+    lib.vl2_last_error.restype = C.c_char_p
+    lib.vl2_launch_count.restype = C.c_int64
+    sigs = {
+        "vl2_gemm_bf16": [C.POINTER(GemmArgs), vp],
+        "vl2_gemm_skinny": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "vl2_attention": [C.POINTER(AttnArgs), vp],
+        "vl2_layernorm": [vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
+        "vl2_rmsnorm": [vp, vp, vp, i64, i32, f32, vp],
+        "vl2_patch_im2col": [vp, vp, i32, i32, i32, i32, i32, vp],
+        "vl2_clip_embed_finish": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
+        "vl2_dwconv3x3_ln_silu": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "vl2_se_scale": [vp, vp, i32, i32, i32, vp],
+        "vl2_conv3d_im2col": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vl2_rope_inplace": [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp],
+        "vl2_embed_splice": [vp, vp, i32, vp, i64, vp, i32, vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vl2_last_error().decode(errors="replace")
+        exc = ValueError if rc in (-1, -2, -3) else (NotImplementedError if rc == -6 else Vl2Error)
+        raise exc(f"{what} failed (code {rc}): {msg}")

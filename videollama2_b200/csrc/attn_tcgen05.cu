@@ -1,0 +1,327 @@
+// FlashAttention-style fused attention for sm_100a (non-causal ViT heads and causal GQA decoder heads).
+//
+// One CTA = one 128-row query tile of one (batch, head).  192 threads:
+//   warps 0..3  softmax / output warps: thread r owns query row r (TMEM lane r) -> no cross-thread reductions
+//   warp 4      TMA producer (one lane): Q once, then K/V tiles of 128 keys into a 2-stage smem ring
+//   warp 5      TMEM allocator + MMA issuer (one lane):
+//                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
+//                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
+//                                     B = V tile as MN-major SW128 operand (no transpose pass needed)
+// Online softmax state (m, l) and the running output O live in registers of the row's thread; after each P V the
+// partial product is pulled out of TMEM and folded in:  O = O * alpha_j + Ot_j.   QK^T of tile j+1 is issued before
+// the softmax of tile j finishes, so tensor-core and MUFU work overlap.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vl2 {
+
+static constexpr int kAttnThreads = 192;
+static constexpr int BQ = 128;
+static constexpr int BKV = 128;
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kAtoms = D / 64;                 // 64-column (128-byte) swizzle atoms per row
+  static constexpr int kTileBytes = BKV * D * 2;        // one Q / K / V tile
+  static constexpr int kAtomBytes = 128 * 128;          // 128 rows x 128 B
+  static constexpr int kPBytes = BQ * BKV * 2;          // 32 KB
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = kTileBytes;              // 2 stages
+  static constexpr int kOffV = 3 * kTileBytes;          // 2 stages
+  static constexpr int kOffP = 5 * kTileBytes;
+  static constexpr int kOffBar = kOffP + kPBytes;
+  static constexpr int kSmemUsed = kOffBar + 256;
+  // at least 116 KB so that only one CTA is resident per SM (each CTA allocates all 512 TMEM columns)
+  static constexpr int kSmemBytes = (kSmemUsed + 1024 > 116 * 1024) ? (kSmemUsed + 1024) : 116 * 1024;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
+};
+
+struct AttnParams {
+  void* out;
+  int64_t ldo;
+  int S, Hq, group;  // group = Hq / Hkv
+  int causal;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + Cfg::kOffQ;
+  uint8_t* sK = smem + Cfg::kOffK;
+  uint8_t* sV = smem + Cfg::kOffV;
+  uint8_t* sP = smem + Cfg::kOffP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* v_full = bars + 3;    // [2]
+  uint64_t* kv_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;    // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // heavy (late) causal tiles first
+  const int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int kvh = head / p.group;
+  const int q0 = qt * BQ;
+  const int n_kv = p.causal ? (qt + 1) : (p.S + BKV - 1) / BKV;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
+#pragma unroll
+      for (int a = 0; a < Cfg::kAtoms; ++a)
+        tma_load_3d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, head * D + a * 64, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_3d(sK + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[st], kvh * D + a * 64, j * BKV, b);
+        mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_3d(sV + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[st], kvh * D + a * 64, j * BKV, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
+        const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32;
+          umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + off, 16, 1024), umma_desc_sw128(k_addr + off, 16, 1024),
+                       idesc_qk, kk != 0);
+        }
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
+          // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
+          const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
+          umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, kk != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    // ===================== softmax / output warps (thread == query row) =====================
+    const int r = warp * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float O[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) O[i] = 0.f;
+
+    auto fold_output = [&](int j_done, float alpha) {
+      mbar_wait(o_full, j_done & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_sel + Cfg::kColO + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) O[c * 32 + i] = fmaf(O[c * 32 + i], alpha, __uint_as_float(v[i]));
+      }
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0);
+      const int kv0 = j * BKV;
+      const bool need_mask = (kv0 + BKV > p.S) || (p.causal && (kv0 + BKV - 1 > q0));
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after_sync();
+      // pass 1: row maximum (log2 domain)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_taddr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (need_mask) {
+            const int kvi = kv0 + c * 32 + i;
+            if (kvi >= p.S || (p.causal && kvi > qi)) s = -INFINITY;
+          }
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      // rows past the end of the sequence in a causal launch can be fully masked: keep them finite
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m - m_use);
+      // fold the previous tile's P V (this also guarantees the P buffer is free again)
+      if (j > 0) fold_output(j - 1, alpha_prev);
+      // pass 2: probabilities -> smem (bf16, K-major SW128 A operand), row sum
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_taddr + c * 32, v);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (need_mask) {
+            const int kvi = kv0 + c * 32 + i;
+            if (kvi >= p.S || (p.causal && kvi > qi)) s = -INFINITY;
+          }
+          pr[i] = exp2f(fmaf(s, p.scale_log2, -m_use));
+          rs += pr[i];
+        }
+        // 32 columns = 4 chunks of 16 B inside atom (c >> 1), chunk index (c & 1) * 4 + g
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = (c & 1) * 4 + g;
+          uint8_t* dst = sP + (c >> 1) * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
+                         pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
+        }
+      }
+      l = l * alpha + rs;
+      m = m_use;
+      alpha_prev = alpha;
+      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(p_full);
+    }
+    fold_output(n_kv - 1, alpha_prev);
+    if (qi < p.S) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
+#pragma unroll
+      for (int g = 0; g < D / 8; ++g) {
+        *reinterpret_cast<uint4*>(orow + g * 8) =
+            make_uint4(pack_bf16(O[g * 8 + 0] * inv, O[g * 8 + 1] * inv), pack_bf16(O[g * 8 + 2] * inv, O[g * 8 + 3] * inv),
+                       pack_bf16(O[g * 8 + 4] * inv, O[g * 8 + 5] * inv), pack_bf16(O[g * 8 + 6] * inv, O[g * 8 + 7] * inv));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int D>
+static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    uint64_t dims[3] = {(uint64_t)a->Hq * D, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->ldq * 2, (uint64_t)a->ldq * 2 * a->S};
+    int rc = make_tmap_bf16(&tq, a->q, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->Hkv * D, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->ldk * 2, (uint64_t)a->ldk * 2 * a->S};
+    int rc = make_tmap_bf16(&tk, a->k, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)a->Hkv * D, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->ldv * 2, (uint64_t)a->ldv * 2 * a->S};
+    int rc = make_tmap_bf16(&tv, a->v, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.out = a->out; p.ldo = a->ldo; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((a->S + BQ - 1) / BQ, a->Hq, a->B);
+  attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  VL2_CHECK_LAUNCH("attn_fwd_kernel");
+  return VL2_OK;
+}
+
+}  // namespace vl2
+
+extern "C" int vl2_attention(const vl2_attn_args* a, void* stream) {
+  using namespace vl2;
+  VL2_REQUIRE(a != nullptr, VL2_E_BADSHAPE, "vl2_attention: null args");
+  VL2_REQUIRE(a->B > 0 && a->S > 0 && a->Hq > 0 && a->Hkv > 0 && a->Hq % a->Hkv == 0, VL2_E_BADSHAPE,
+              "vl2_attention: bad B/S/heads (%d,%d,%d,%d)", a->B, a->S, a->Hq, a->Hkv);
+  VL2_REQUIRE(a->D == 64 || a->D == 128, VL2_E_UNSUPPORTED, "vl2_attention: head_dim %d unsupported (64 or 128)", a->D);
+  VL2_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, VL2_E_BADALIGN,
+              "vl2_attention: row strides must be multiples of 8 elements");
+  VL2_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out), VL2_E_BADALIGN,
+              "vl2_attention: pointers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->D == 64) return launch_attn<64>(a, st);
+  return launch_attn<128>(a, st);
+}

@@ -1,0 +1,323 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,Nout] = epi(A[M,K] * W[N,K]^T).
+//
+//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
+//   warp 1      MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, accumulators in TMEM
+//   warp 2      TMEM allocator (2 x BN fp32 columns: the epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 4..7  epilogue: tcgen05.ld (thread == accumulator row) -> row_scale/bias/activation/residual -> global
+//
+// Tiles are 128 x BN (BN in {64,128,256}), BLOCK_K = 64 bf16 = one 128-byte swizzle atom; the grid is persistent
+// (<= #SMs CTAs, static round-robin over tiles, M fastest so that a wave shares W tiles through L2).
+// M/N/K tails: TMA zero-fills out-of-bounds reads, stores are predicated.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vl2 {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int kGemmThreads = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = BM * BK * 2;
+  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: all powers of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  void* C;
+  const float* bias;
+  const void* residual;
+  const float* row_scale;
+  int64_t ldc, ldr;
+  int M, N, K;
+  int act;
+  int out_f32;
+  int num_m_tiles, num_n_tiles;
+};
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case VL2_ACT_QUICK_GELU: return x / (1.f + __expf(-1.702f * x));
+    case VL2_ACT_SILU: return x / (1.f + __expf(-x));
+    case VL2_ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    default: return x;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                        // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;    // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]        epilogue -> MMA
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_k_blocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_tiles) * BM;
+        const int n0 = (tile / p.num_m_tiles) * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue drained this accumulator stage
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kStageBytesA);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = ew * 32 + lane;
+    const bool swiglu = (p.act == VL2_ACT_SWIGLU);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile % p.num_m_tiles) * BM;
+      const int n0 = (tile / p.num_m_tiles) * BN;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
+      const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * rs;
+        const int ncols = min(32, p.N - col0);  // multiple of 8
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g * 4 < ncols) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
+              x[g * 4 + 0] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
+            }
+          }
+        }
+        if (swiglu) {
+          // columns interleave (gate, up): 32 accumulator columns -> 16 outputs
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + (col0 >> 1);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g * 16 < ncols) {
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float g0 = x[g * 16 + 4 * j + 0], u0 = x[g * 16 + 4 * j + 1];
+                const float g1 = x[g * 16 + 4 * j + 2], u1 = x[g * 16 + 4 * j + 3];
+                o[j] = pack_bf16(g0 / (1.f + __expf(-g0)) * u0, g1 / (1.f + __expf(-g1)) * u1);
+              }
+              *reinterpret_cast<uint4*>(crow + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          continue;
+        }
+        if (p.act != VL2_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], p.act);
+        }
+        if (p.residual != nullptr) {
+          const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (int64_t)row * p.ldr + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 < ncols) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rrow + g * 8);
+              x[g * 8 + 0] += bf16_lo(r.x); x[g * 8 + 1] += bf16_hi(r.x);
+              x[g * 8 + 2] += bf16_lo(r.y); x[g * 8 + 3] += bf16_hi(r.y);
+              x[g * 8 + 4] += bf16_lo(r.z); x[g * 8 + 5] += bf16_hi(r.z);
+              x[g * 8 + 6] += bf16_lo(r.w); x[g * 8 + 7] += bf16_hi(r.w);
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* crow = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g * 4 < ncols)
+              *reinterpret_cast<float4*>(crow + g * 4) = make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+        } else {
+          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g * 8 < ncols)
+              *reinterpret_cast<uint4*>(crow + g * 8) =
+                  make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
+                             pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+        }
+      }
+      // all tcgen05.ld of this thread have completed (wait::ld above) -> hand the accumulator stage back
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    uint64_t str[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&ta, a->A, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->ldw * 2};
+    uint32_t box[2] = {BK, BN};
+    int rc = make_tmap_bf16(&tb, a->W, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
+  p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
+  p.num_m_tiles = (a->M + BM - 1) / BM;
+  p.num_n_tiles = (a->N + BN - 1) / BN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
+  return VL2_OK;
+}
+
+}  // namespace vl2
+
+extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
+  using namespace vl2;
+  VL2_REQUIRE(a != nullptr, VL2_E_BADSHAPE, "vl2_gemm_bf16: null args");
+  VL2_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, VL2_E_BADSHAPE, "vl2_gemm_bf16: M,N,K must be positive (%d,%d,%d)",
+              a->M, a->N, a->K);
+  VL2_REQUIRE(a->K % 8 == 0 && a->N % 8 == 0, VL2_E_BADSHAPE, "vl2_gemm_bf16: K and N must be multiples of 8 (%d,%d)",
+              a->K, a->N);
+  VL2_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldc % 8 == 0 && (a->residual == nullptr || a->ldr % 8 == 0),
+              VL2_E_BADALIGN, "vl2_gemm_bf16: leading dimensions must be multiples of 8 elements");
+  VL2_REQUIRE(a->lda >= a->K && a->ldw >= a->K, VL2_E_BADSHAPE, "vl2_gemm_bf16: lda/ldw smaller than K");
+  VL2_REQUIRE(aligned16(a->A) && aligned16(a->W) && aligned16(a->C) && aligned16(a->residual) && aligned16(a->bias),
+              VL2_E_BADALIGN, "vl2_gemm_bf16: pointers must be 16-byte aligned");
+  VL2_REQUIRE(a->act >= VL2_ACT_NONE && a->act <= VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: unknown act %d",
+              a->act);
+  if (a->act == VL2_ACT_SWIGLU) {
+    VL2_REQUIRE(a->residual == nullptr && !a->out_f32 && a->N % 16 == 0, VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Tile-width choice: fewest (waves x tile width); ties go to the wider tile (less A re-streaming).
+  const int sms = sm_count();
+  const int mt = (a->M + BM - 1) / BM;
+  int best_bn = 256;
+  long best_cost = -1;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && a->N <= bn / 2) continue;
+    const long tiles = (long)mt * ((a->N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const long cost = waves * (bn + 24);  // +24: per-tile fixed overhead (pipeline fill / epilogue tail)
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+  }
+  switch (best_bn) {
+    case 256: return launch_gemm<256>(a, st);
+    case 128: return launch_gemm<128>(a, st);
+    default: return launch_gemm<64>(a, st);
+  }
+}

@@ -1,0 +1,596 @@
+// HBM-bound row kernels: LayerNorm(+SiLU,+residual), RMSNorm, CLIP embedding assembly, depthwise 3x3 + LN + SiLU
+// (+ SE pooling), SE scaling, im2col front-ends, RoPE, embedding gather.  bf16 storage, fp32 math, 16-byte accesses.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace vl2 {
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+// Block-wide sum of two floats (blockDim.x multiple of 32, <= 1024).  `red` is 64 floats of shared memory.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();  // protect `red` against the previous use
+  if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
+  __syncthreads();
+  float ra = (lane < nw) ? red[lane] : 0.f;
+  float rb = (lane < nw) ? red[32 + lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ra += __shfl_xor_sync(0xffffffffu, ra, o);
+    rb += __shfl_xor_sync(0xffffffffu, rb, o);
+  }
+  return make_float2(ra, rb);
+}
+
+static inline int row_threads(int C) {
+  int t = (C / 8 + 31) / 32 * 32;
+  if (t > 512) t = 512;
+  if (t < 32) t = 32;
+  return t;
+}
+static constexpr int kMaxVec = 4;  // vectors of 8 channels held per thread => C <= 512*8*4 = 16384
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm (+ residual, + SiLU), one CTA per row.  Two-pass (mean, then centred variance) in registers.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                 const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
+                                 __nv_bfloat16* __restrict__ y, int C, float eps, int act) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  float v[kMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      unpack8(xr[vi], v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = block_sum2(s, 0.f, red).x / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  const uint4* br = reinterpret_cast<const uint4*>(beta);
+  const uint4* rr = residual ? reinterpret_cast<const uint4*>(residual + row * C) : nullptr;
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(__ldg(gr + vi), g);
+      unpack8(__ldg(br + vi), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      if (rr) {
+        float r[8];
+        unpack8(rr[vi], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      if (act == VL2_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = silu(o[j]);
+      }
+      yr[vi] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RMSNorm with HF rounding order: y = gamma * bf16(x * rstd).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                               __nv_bfloat16* __restrict__ y, int C, float eps) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  float v[kMaxVec][8];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      unpack8(xr[vi], v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += v[i][j] * v[i][j];
+    }
+  }
+  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      float g[8], o[8];
+      unpack8(__ldg(gr + vi), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * __bfloat162float(__float2bfloat16_rn(v[i][j] * rstd));
+      yr[vi] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CLIP embeddings: tok[f,0] = cls + pos[0]; tok[f,1+p] = patch[f,p] + pos[1+p]; then pre_layrnorm.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void clip_embed_finish_kernel(const __nv_bfloat16* __restrict__ patch, const __nv_bfloat16* __restrict__ cls,
+                                         const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ gamma,
+                                         const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ tok, int np,
+                                         int C, float eps) {
+  __shared__ float red[64];
+  const int t = blockIdx.x % (np + 1);
+  const int f = blockIdx.x / (np + 1);
+  const int nvec = C / 8;
+  const uint4* src = (t == 0) ? reinterpret_cast<const uint4*>(cls)
+                              : reinterpret_cast<const uint4*>(patch + ((int64_t)f * np + (t - 1)) * C);
+  const uint4* pr = reinterpret_cast<const uint4*>(pos + (int64_t)t * C);
+  float v[kMaxVec][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      float a[8], b[8];
+      unpack8(src[vi], a);
+      unpack8(__ldg(pr + vi), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] = a[j] + b[j];
+        s += v[i][j];
+      }
+    }
+  }
+  const float mean = block_sum2(s, 0.f, red).x / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  const uint4* br = reinterpret_cast<const uint4*>(beta);
+  uint4* yr = reinterpret_cast<uint4*>(tok + (int64_t)blockIdx.x * C);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = threadIdx.x + i * blockDim.x;
+    if (vi < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(__ldg(gr + vi), g);
+      unpack8(__ldg(br + vi), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
+      yr[vi] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Patch im2col: pixels [F,3,H,W] -> A [F*(H/P)*(W/P), Kpad]; column = c*P*P + i*P + j.  One thread per bf16 pair.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void patch_im2col_kernel(const __nv_bfloat16* __restrict__ px, __nv_bfloat16* __restrict__ A, int F, int H,
+                                    int W, int P, int Kpad) {
+  const int gw = W / P, gh = H / P;
+  const int K = 3 * P * P;
+  const int64_t total = (int64_t)F * gh * gw * (Kpad / 2);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % (Kpad / 2)) * 2;
+    const int64_t row = idx / (Kpad / 2);
+    uint32_t out = 0;
+    if (col < K) {
+      const int pw = (int)(row % gw), ph = (int)((row / gw) % gh), f = (int)(row / ((int64_t)gw * gh));
+      const int c = col / (P * P), r = col % (P * P), i = r / P, j = r % P;
+      const __nv_bfloat16* s = px + (((int64_t)f * 3 + c) * H + (ph * P + i)) * W + pw * P + j;
+      if (j + 1 < P) {
+        out = *reinterpret_cast<const uint32_t*>(s);  // P even, j even => 4-byte aligned, same image row
+      } else {
+        out = (uint32_t)__bfloat16_as_ushort(s[0]);
+        // odd P: the pair straddles kernel rows / channels
+        const int col1 = col + 1;
+        if (col1 < K) {
+          const int c1 = col1 / (P * P), r1 = col1 % (P * P), i1 = r1 / P, j1 = r1 % P;
+          out |= (uint32_t)__bfloat16_as_ushort(px[(((int64_t)f * 3 + c1) * H + (ph * P + i1)) * W + pw * P + j1]) << 16;
+        }
+      }
+    }
+    *reinterpret_cast<uint32_t*>(A + row * Kpad + col) = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Depthwise 3x3 (zero pad 1, per frame) + LayerNorm over C + SiLU, channels-last.  One CTA per (frame, image row);
+// the 3x3 window slides along W in registers (3 new 16-byte loads per pixel per thread); per-(f,h) channel sums of the
+// output go to `pool_partial[f, h, C]` (deterministic SE pooling: reduced by se_pool_reduce_kernel).
+// Thread t owns channels [8t, 8t+8) => C <= 8 * blockDim.x.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w9c,
+                         const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                         __nv_bfloat16* __restrict__ y, float* __restrict__ pool_partial, int H, int W, int C,
+                         float eps) {
+  __shared__ float red[64];
+  const int h = blockIdx.x % H;
+  const int f = blockIdx.x / H;
+  const int c0 = threadIdx.x * 8;
+  const bool active = c0 < C;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  uint4 wt[9];  // packed bf16 (register budget: 512 threads x <=128 regs)
+  uint4 gp = zero4, bp = zero4;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wt[k] = active ? __ldg(reinterpret_cast<const uint4*>(w9c + (int64_t)k * C + c0)) : zero4;
+  if (active) {
+    gp = __ldg(reinterpret_cast<const uint4*>(gamma + c0));
+    bp = __ldg(reinterpret_cast<const uint4*>(beta + c0));
+  }
+  const __nv_bfloat16* xf = x + (int64_t)f * H * W * C;
+  auto load_col = [&](int wcol, uint4 (&col)[3]) {
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hh = h + dh - 1;
+      if (active && hh >= 0 && hh < H && wcol >= 0 && wcol < W)
+        col[dh] = *reinterpret_cast<const uint4*>(xf + ((int64_t)hh * W + wcol) * C + c0);
+      else
+        col[dh] = zero4;
+    }
+  };
+  uint4 win[3][3];  // [dw][dh], packed bf16
+  load_col(-1, win[0]);
+  load_col(0, win[1]);
+  float pool[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pool[j] = 0.f;
+  for (int wc = 0; wc < W; ++wc) {
+    load_col(wc + 1, win[2]);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dw = 0; dw < 3; ++dw) {
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        float xv[8], wv[8];
+        unpack8(win[dw][dh], xv);
+        unpack8(wt[dh * 3 + dw], wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wv[j], acc[j]);
+      }
+    }
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += acc[j];  // inactive threads hold zeros
+    const float mean = block_sum2(s, 0.f, red).x / (float)C;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = acc[j] - mean; q += d * d; }
+    }
+    const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
+    if (active) {
+      float o[8], g[8], b[8];
+      unpack8(gp, g);
+      unpack8(bp, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = silu((acc[j] - mean) * rstd * g[j] + b[j]);
+      const uint4 packed = pack8(o);
+      *reinterpret_cast<uint4*>(y + (((int64_t)f * H + h) * W + wc) * C + c0) = packed;
+      float r[8];
+      unpack8(packed, r);  // pool what the next op will actually read (bf16-rounded)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pool[j] += r[j];
+    }
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) { win[0][dh] = win[1][dh]; win[1][dh] = win[2][dh]; }
+  }
+  if (active && pool_partial != nullptr) {
+    float* pp = pool_partial + ((int64_t)f * H + h) * C + c0;
+    *reinterpret_cast<float4*>(pp) = make_float4(pool[0], pool[1], pool[2], pool[3]);
+    *reinterpret_cast<float4*>(pp + 4) = make_float4(pool[4], pool[5], pool[6], pool[7]);
+  }
+}
+
+// pooled[f,c] = (sum_h partial[f,h,c]) / (H*W)
+__global__ void se_pool_reduce_kernel(const float* __restrict__ partial, float* __restrict__ pooled, int H, int C,
+                                      float inv_hw) {
+  const int f = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) s += partial[((int64_t)f * H + h) * C + c];
+  pooled[(int64_t)f * C + c] = s * inv_hw;
+}
+
+__global__ void se_scale_kernel(__nv_bfloat16* __restrict__ y, const float* __restrict__ s, int HW, int C,
+                                int64_t total_vec) {
+  const int cv = C / 8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total_vec;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % cv) * 8;
+    const int64_t pix = idx / cv;
+    const int f = (int)(pix / HW);
+    uint4* p = reinterpret_cast<uint4*>(y) + idx;
+    float v[8];
+    unpack8(*p, v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (int64_t)f * C + c0));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (int64_t)f * C + c0 + 4));
+    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+    v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    *p = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Conv3d (k = s = 2) im2col, channels-last: A[(to,ho,wo), tap*C + c] = x[2to-pad+dt, 2ho-pad+dh, 2wo-pad+dw, c].
+// ---------------------------------------------------------------------------------------------------------
+__global__ void conv3d_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int T, int H,
+                                     int W, int C, int pad, int To, int Ho, int Wo) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)To * Ho * Wo * 8 * cv;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(idx % cv) * 8;
+    const int tap = (int)((idx / cv) % 8);
+    const int64_t row = idx / ((int64_t)cv * 8);
+    const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho), to = (int)(row / ((int64_t)Wo * Ho));
+    const int dt = tap >> 2, dh = (tap >> 1) & 1, dw = tap & 1;
+    const int t = 2 * to - pad + dt, hh = 2 * ho - pad + dh, ww = 2 * wo - pad + dw;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t >= 0 && t < T && hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = *reinterpret_cast<const uint4*>(x + (((int64_t)t * H + hh) * W + ww) * C + c0);
+    *reinterpret_cast<uint4*>(A + row * (8 * (int64_t)C) + (int64_t)tap * C + c0) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RoPE (rotate-half pairing i <-> i + D/2) applied in place to the q and k heads of a fused QKV buffer.
+// One thread per (token, i); loops over heads.  cos/sin from fp32 inv_freq (HF computes them in fp32).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off,
+                            int k_off, int pos0, const float* __restrict__ inv_freq) {
+  const int half = D / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * half) return;
+  const int i = idx % half, s = idx / half;
+  float sn, cs;
+  sincosf((float)(pos0 + s) * inv_freq[i], &sn, &cs);
+  // HF casts cos/sin to the activation dtype before use
+  cs = __bfloat162float(__float2bfloat16_rn(cs));
+  sn = __bfloat162float(__float2bfloat16_rn(sn));
+  __nv_bfloat16* row = qkv + (int64_t)s * ld;
+  for (int h = 0; h < Hq + Hkv; ++h) {
+    __nv_bfloat16* p = row + (h < Hq ? q_off + h * D : k_off + (h - Hq) * D);
+    const float a = __bfloat162float(p[i]), b = __bfloat162float(p[i + half]);
+    p[i] = __float2bfloat16_rn(a * cs - b * sn);
+    p[i + half] = __float2bfloat16_rn(b * cs + a * sn);
+  }
+}
+
+// out[dst_row[i], :] = table[ids[i], :]
+__global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ dst_row,
+                                    const __nv_bfloat16* __restrict__ table, int64_t vocab,
+                                    __nv_bfloat16* __restrict__ out, int H) {
+  const int i = blockIdx.x;
+  int64_t id = ids[i];
+  if (id < 0 || id >= vocab) return;  // modal placeholder or invalid id: row is written by the connector
+  const uint4* src = reinterpret_cast<const uint4*>(table + id * H);
+  uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)dst_row[i] * H);
+  for (int v = threadIdx.x; v < H / 8; v += blockDim.x) dst[v] = __ldg(src + v);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Skinny GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias), M <= 32.  One warp per output column n; W streams once from
+// HBM (16-byte loads), A (tiny) is re-read from L1/L2.
+// ---------------------------------------------------------------------------------------------------------
+template <bool A_F32>
+__global__ void gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt,
+                                   const float* __restrict__ bias, void* __restrict__ Cv, int out_f32, int M, int N,
+                                   int K, int act) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const int n = warp;
+  const uint4* wr = reinterpret_cast<const uint4*>(Wt + (int64_t)n * K);
+  const int kv = K / 8;
+  for (int m0 = 0; m0 < M; m0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int v = lane; v < kv; v += 32) {
+      float w[8];
+      unpack8(__ldg(wr + v), w);
+#pragma unroll
+      for (int mm = 0; mm < 4; ++mm) {
+        if (m0 + mm < M) {
+          float a[8];
+          if (A_F32) {
+            const float* ar = reinterpret_cast<const float*>(Av) + (int64_t)(m0 + mm) * K + v * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(ar), a1 = *reinterpret_cast<const float4*>(ar + 4);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+          } else {
+            unpack8(*(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + (int64_t)(m0 + mm) * K) + v), a);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[mm] = fmaf(a[j], w[j], acc[mm]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mm = 0; mm < 4; ++mm) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[mm] += __shfl_xor_sync(0xffffffffu, acc[mm], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int mm = 0; mm < 4; ++mm) {
+        if (m0 + mm < M) {
+          float r = acc[mm] + (bias ? bias[n] : 0.f);
+          if (act == VL2_ACT_SILU) r = silu(r);
+          else if (act == 100) r = 1.f / (1.f + __expf(-r));
+          if (out_f32) reinterpret_cast<float*>(Cv)[(int64_t)(m0 + mm) * N + n] = r;
+          else reinterpret_cast<__nv_bfloat16*>(Cv)[(int64_t)(m0 + mm) * N + n] = __float2bfloat16_rn(r);
+        }
+      }
+    }
+  }
+}
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks = 148 * 16) {
+  int64_t b = (work_items + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace vl2
+
+using namespace vl2;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta, const void* residual, void* y,
+                             int64_t rows, int C, float eps, int act, void* stream) {
+  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE,
+              "vl2_layernorm: rows=%lld C=%d unsupported (C %% 8 == 0, C <= 16384)", (long long)rows, C);
+  VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU, VL2_E_UNSUPPORTED, "vl2_layernorm: act %d unsupported", act);
+  VL2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(residual), VL2_E_BADALIGN,
+              "vl2_layernorm: pointers must be 16-byte aligned");
+  layernorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (const bf16*)residual, (bf16*)y, C, eps, act);
+  VL2_CHECK_LAUNCH("layernorm_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t rows, int C, float eps, void* stream) {
+  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE,
+              "vl2_rmsnorm: rows=%lld C=%d unsupported", (long long)rows, C);
+  VL2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma), VL2_E_BADALIGN, "vl2_rmsnorm: 16-byte alignment");
+  rmsnorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma,
+                                                                            (bf16*)y, C, eps);
+  VL2_CHECK_LAUNCH("rmsnorm_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_patch_im2col(const void* pixels, void* A, int F, int H, int W, int P, int Kpad, void* stream) {
+  VL2_REQUIRE(F > 0 && P > 0 && H % P == 0 && W % P == 0, VL2_E_BADSHAPE, "vl2_patch_im2col: H,W must be multiples of P");
+  VL2_REQUIRE(Kpad % 8 == 0 && Kpad >= 3 * P * P && W % 2 == 0, VL2_E_BADSHAPE,
+              "vl2_patch_im2col: Kpad %% 8 == 0, Kpad >= 3*P*P and even W required");
+  const int64_t total = (int64_t)F * (H / P) * (W / P) * (Kpad / 2);
+  patch_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)pixels, (bf16*)A, F, H, W, P,
+                                                                             Kpad);
+  VL2_CHECK_LAUNCH("patch_im2col_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_clip_embed_finish(const void* patch, const void* cls, const void* pos, const void* gamma,
+                                     const void* beta, void* tok, int F, int np, int C, float eps, void* stream) {
+  VL2_REQUIRE(F > 0 && np > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE, "vl2_clip_embed_finish: bad shape");
+  VL2_REQUIRE(aligned16(patch) && aligned16(cls) && aligned16(pos) && aligned16(tok), VL2_E_BADALIGN,
+              "vl2_clip_embed_finish: 16-byte alignment");
+  clip_embed_finish_kernel<<<(unsigned)(F * (np + 1)), row_threads(C), 0, (cudaStream_t)stream>>>(
+      (const bf16*)patch, (const bf16*)cls, (const bf16*)pos, (const bf16*)gamma, (const bf16*)beta, (bf16*)tok, np, C,
+      eps);
+  VL2_CHECK_LAUNCH("clip_embed_finish_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void* gamma, const void* beta, void* y,
+                                     float* pooled, int F, int H, int W, int C, float eps, void* stream) {
+  VL2_REQUIRE(F > 0 && H > 0 && W > 0 && C % 8 == 0 && C <= 8 * 512, VL2_E_BADSHAPE,
+              "vl2_dwconv3x3_ln_silu: C %% 8 == 0 and C <= 4096 required (C=%d)", C);
+  VL2_REQUIRE(aligned16(x) && aligned16(w9c) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(pooled),
+              VL2_E_BADALIGN, "vl2_dwconv3x3_ln_silu: 16-byte alignment");
+  // `pooled` layout: [F*C] pooled means followed by [F*H*C] per-row partial sums (workspace); see vl2.h.
+  int threads = (C / 8 + 31) / 32 * 32;
+  float* partial = pooled ? pooled + (int64_t)F * C : nullptr;
+  dwconv3x3_ln_silu_kernel<<<(unsigned)(F * H), threads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)w9c, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, partial, H, W, C, eps);
+  VL2_CHECK_LAUNCH("dwconv3x3_ln_silu_kernel");
+  if (pooled) {
+    dim3 grid((C + 255) / 256, F);
+    se_pool_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, pooled, H, C, 1.f / (float)(H * W));
+    VL2_CHECK_LAUNCH("se_pool_reduce_kernel");
+  }
+  return VL2_OK;
+}
+
+extern "C" int vl2_se_scale(void* y, const float* s, int F, int HW, int C, void* stream) {
+  VL2_REQUIRE(F > 0 && HW > 0 && C % 8 == 0, VL2_E_BADSHAPE, "vl2_se_scale: bad shape");
+  const int64_t total = (int64_t)F * HW * (C / 8);
+  se_scale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)y, s, HW, C, total);
+  VL2_CHECK_LAUNCH("se_scale_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_conv3d_im2col(const void* x, void* A, int T, int H, int W, int C, int pad, int To, int Ho, int Wo,
+                                 void* stream) {
+  VL2_REQUIRE(T > 0 && H > 0 && W > 0 && C % 8 == 0 && To > 0 && Ho > 0 && Wo > 0 && (pad == 0 || pad == 1),
+              VL2_E_BADSHAPE, "vl2_conv3d_im2col: bad shape");
+  const int64_t total = (int64_t)To * Ho * Wo * 8 * (C / 8);
+  conv3d_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)A, T, H, W, C, pad,
+                                                                              To, Ho, Wo);
+  VL2_CHECK_LAUNCH("conv3d_im2col_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off, int k_off, int pos0,
+                                const float* inv_freq, void* stream) {
+  VL2_REQUIRE(S > 0 && D % 2 == 0 && Hq > 0 && Hkv >= 0 && inv_freq != nullptr, VL2_E_BADSHAPE, "vl2_rope_inplace: bad shape");
+  const int total = S * (D / 2);
+  rope_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>((bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
+                                                                    inv_freq);
+  VL2_CHECK_LAUNCH("rope_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_embed_splice(const int64_t* ids, const int32_t* dst_row, int n, const void* table, int64_t vocab,
+                                void* out, int H, void* stream) {
+  VL2_REQUIRE(n > 0 && H % 8 == 0, VL2_E_BADSHAPE, "vl2_embed_splice: bad shape");
+  embed_splice_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(ids, dst_row, (const bf16*)table, vocab, (bf16*)out, H);
+  VL2_CHECK_LAUNCH("embed_splice_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, void* C, int out_f32, int M,
+                               int N, int K, int act, void* stream) {
+  VL2_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 8 == 0, VL2_E_BADSHAPE,
+              "vl2_gemm_skinny: need 0 < M <= 32 and K %% 8 == 0 (M=%d K=%d)", M, K);
+  VL2_REQUIRE(aligned16(A) && aligned16(W), VL2_E_BADALIGN, "vl2_gemm_skinny: 16-byte alignment");
+  VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU || act == 100, VL2_E_UNSUPPORTED, "vl2_gemm_skinny: act %d", act);
+  const int threads = 256;
+  const int blocks = (N * 32 + threads - 1) / threads;
+  if (a_f32)
+    gemm_skinny_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act);
+  else
+    gemm_skinny_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act);
+  VL2_CHECK_LAUNCH("gemm_skinny_kernel");
+  return VL2_OK;
+}

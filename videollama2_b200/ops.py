@@ -1,0 +1,220 @@
+"""torch-tensor front end of the C-ABI (include/vl2.h).  Every function enqueues libvl2 kernels on the current CUDA
+stream and returns the output tensor; nothing here computes with torch ops (torch only owns memory and streams)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_SIGMOID, ACT_SILU, ACT_SWIGLU, AttnArgs, GemmArgs,
+                   check)
+
+__all__ = [
+    "gemm", "gemm_skinny", "attention", "layernorm", "rmsnorm", "patch_im2col", "clip_embed_finish",
+    "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
+    "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_SWIGLU", "ACT_SIGMOID",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.Vl2Error("videollama2_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def _bf16(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and t.dtype != torch.bfloat16:
+            raise TypeError(f"expected bfloat16 tensor, got {t.dtype}")
+
+
+def launch_count() -> int:
+    return int(_lib.load().vl2_launch_count())
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous)."""
+    _need_cuda(a, w, bias, residual, row_scale, out)
+    _bf16(a, w, residual)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1, "gemm: 2-D, unit inner stride"
+    M, K = a.shape
+    N, Kw = w.shape
+    if K != Kw:
+        raise ValueError(f"gemm: K mismatch {K} vs {Kw}")
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    if residual is not None:
+        assert residual.shape == (M, n_out) and residual.stride(1) == 1
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.numel() == M and row_scale.is_contiguous()
+    args = GemmArgs(A=a.data_ptr(), W=w.data_ptr(), C=out.data_ptr(), bias=_ptr(bias), residual=_ptr(residual),
+                    row_scale=_ptr(row_scale), lda=a.stride(0), ldw=w.stride(0), ldc=out.stride(0),
+                    ldr=residual.stride(0) if residual is not None else 0, M=M, N=N, K=K, act=act,
+                    out_f32=1 if out.dtype == torch.float32 else 0, reserved=0)
+    if out.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("gemm: out must be bf16 or fp32")
+    check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
+    return out
+
+
+def gemm_skinny(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    _need_cuda(a, w, bias)
+    _bf16(w)
+    assert a.is_contiguous() and w.is_contiguous() and a.dim() == 2 and w.dim() == 2
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    assert a.dtype in (torch.float32, torch.bfloat16)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    check(_lib.load().vl2_gemm_skinny(a.data_ptr(), 1 if a.dtype == torch.float32 else 0, w.data_ptr(), _ptr(bias),
+                                      out.data_ptr(), 1 if out_dtype == torch.float32 else 0, M, N, K, act, _stream()),
+          "vl2_gemm_skinny")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, S: int, Hq: int, Hkv: int, D: int,
+              causal: bool, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v: 2-D row-strided views [B*S, H*D] (e.g. column slices of a fused QKV buffer)."""
+    _need_cuda(q, k, v, out)
+    _bf16(q, k, v)
+    for t, h in ((q, Hq), (k, Hkv), (v, Hkv)):
+        assert t.dim() == 2 and t.shape == (B * S, h * D) and t.stride(1) == 1
+    if out is None:
+        out = torch.empty((B * S, Hq * D), device=q.device, dtype=torch.bfloat16)
+    args = AttnArgs(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(), ldq=q.stride(0),
+                    ldk=k.stride(0), ldv=v.stride(0), ldo=out.stride(0), B=B, S=S, Hq=Hq, Hkv=Hkv, D=D,
+                    causal=1 if causal else 0, scale=float(scale), reserved=0)
+    check(_lib.load().vl2_attention(C.byref(args), _stream()), "vl2_attention")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, act: int = ACT_NONE,
+              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, gamma, beta, residual, out)
+    _bf16(x, gamma, beta, residual)
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    if out is None:
+        out = torch.empty_like(x)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == x.shape
+    check(_lib.load().vl2_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(residual), out.data_ptr(),
+                                    rows, Cc, float(eps), act, _stream()), "vl2_layernorm")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, gamma, out)
+    _bf16(x, gamma)
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().vl2_rmsnorm(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), x.numel() // Cc, Cc, float(eps),
+                                  _stream()), "vl2_rmsnorm")
+    return out
+
+
+def patch_im2col(pixels: torch.Tensor, P: int, Kpad: int) -> torch.Tensor:
+    _need_cuda(pixels)
+    _bf16(pixels)
+    assert pixels.is_contiguous() and pixels.dim() == 4 and pixels.shape[1] == 3
+    F, _, H, W = pixels.shape
+    out = torch.empty((F * (H // P) * (W // P), Kpad), device=pixels.device, dtype=torch.bfloat16)
+    check(_lib.load().vl2_patch_im2col(pixels.data_ptr(), out.data_ptr(), F, H, W, P, Kpad, _stream()),
+          "vl2_patch_im2col")
+    return out
+
+
+def clip_embed_finish(patch: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, gamma: torch.Tensor,
+                      beta: torch.Tensor, F: int, eps: float) -> torch.Tensor:
+    _need_cuda(patch, cls, pos, gamma, beta)
+    _bf16(patch, cls, pos, gamma, beta)
+    assert patch.is_contiguous() and pos.is_contiguous()
+    Cc = patch.shape[-1]
+    np_ = patch.shape[0] // F
+    assert pos.shape == (np_ + 1, Cc)
+    out = torch.empty((F * (np_ + 1), Cc), device=patch.device, dtype=torch.bfloat16)
+    check(_lib.load().vl2_clip_embed_finish(patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), gamma.data_ptr(),
+                                            beta.data_ptr(), out.data_ptr(), F, np_, Cc, float(eps), _stream()),
+          "vl2_clip_embed_finish")
+    return out
+
+
+def dwconv3x3_ln_silu(x: torch.Tensor, w9c: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                      with_pool: bool = True):
+    """x: [F,H,W,C] channels-last bf16.  Returns (y, pooled[F,C] fp32 or None)."""
+    _need_cuda(x, w9c, gamma, beta)
+    _bf16(x, w9c, gamma, beta)
+    assert x.is_contiguous() and x.dim() == 4 and w9c.is_contiguous() and w9c.shape == (9, x.shape[-1])
+    F, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    pool = torch.empty((F * Cc + F * H * Cc,), device=x.device, dtype=torch.float32) if with_pool else None
+    check(_lib.load().vl2_dwconv3x3_ln_silu(x.data_ptr(), w9c.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                            y.data_ptr(), _ptr(pool), F, H, W, Cc, float(eps), _stream()),
+          "vl2_dwconv3x3_ln_silu")
+    return y, (pool[: F * Cc].view(F, Cc) if with_pool else None)
+
+
+def se_scale(y: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """In place: y[f, :, :, c] *= s[f, c]."""
+    _need_cuda(y, s)
+    _bf16(y)
+    assert y.is_contiguous() and s.dtype == torch.float32 and s.is_contiguous()
+    F, Cc = s.shape
+    HW = y.numel() // (F * Cc)
+    check(_lib.load().vl2_se_scale(y.data_ptr(), s.data_ptr(), F, HW, Cc, _stream()), "vl2_se_scale")
+    return y
+
+
+def conv3d_im2col(x: torch.Tensor, pad: int) -> torch.Tensor:
+    """x: [T,H,W,C] -> A [(To*Ho*Wo), 8*C] for the k=s=2 Conv3d with padding `pad`."""
+    _need_cuda(x)
+    _bf16(x)
+    assert x.is_contiguous() and x.dim() == 4
+    T, H, W, Cc = x.shape
+    To, Ho, Wo = (T + 2 * pad - 2) // 2 + 1, (H + 2 * pad - 2) // 2 + 1, (W + 2 * pad - 2) // 2 + 1
+    out = torch.empty((To * Ho * Wo, 8 * Cc), device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().vl2_conv3d_im2col(x.data_ptr(), out.data_ptr(), T, H, W, Cc, pad, To, Ho, Wo, _stream()),
+          "vl2_conv3d_im2col")
+    return out
+
+
+def rope_inplace(qkv: torch.Tensor, S: int, Hq: int, Hkv: int, D: int, q_off: int, k_off: int, pos0: int,
+                 inv_freq: torch.Tensor) -> torch.Tensor:
+    _need_cuda(qkv, inv_freq)
+    _bf16(qkv)
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and inv_freq.dtype == torch.float32 and inv_freq.numel() == D // 2
+    check(_lib.load().vl2_rope_inplace(qkv.data_ptr(), qkv.stride(0), S, Hq, Hkv, D, q_off, k_off, pos0,
+                                       inv_freq.data_ptr(), _stream()), "vl2_rope_inplace")
+    return qkv
+
+
+def embed_splice(ids: torch.Tensor, dst_row: torch.Tensor, table: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _need_cuda(ids, dst_row, table, out)
+    _bf16(table, out)
+    assert ids.dtype == torch.int64 and dst_row.dtype == torch.int32 and ids.numel() == dst_row.numel()
+    assert table.is_contiguous() and out.is_contiguous() and table.shape[1] == out.shape[1]
+    check(_lib.load().vl2_embed_splice(ids.data_ptr(), dst_row.data_ptr(), ids.numel(), table.data_ptr(),
+                                       table.shape[0], out.data_ptr(), out.shape[1], _stream()), "vl2_embed_splice")
+    return out
