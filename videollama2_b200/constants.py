@@ -1,0 +1,18 @@
+"""Model constants of the reference (videollama2/constants.py:4-32) that the hot path needs."""
+IGNORE_INDEX = -100
+
+IMAGE_TOKEN_INDEX = -200
+DEFAULT_IMAGE_TOKEN = "<image>"
+VIDEO_TOKEN_INDEX = -201
+DEFAULT_VIDEO_TOKEN = "<video>"
+AUDIO_TOKEN_INDEX = -202
+DEFAULT_AUDIO_TOKEN = "<audio>"
+
+NUM_FRAMES = 8
+MAX_FRAMES = 32
+
+MODAL_INDEX_MAP = {
+    "<image>": -200,
+    "<video>": -201,
+    "<audio>": -202,
+}

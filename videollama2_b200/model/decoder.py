@@ -1,0 +1,94 @@
+"""Mistral-7B / Qwen2 decoder prefill (+ greedy decode) on libvl2 kernels.
+
+Arithmetic of HF MistralModel / Qwen2Model (HF:mistral/modeling_mistral.py:35-48,51-82,122-239,262-470;
+HF:qwen2/modeling_qwen2.py:187-246): RMSNorm -> fused QKV GEMM (+bias for Qwen2) -> RoPE -> causal GQA flash attention
+-> o_proj(+residual) -> RMSNorm -> gate/up GEMM with SwiGLU epilogue -> down_proj(+residual) -> norm -> lm_head.
+Weights are repacked once: q/k/v concatenated, gate/up rows interleaved so SwiGLU happens inside the GEMM tile."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops
+
+
+class DecoderEngine:
+    def __init__(self, config):
+        self.config = config
+        self.H = config.hidden_size
+        self.Hq = config.num_attention_heads
+        self.Hkv = config.num_key_value_heads
+        self.D = config.hidden_size // config.num_attention_heads
+        self.I = config.intermediate_size
+        self.eps = config.rms_norm_eps
+        self.layers: List[Dict[str, torch.Tensor]] = []
+        self.w: Dict[str, torch.Tensor] = {}
+        self.is_loaded = False
+        self.kv: List[torch.Tensor] = []   # per layer [S_max, (Hq+2Hkv)*D] fused qkv rows (K,V columns = cache)
+        self.kv_len = 0
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], device) -> "DecoderEngine":
+        dev = torch.device(device)
+        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        self.layers = []
+        for i in range(self.config.num_hidden_layers):
+            p = f"model.layers.{i}."
+            names = ("q_proj", "k_proj", "v_proj")
+            L = {
+                "g1": bf(sd[p + "input_layernorm.weight"]), "g2": bf(sd[p + "post_attention_layernorm.weight"]),
+                "wqkv": bf(torch.cat([sd[p + f"self_attn.{n}.weight"] for n in names], 0)),
+                "wo": bf(sd[p + "self_attn.o_proj.weight"]),
+                "wgu": bf(torch.stack([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], 1).reshape(2 * self.I, self.H)),
+                "wd": bf(sd[p + "mlp.down_proj.weight"]),
+            }
+            if p + "self_attn.q_proj.bias" in sd:
+                L["bqkv"] = f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in names], 0))
+            self.layers.append(L)
+        self.w = {"embed": bf(sd["model.embed_tokens.weight"]), "norm": bf(sd["model.norm.weight"]),
+                  "lm_head": bf(sd["lm_head.weight"])}
+        inv = 1.0 / (self.config.rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))
+        self.w["inv_freq"] = inv.to(dev)
+        self.device = dev
+        self.is_loaded = True
+        return self
+
+    @property
+    def embed_tokens(self) -> torch.Tensor:
+        return self.w["embed"]
+
+    # ---- prefill ---------------------------------------------------------------------------------------------
+    def _layer(self, L, x: torch.Tensor, S: int, pos0: int, qkv_out: Optional[torch.Tensor]) -> torch.Tensor:
+        Hq, Hkv, D = self.Hq, self.Hkv, self.D
+        y = ops.rmsnorm(x, L["g1"], self.eps)
+        qkv = ops.gemm(y, L["wqkv"], bias=L.get("bqkv"), out=qkv_out)
+        ops.rope_inplace(qkv, S, Hq, Hkv, D, 0, Hq * D, pos0, self.w["inv_freq"])
+        o = ops.attention(qkv[:, : Hq * D], qkv[:, Hq * D: (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], B=1, S=S, Hq=Hq,
+                          Hkv=Hkv, D=D, causal=True, scale=D ** -0.5)
+        x = ops.gemm(o, L["wo"], residual=x)
+        y = ops.rmsnorm(x, L["g2"], self.eps)
+        h = ops.gemm(y, L["wgu"], act=ops.ACT_SWIGLU)
+        return ops.gemm(h, L["wd"], residual=x)
+
+    def prefill(self, embeds: torch.Tensor, all_logits: bool = False, keep_cache: bool = False,
+                max_len: Optional[int] = None):
+        """embeds [S,H] bf16 -> (logits fp32 [S,V] or [1,V], final hidden [S,H])."""
+        if not self.is_loaded:
+            raise RuntimeError("DecoderEngine: weights not loaded")
+        S = embeds.shape[0]
+        x = embeds
+        if keep_cache:
+            cap = max_len or S
+            width = (self.Hq + 2 * self.Hkv) * self.D
+            self.kv = [torch.empty((cap, width), device=x.device, dtype=torch.bfloat16) for _ in self.layers]
+            self.kv_len = S
+        for i, L in enumerate(self.layers):
+            x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None)
+        if all_logits:
+            hn = ops.rmsnorm(x, self.w["norm"], self.eps)
+            logits = ops.gemm(hn, self.w["lm_head"], out_dtype=torch.float32)
+        else:
+            hn = ops.rmsnorm(x[S - 1:].contiguous(), self.w["norm"], self.eps)
+            logits = ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
+        return logits, x

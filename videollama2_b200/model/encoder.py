@@ -1,0 +1,167 @@
+"""CLIP ViT tower on libvl2 kernels — same class surface as the reference's CLIPVisionTower
+(videollama2/model/encoder.py:12-81), arithmetic of HF CLIPVisionModel (HF:clip/modeling_clip.py:202-218,282-385,647-696).
+
+Only the layers that feed `hidden_states[select_layer]` are executed (select_layer = -2 -> 23 of 24; the reference runs
+the 24th layer and post_layernorm and throws the result away)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops
+from .config import VisionConfig
+
+_PFX = "vision_tower.vision_model."
+
+
+class _ImageProcessorInfo:
+    """Carries the fields of CLIPImageProcessor the callers read (crop/size/mean/std); preprocessing itself is CPU I/O."""
+
+    def __init__(self, size: int):
+        self.crop_size = {"height": size, "width": size}
+        self.size = {"shortest_edge": size}
+        self.image_mean = [0.48145466, 0.4578275, 0.40821073]
+        self.image_std = [0.26862954, 0.26130258, 0.27577711]
+
+
+class CLIPVisionTower:
+    def __init__(self, vision_tower: str, args, vision_config: Optional[VisionConfig] = None, load_pretrained=False):
+        self.is_loaded = False
+        self.vision_tower_name = vision_tower
+        self.select_layer = args.mm_vision_select_layer
+        self.select_feature = getattr(args, "mm_vision_select_feature", "patch")
+        if self.select_feature not in ("patch", "cls_patch"):
+            raise ValueError(f"Unexpected select feature: {self.select_feature}")
+        if vision_config is None:
+            vision_config = getattr(args, "vision_config", None) or VisionConfig.from_dir(vision_tower)
+        self._config = vision_config
+        self.image_processor = _ImageProcessorInfo(vision_config.image_size)
+        self._device = torch.device("cpu")
+        self.w: Dict[str, torch.Tensor] = {}
+        self.layers: List[Dict[str, torch.Tensor]] = []
+
+    # ---- weights -------------------------------------------------------------------------------------------
+    @property
+    def n_used_layers(self) -> int:
+        L = self._config.num_hidden_layers
+        n = L + 1 + self.select_layer if self.select_layer < 0 else self.select_layer
+        if not 0 <= n <= L:
+            raise ValueError(f"select_layer {self.select_layer} out of range for {L} layers")
+        return n
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], device, prefix: str = _PFX) -> "CLIPVisionTower":
+        """Repack HF-named CLIP weights once: fused QKV [3C,C], fp32 biases, patch conv as [C, Kpad] GEMM weight."""
+        c = self._config
+        dev = torch.device(device)
+        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        K = 3 * c.patch_size * c.patch_size
+        self.kpad = (K + 63) // 64 * 64
+        wp = torch.zeros((c.hidden_size, self.kpad), dtype=torch.bfloat16, device=dev)
+        wp[:, :K] = bf(sd[prefix + "embeddings.patch_embedding.weight"]).reshape(c.hidden_size, K)
+        self.w = {
+            "patch": wp,
+            "cls": bf(sd[prefix + "embeddings.class_embedding"]),
+            "pos": bf(sd[prefix + "embeddings.position_embedding.weight"]),
+            "pre_g": bf(sd[prefix + "pre_layrnorm.weight"]), "pre_b": bf(sd[prefix + "pre_layrnorm.bias"]),
+        }
+        self.layers = []
+        for i in range(self.n_used_layers):
+            p = f"{prefix}encoder.layers.{i}."
+            self.layers.append({
+                "ln1_g": bf(sd[p + "layer_norm1.weight"]), "ln1_b": bf(sd[p + "layer_norm1.bias"]),
+                "ln2_g": bf(sd[p + "layer_norm2.weight"]), "ln2_b": bf(sd[p + "layer_norm2.bias"]),
+                "wqkv": bf(torch.cat([sd[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
+                "bqkv": f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
+                "wo": bf(sd[p + "self_attn.out_proj.weight"]), "bo": f32(sd[p + "self_attn.out_proj.bias"]),
+                "w1": bf(sd[p + "mlp.fc1.weight"]), "b1": f32(sd[p + "mlp.fc1.bias"]),
+                "w2": bf(sd[p + "mlp.fc2.weight"]), "b2": f32(sd[p + "mlp.fc2.bias"]),
+            })
+        self._device = dev
+        self.is_loaded = True
+        return self
+
+    # ---- forward -------------------------------------------------------------------------------------------
+    def hidden_states(self, images: torch.Tensor) -> torch.Tensor:
+        """[F,3,H,W] bf16 -> residual stream after the selected layer, [F, np+1, C]."""
+        c = self._config
+        Fn = images.shape[0]
+        C = c.hidden_size
+        H = c.num_attention_heads
+        D = C // H
+        S = self.num_patches + 1
+        A = ops.patch_im2col(images.contiguous(), c.patch_size, self.kpad)
+        patch = ops.gemm(A, self.w["patch"])
+        x = ops.clip_embed_finish(patch, self.w["cls"], self.w["pos"], self.w["pre_g"], self.w["pre_b"], Fn,
+                                  c.layer_norm_eps)
+        for L in self.layers:
+            y = ops.layernorm(x, L["ln1_g"], L["ln1_b"], c.layer_norm_eps)
+            qkv = ops.gemm(y, L["wqkv"], bias=L["bqkv"])
+            o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B=Fn, S=S, Hq=H, Hkv=H, D=D, causal=False,
+                              scale=D ** -0.5)
+            x = ops.gemm(o, L["wo"], bias=L["bo"], residual=x)
+            y = ops.layernorm(x, L["ln2_g"], L["ln2_b"], c.layer_norm_eps)
+            h = ops.gemm(y, L["w1"], bias=L["b1"], act=ops.ACT_QUICK_GELU)
+            x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x)
+        return x.view(Fn, S, C)
+
+    def feature_select(self, hidden: torch.Tensor) -> torch.Tensor:
+        if self.select_feature == "patch":
+            return hidden[:, 1:]
+        return hidden
+
+    @torch.no_grad()
+    def forward(self, images):
+        if not self.is_loaded:
+            raise RuntimeError("CLIPVisionTower: weights not loaded")
+        if type(images) is list:
+            return [self.forward(im.unsqueeze(0)) for im in images]
+        if not images.is_cuda:
+            raise ops._lib.Vl2Error("CLIPVisionTower needs CUDA tensors (no CPU fallback)")
+        dt = images.dtype
+        feats = self.feature_select(self.hidden_states(images.to(torch.bfloat16))).contiguous()
+        return feats.to(dt)
+
+    __call__ = forward
+
+    # ---- properties of the reference class (encoder.py:55-81) -----------------------------------------------
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def config(self):
+        return self._config
+
+    @property
+    def hidden_size(self):
+        return self._config.hidden_size
+
+    @property
+    def num_patches(self):
+        return (self._config.image_size // self._config.patch_size) ** 2
+
+    @property
+    def num_patches_per_side(self):
+        return self._config.image_size // self._config.patch_size
+
+    @property
+    def image_size(self):
+        return self._config.image_size
+
+
+def build_vision_tower(vision_tower_cfg, **kwargs):
+    """encoder.py:154-164: only CLIP towers are implemented on this path (SigLIP is a later row)."""
+    vision_tower = getattr(vision_tower_cfg, "mm_vision_tower", getattr(vision_tower_cfg, "vision_tower", None))
+    if vision_tower is None:
+        raise ValueError("Unknown vision tower: None")
+    if "clip" in vision_tower.lower() or getattr(vision_tower_cfg, "vision_config", None) is not None:
+        return CLIPVisionTower(vision_tower, args=vision_tower_cfg, **kwargs)
+    if "siglip" in vision_tower.lower():
+        raise NotImplementedError("SiglipVisionTower is not implemented in the B200 engine yet")
+    raise ValueError(f"Unknown vision tower: {vision_tower}")

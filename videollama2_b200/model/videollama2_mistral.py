@@ -1,0 +1,153 @@
+"""Videollama2MistralForCausalLM with the reference's call surface (videollama2/model/videollama2_mistral.py:47-153),
+backed by the B200 engine instead of HF MistralForCausalLM."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops
+from .config import Videollama2Config
+from .videollama2_arch import Videollama2MetaForCausalLM, Videollama2MetaModel
+
+
+class Videollama2MistralConfig(Videollama2Config):
+    model_type = "videollama2_mistral"
+
+
+class CausalLMOutput(SimpleNamespace):
+    """Field-compatible with transformers' CausalLMOutputWithPast for what callers read (.logits, .loss, .labels)."""
+
+    def __getitem__(self, i):
+        return (self.loss, self.logits)[i] if self.loss is not None else (self.logits,)[i]
+
+
+class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
+    config_class = Videollama2MistralConfig
+
+    def __init__(self, config, **kwargs):
+        self.config = config
+        self.model = Videollama2MetaModel(config)
+        self.vocab_size = config.vocab_size
+        self._device = torch.device("cpu")
+
+    # ---- construction -----------------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, config, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        """Build from HF-named weights (the reference's checkpoint format) and repack for the kernels."""
+        self = cls(config)
+        self.load_state_dict(state_dict, device)
+        return self
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], device="cuda"):
+        dev = torch.device(device)
+        m = self.model
+        m.decoder.load_state_dict(sd, dev)
+        if m.vision_tower is not None:
+            m.vision_tower.load_state_dict(sd, dev, prefix="model.vision_tower.vision_tower.vision_model.")
+            m.mm_projector.load_state_dict(sd, dev, prefix="model.mm_projector.")
+        self._device = dev
+        return self
+
+    def get_model(self):
+        return self.model
+
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    def eval(self):
+        return self
+
+    # ---- forward (videollama2_mistral.py:63-108) -----------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, images=None,
+                return_dict=None, **kwargs):
+        if output_attentions:
+            raise NotImplementedError("output_attentions is not supported by the fused attention kernel")
+        if past_key_values is not None:
+            raise NotImplementedError("forward() with past_key_values is not supported; use generate()")
+        new_len = None
+        if inputs_embeds is None:
+            input_ids, attention_mask, past_key_values, inputs_embeds, labels = \
+                self.prepare_inputs_labels_for_multimodal(input_ids, attention_mask, past_key_values, labels, images)
+            if inputs_embeds is None:   # text-only early-out (arch.py:166-169)
+                inputs_embeds = self.get_model().embed_tokens(input_ids)
+            else:
+                new_len = self._last_new_len
+        if inputs_embeds.dim() == 2:
+            inputs_embeds = inputs_embeds.unsqueeze(0)
+        B, S, _ = inputs_embeds.shape
+        dec = self.get_model().decoder
+        logits = torch.zeros((B, S, self.vocab_size), device=inputs_embeds.device, dtype=torch.float32)
+        hidden = [] if output_hidden_states else None
+        for b in range(B):
+            n = S if new_len is None else new_len[b]
+            if attention_mask is not None and new_len is None:
+                n = int(attention_mask[b].sum().item())            # right padding only (reference convention)
+            lg, hx = dec.prefill(inputs_embeds[b, :n].to(torch.bfloat16).contiguous(), all_logits=True)
+            logits[b, :n] = lg
+            if hidden is not None:
+                hidden.append(hx)
+        loss = None
+        if labels is not None:
+            shift_logits = logits[:, :-1].reshape(-1, self.vocab_size)
+            shift_labels = labels[:, 1:].reshape(-1).to(shift_logits.device)
+            loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=-100)
+        out = CausalLMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden, attentions=None)
+        out.labels = labels
+        return out
+
+    __call__ = forward
+
+    # ---- generate (videollama2_mistral.py:110-144) -----------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, inputs=None, images=None, **kwargs):
+        """Greedy decoding; returns only the NEW token ids (as HF generate does with inputs_embeds)."""
+        kwargs.pop("position_ids", None)
+        attention_mask = kwargs.pop("attention_mask", None)
+        if "inputs_embeds" in kwargs:
+            raise NotImplementedError("`inputs_embeds` is not supported")
+        if kwargs.get("do_sample", False) and kwargs.get("temperature", 0.0) not in (0, 0.0, None):
+            raise NotImplementedError("sampling is not implemented in the B200 engine; use do_sample=False")
+        if inputs.shape[0] != 1:
+            raise NotImplementedError("generate supports batch size 1 (as the reference's inference scripts)")
+        max_new = int(kwargs.get("max_new_tokens", 20))
+        eos = kwargs.get("eos_token_id", getattr(self.config, "eos_token_id", None))
+        eos_ids = set(eos if isinstance(eos, (list, tuple)) else [eos]) if eos is not None else set()
+        stopping = kwargs.get("stopping_criteria") or []
+        if images is not None:
+            _, attention_mask, _, inputs_embeds, _ = self.prepare_inputs_labels_for_multimodal(
+                input_ids=inputs, attention_mask=attention_mask, past_key_values=None, labels=None, images=images)
+            if inputs_embeds is None:
+                inputs_embeds = self.get_model().embed_tokens(inputs)
+        else:
+            inputs_embeds = self.get_model().embed_tokens(inputs)
+        dec = self.get_model().decoder
+        x = inputs_embeds[0].to(torch.bfloat16).contiguous()
+        new_ids: List[int] = []
+        # Round-1 decode: every step re-runs the prefill kernels on the grown sequence (exact, O(n^2));
+        # the KV-cache single-token path is the next row of the scope table.
+        for _ in range(max_new):
+            logits, _ = dec.prefill(x, all_logits=False)
+            tok = int(torch.argmax(logits[0]).item())
+            new_ids.append(tok)
+            out_ids = torch.tensor([new_ids], dtype=torch.long)
+            if tok in eos_ids or any(sc(out_ids, None) for sc in stopping):
+                break
+            x = torch.cat([x, self.get_model().embed_tokens(torch.tensor([tok]))], 0)
+        return torch.tensor([new_ids], dtype=torch.long, device=self.device)
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        images = kwargs.pop("images", None)
+        _inputs = {"input_ids": input_ids, "past_key_values": past_key_values, "inputs_embeds": inputs_embeds}
+        _inputs.update(kwargs)
+        if images is not None:
+            _inputs["images"] = images
+        return _inputs

@@ -1,0 +1,91 @@
+"""Frame-parallel vision stage: the ViT treats frames as batch (videollama2_arch.py:130-131), so one video's frames are
+sharded over the ranks of a node, encoded independently, and exchanged with ONE all-gather of visual tokens
+(NCCL over NVLink 5 / NVSwitch) before the first op that mixes time (the connector's Conv3d, projector.py:208).
+The reference has no such path (its multi-GPU inference is one process per GPU over dataset chunks,
+scripts/eval/eval_video_mcqa_mvbench.sh:8-34); this is the exchange step BASELINE.json's north_star names.
+
+Host logic is backend-agnostic (tests run it with gloo, world_size 2, on CPU tensors)."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def frame_shard(num_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [start, end) of frames for `rank`; sizes differ by at most one (first ranks take the remainder)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, rem = divmod(num_frames, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(num_frames: int, world: int) -> List[int]:
+    return [frame_shard(num_frames, r, world)[1] - frame_shard(num_frames, r, world)[0] for r in range(world)]
+
+
+def all_gather_frames(local: torch.Tensor, num_frames: int, group=None) -> torch.Tensor:
+    """local [f_r, n, C] on each rank -> [num_frames, n, C] on every rank, frame order preserved."""
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(num_frames, world)
+    rank = dist.get_rank(group)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} frames, expected {sizes[rank]}")
+    out = torch.empty((num_frames,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if len(set(sizes)) == 1 and sizes[0] > 0:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # ragged: pad every shard to the largest one, gather, then compact
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    buf = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    pos = 0
+    for r, n in enumerate(sizes):
+        out[pos:pos + n] = buf[r * mx: r * mx + n]
+        pos += n
+    return out
+
+
+def encode_frames_sharded(tower, frames: torch.Tensor, group=None) -> torch.Tensor:
+    """frames [F,3,H,W] (identical on every rank) -> [F, n, C] on every rank: local ViT on this rank's shard + all-gather."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    a, b = frame_shard(frames.shape[0], rank, world)
+    if b > a:
+        local = tower(frames[a:b])
+    else:
+        n = tower.num_patches
+        local = torch.empty((0, n, tower.hidden_size), dtype=frames.dtype, device=frames.device)
+    return all_gather_frames(local, frames.shape[0], group)
+
+
+def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev, iters: int = 5) -> dict:
+    """Device-timed (CUDA events, max over ranks) ViT(shard) + all-gather for one 16-frame video."""
+    tower = model.get_vision_tower()
+    F = px_dev.shape[0]
+    for _ in range(2):
+        encode_frames_sharded(tower, px_dev)
+    times = []
+    for _ in range(iters):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a, b = frame_shard(F, rank, world)
+        e0.record()
+        local = tower(px_dev[a:b])
+        e1.record()
+        all_gather_frames(local, F)
+        e2.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1), e1.elapsed_time(e2)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(t.tolist())
+    times.sort(key=lambda x: x[0])
+    tot, vit, gat = times[len(times) // 2]
+    return {"ranks": world, "frames_per_rank": shard_sizes(F, world), "vit_shard_plus_gather_ms": tot, "vit_shard_ms": vit,
+            "all_gather_ms": gat, "frames_per_s": F / (tot * 1e-3),
+            "gather_bytes": int(F * tower.num_patches * tower.hidden_size * 2)}
