@@ -100,7 +100,7 @@ def cpu_reference_sample(steps: int = 1, warmup: int = 0):
     px, _ = synth.inputs(cfg)
     v, l = cfg.vision, cfg.llm
     sd = dict(synth.iter_state(synth.vision_specs(v)))
-    n_frames = 2
+    n_frames = 1
 
     def t_of(fn, reps):
         ts = []
@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -232,6 +234,13 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    if args.profile_one_step:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -1,0 +1,39 @@
+"""Host logic of the frame-parallel vision stage on CPU: world_size 2, gloo (the N>1 path of bench.py / parallel.py)."""
+import os
+import socket
+
+import pytest
+import subprocess
+import sys
+
+
+def test_frame_shard_partition():
+    from videollama2_b200.parallel import frame_shard, shard_sizes
+    for F in (1, 2, 7, 16, 32):
+        for W in (1, 2, 3, 4, 8):
+            spans = [frame_shard(F, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == F
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            sizes = shard_sizes(F, W)
+            assert sum(sizes) == F and max(sizes) - min(sizes) <= 1
+    assert [frame_shard(16, r, 8) for r in range(8)] == [(2 * r, 2 * r + 2) for r in range(8)]
+    with pytest.raises(ValueError):
+        frame_shard(4, 2, 2)
+
+
+@pytest.mark.parametrize("F", [16, 7, 1])
+def test_all_gather_frames_world2(F):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_gloo_worker.py")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, worker, str(F)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=150)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "RANK0 OK" in outs[0] and "RANK1 OK" in outs[1]

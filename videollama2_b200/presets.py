@@ -54,6 +54,7 @@ def state_dict_specs(cfg: Videollama2Config):
               (p + "mlp.fc1.weight", (Iv, C), "w"), (p + "mlp.fc1.bias", (Iv,), "bias"),
               (p + "mlp.fc2.weight", (C, Iv), "w"), (p + "mlp.fc2.bias", (C,), "bias"),
               (p + "layer_norm2.weight", (C,), "gain"), (p + "layer_norm2.bias", (C,), "bias")]
+    s += [(vp + "post_layernorm.weight", (C,), "gain"), (vp + "post_layernorm.bias", (C,), "bias")]
     pp = "model.mm_projector."
     for stage, first_in in (("s1", C), ("s2", H)):
         for b in range(1, 5):
