@@ -70,7 +70,7 @@ typedef struct vl2_gemm_args {
   int32_t M, N, K;
   int32_t act;
   int32_t out_f32;
-  int32_t reserved;
+  int32_t reserved; /* 0 = choose the N tile width by the library's cost model; 64..256 (step 32) forces it (tests) */
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 

@@ -40,6 +40,20 @@ def test_gemm_plain(cuda, M, N, K):
     assert relerr(out, ref) < 6e-3, (M, N, K)
 
 
+@pytest.mark.parametrize("bn", [64, 96, 128, 160, 192, 224, 256])
+def test_gemm_every_tile_width(cuda, bn):
+    """Each instantiated tile width, multi-tile persistent loop (tiles > SMs for the narrow ones), M/N/K tails."""
+    from videollama2_b200 import ops
+    M, N, K = 1100, 2072, 328
+    a = rnd((M, K), cuda, seed=40)
+    w = rnd((N, K), cuda, 0.06, seed=41)
+    bias = torch.randn(N, device=cuda)
+    res = rnd((M, N), cuda, seed=42)
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_SILU, residual=res, bn=bn)
+    ref = torch.nn.functional.silu(a.float() @ w.float().t() + bias) + res.float()
+    assert relerr(out, ref) < 6e-3, bn
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_gemm_epilogue(cuda, act, with_res):

@@ -7,9 +7,9 @@
 //                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
 //                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
 //                                     B = V tile as MN-major SW128 operand (no transpose pass needed)
-// Online softmax state (m, l) and the running output O live in registers of the row's thread; after each P V the
-// partial product is pulled out of TMEM and folded in:  O = O * alpha_j + Ot_j.   QK^T of tile j+1 is issued before
-// the softmax of tile j finishes, so tensor-core and MUFU work overlap.
+// Online softmax state (m, l) lives in registers of the row's thread; O accumulates in TMEM over all key tiles and is
+// rescaled in place only when a row maximum grows by more than 2^8 (lazy rescale).  S is read from TMEM once per tile.
+// QK^T of tile j+1 is issued before the softmax of tile j finishes, so tensor-core and MUFU work overlap.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -156,7 +156,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
           // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
           const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
-          umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, kk != 0);
+          umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
@@ -164,26 +164,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     // ===================== softmax / output warps (thread == query row) =====================
+    // One TMEM pass over S per tile; O accumulates in TMEM across tiles (tcgen05.mma accumulate) and is rescaled
+    // in place only when a row maximum grows by more than 2^8 (lazy rescale: probabilities stay <= 256, exact after
+    // the final division by l).
     const int r = warp * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float O[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) O[i] = 0.f;
-
-    auto fold_output = [&](int j_done, float alpha) {
-      mbar_wait(o_full, j_done & 1);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_sel + Cfg::kColO + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) O[c * 32 + i] = fmaf(O[c * 32 + i], alpha, __uint_as_float(v[i]));
-      }
-    };
+    const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO;
+    float m = -INFINITY, l = 0.f;
+    constexpr float kRescaleThreshold = 8.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
@@ -192,47 +181,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool need_mask = (kv0 + BKV > p.S) || (p.causal && (kv0 + BKV - 1 > q0));
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after_sync();
-      // pass 1: row maximum (log2 domain)
-      float mx = -INFINITY;
+      uint32_t sv[4][32];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_taddr + c * 32, v);
-        tmem_ld_wait();
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
+      tmem_ld_wait();
+      if (need_mask) {  // warp-uniform; predicated selects, no per-element branches
+        const int lim = p.causal ? min(p.S - 1, qi) : (p.S - 1);   // last visible key index for this row
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (need_mask) {
-            const int kvi = kv0 + c * 32 + i;
-            if (kvi >= p.S || (p.causal && kvi > qi)) s = -INFINITY;
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            sv[c][i] = (kv0 + c * 32 + i <= lim) ? sv[c][i] : 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      // reference maximum for this tile: keep the old one unless it is too stale
+      float m_use = m, alpha = 1.f;
+      const bool grow = (m_tile > m + kRescaleThreshold) || (m == -INFINITY);
+      if (grow) {
+        m_use = (m_tile == -INFINITY) ? 0.f : m_tile;   // fully masked rows stay finite
+        alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
+      }
+      // the previous P V must be complete before P (smem) is overwritten or O (TMEM) is rescaled
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after_sync();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(o_taddr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32(o_taddr + c * 32, ov);
           }
-          mx = fmaxf(mx, s);
+          tmem_st_wait();
         }
       }
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      // rows past the end of the sequence in a causal launch can be fully masked: keep them finite
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m - m_use);
-      // fold the previous tile's P V (this also guarantees the P buffer is free again)
-      if (j > 0) fold_output(j - 1, alpha_prev);
-      // pass 2: probabilities -> smem (bf16, K-major SW128 A operand), row sum
-      float rs = 0.f;
+      // probabilities -> smem (bf16, K-major SW128 A operand), row sum
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_taddr + c * 32, v);
-        tmem_ld_wait();
+      for (int c = 0; c < 4; ++c) {
         float pr[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (need_mask) {
-            const int kvi = kv0 + c * 32 + i;
-            if (kvi >= p.S || (p.causal && kvi > qi)) s = -INFINITY;
-          }
-          pr[i] = exp2f(fmaf(s, p.scale_log2, -m_use));
-          rs += pr[i];
-        }
+        for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { rs0 += pr[i]; rs1 += pr[i + 1]; rs2 += pr[i + 2]; rs3 += pr[i + 3]; }
         // 32 columns = 4 chunks of 16 B inside atom (c >> 1), chunk index (c & 1) * 4 + g
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -243,23 +245,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                          pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
         }
       }
-      l = l * alpha + rs;
+      l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
-      alpha_prev = alpha;
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(p_full);
     }
-    fold_output(n_kv - 1, alpha_prev);
-    if (qi < p.S) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after_sync();
+    const float inv = 1.f / l;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
 #pragma unroll
-      for (int g = 0; g < D / 8; ++g) {
-        *reinterpret_cast<uint4*>(orow + g * 8) =
-            make_uint4(pack_bf16(O[g * 8 + 0] * inv, O[g * 8 + 1] * inv), pack_bf16(O[g * 8 + 2] * inv, O[g * 8 + 3] * inv),
-                       pack_bf16(O[g * 8 + 4] * inv, O[g * 8 + 5] * inv), pack_bf16(O[g * 8 + 6] * inv, O[g * 8 + 7] * inv));
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32(o_taddr + c * 32, ov);
+      tmem_ld_wait();
+      if (qi < p.S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(
+              pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv),
+              pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv),
+              pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv),
+              pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv));
+        }
       }
     }
   }

@@ -3,9 +3,12 @@
 //   warp 0      TMA producer   (one lane): cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
 //   warp 1      MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, accumulators in TMEM
 //   warp 2      TMEM allocator (2 x BN fp32 columns: the epilogue of tile i overlaps the main loop of tile i+1)
-//   warps 4..7  epilogue: tcgen05.ld (thread == accumulator row) -> row_scale/bias/activation/residual -> global
+//   warps 4..11 epilogue: tcgen05.ld (thread == accumulator row; two warps per TMEM lane quarter take alternate
+//               32-column chunks, next chunk + residual prefetched while the current one is processed, bias staged in
+//               smem) -> row_scale/bias/activation/SwiGLU/residual -> global
 //
-// Tiles are 128 x BN (BN in {64,128,256}), BLOCK_K = 64 bf16 = one 128-byte swizzle atom; the grid is persistent
+// Tiles are 128 x BN, BN in {64,...,256} step 32 chosen per launch by a wave/smem-bandwidth cost model (choose_bn);
+// BLOCK_K = 64 bf16 = one 128-byte swizzle atom; the grid is persistent
 // (<= #SMs CTAs, static round-robin over tiles, M fastest so that a wave shares W tiles through L2).
 // M/N/K tails: TMA zero-fills out-of-bounds reads, stores are predicated.
 #include "host_common.h"
@@ -15,16 +18,23 @@ namespace vl2 {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kGemmThreads = 256;
+static constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quarter: they split the 32-column chunks
+static constexpr int kEpiThreads = kEpiWarps * 32;
+static constexpr int kGemmThreads = 128 + kEpiThreads;    // warps 0..3: TMA / MMA / TMEM alloc / spare
 
 template <int BN>
 struct GemmCfg {
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 32 in [64,256]");
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = BN * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: all powers of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kExtraBytes = 1024 /*align slack*/ + 2 * 256 * 4 /*bias staging*/ + 256 /*barriers*/;
+  static constexpr int kMaxStages = (227 * 1024 - kExtraBytes) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kAccStride = BN > 128 ? 256 : (BN > 64 ? 128 : 64);  // TMEM columns between accumulator stages
+  static constexpr int kTmemCols = 2 * kAccStride;                           // power of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + kExtraBytes;
+  static constexpr int kChunks = BN / 32;
 };
 
 struct GemmParams {
@@ -39,10 +49,14 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
 };
 
+__device__ __forceinline__ float fast_sigmoid_mul(float x, float k_log2e) {
+  // x * sigmoid(k x) = x / (1 + 2^(-k*log2e*x)); approximate reciprocal on the MUFU pipe
+  return __fdividef(x, 1.f + fast_exp2(-k_log2e * x));
+}
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
-    case VL2_ACT_QUICK_GELU: return x / (1.f + __expf(-1.702f * x));
-    case VL2_ACT_SILU: return x / (1.f + __expf(-x));
+    case VL2_ACT_QUICK_GELU: return fast_sigmoid_mul(x, 1.702f * 1.4426950408889634f);
+    case VL2_ACT_SILU: return fast_sigmoid_mul(x, 1.4426950408889634f);
     case VL2_ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
     default: return x;
   }
@@ -58,7 +72,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);  // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 512);
   uint64_t* full_bar = bars;                        // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;    // [2]        MMA -> epilogue
@@ -81,7 +96,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -123,7 +138,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue drained this accumulator stage
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
@@ -142,10 +157,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // warp w: TMEM lane quarter (w & 3); chunk parity ((w - 4) >> 2): even / odd 32-column chunks of the tile.
+    const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int etid = threadIdx.x - 128;
     const int row_in_tile = ew * 32 + lane;
     const bool swiglu = (p.act == VL2_ACT_SWIGLU);
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -154,29 +173,49 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n0 = (tile / p.num_m_tiles) * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
+      float* sb = sbias + as * 256;
+      if (p.bias != nullptr) {  // stage this tile's bias slice once (broadcast LDS later instead of exposed LDG latency)
+        for (int i = etid; i < BN; i += kEpiThreads) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      }
+      const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
-      const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
+      const uint32_t taddr = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
+      const int64_t res_row = (int64_t)row * p.ldr;
+
+      uint32_t v[32];
+      uint4 rr[4];
+      auto issue = [&](int c) {  // TMEM load of chunk c + its residual slice, both asynchronous
+        tmem_ld_32x32(taddr + c * 32, v);
+        if (res != nullptr && row_ok) {
+          const int col0 = n0 + c * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            rr[g] = (col0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(res + res_row + col0 + g * 8) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      int c = grp;
+      if (c < Cfg::kChunks && n0 + c * 32 < p.N) issue(c);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (; c < Cfg::kChunks; c += 2) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        if (!row_ok) continue;
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * rs;
+        uint4 rc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rc[g] = rr[g];
+        if (c + 2 < Cfg::kChunks && col0 + 64 < p.N) issue(c + 2);  // prefetch the next chunk while this one is processed
+        if (!row_ok) continue;
         const int ncols = min(32, p.N - col0);  // multiple of 8
         if (p.bias != nullptr) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            if (g * 4 < ncols) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
-              x[g * 4 + 0] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
-            }
+            const float4 b = *reinterpret_cast<const float4*>(sb + c * 32 + g * 4);
+            x[g * 4 + 0] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
           }
         }
         if (swiglu) {
@@ -190,7 +229,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               for (int j = 0; j < 4; ++j) {
                 const float g0 = x[g * 16 + 4 * j + 0], u0 = x[g * 16 + 4 * j + 1];
                 const float g1 = x[g * 16 + 4 * j + 2], u1 = x[g * 16 + 4 * j + 3];
-                o[j] = pack_bf16(g0 / (1.f + __expf(-g0)) * u0, g1 / (1.f + __expf(-g1)) * u1);
+                o[j] = pack_bf16(fast_sigmoid_mul(g0, 1.4426950408889634f) * u0, fast_sigmoid_mul(g1, 1.4426950408889634f) * u1);
               }
               *reinterpret_cast<uint4*>(crow + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -201,17 +240,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], p.act);
         }
-        if (p.residual != nullptr) {
-          const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (int64_t)row * p.ldr + col0;
+        if (res != nullptr) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (g * 8 < ncols) {
-              const uint4 r = *reinterpret_cast<const uint4*>(rrow + g * 8);
-              x[g * 8 + 0] += bf16_lo(r.x); x[g * 8 + 1] += bf16_hi(r.x);
-              x[g * 8 + 2] += bf16_lo(r.y); x[g * 8 + 3] += bf16_hi(r.y);
-              x[g * 8 + 4] += bf16_lo(r.z); x[g * 8 + 5] += bf16_hi(r.z);
-              x[g * 8 + 6] += bf16_lo(r.w); x[g * 8 + 7] += bf16_hi(r.w);
-            }
+            x[g * 8 + 0] += bf16_lo(rc[g].x); x[g * 8 + 1] += bf16_hi(rc[g].x);
+            x[g * 8 + 2] += bf16_lo(rc[g].y); x[g * 8 + 3] += bf16_hi(rc[g].y);
+            x[g * 8 + 4] += bf16_lo(rc[g].z); x[g * 8 + 5] += bf16_hi(rc[g].z);
+            x[g * 8 + 6] += bf16_lo(rc[g].w); x[g * 8 + 7] += bf16_hi(rc[g].w);
           }
         }
         if (p.out_f32) {
@@ -280,6 +315,29 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   return VL2_OK;
 }
 
+// Tile-width choice.  Model: one 128 x BN x 16 MMA occupies the tensor pipe for ~BN/2 cycles; operands come from smem
+// (A 16 KB + B BN*128 B per k-block at <= 128 B/cycle), so narrow tiles are smem-bound; a launch costs
+// waves x tile time + one un-overlapped epilogue.  Ties go to the wider tile.
+static int choose_bn(int M, int N, int K, int sms) {
+  const int mt = (M + BM - 1) / BM;
+  const int kb = (K + BK - 1) / BK;
+  static const int cands[7] = {256, 224, 192, 160, 128, 96, 64};
+  int best = 256;
+  double best_cost = -1;
+  for (int i = 0; i < 7; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N <= bn - 32) continue;  // do not pick a tile much wider than the matrix
+    const long tiles = (long)mt * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const double mma = 4.0 * (bn / 2.0);
+    const double smem = (16384.0 + bn * 128.0) / 128.0;
+    const double per_kb = mma > smem ? mma : smem;
+    const double cost = waves * (kb * per_kb + 400.0) + 1500.0 + bn * 12.0;
+    if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 }  // namespace vl2
 
 extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
@@ -301,23 +359,15 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
                 "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Tile-width choice: fewest (waves x tile width); ties go to the wider tile (less A re-streaming).
-  const int sms = sm_count();
-  const int mt = (a->M + BM - 1) / BM;
-  int best_bn = 256;
-  long best_cost = -1;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
-    if (bn > 64 && a->N <= bn / 2) continue;
-    const long tiles = (long)mt * ((a->N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    const long cost = waves * (bn + 24);  // +24: per-tile fixed overhead (pipeline fill / epilogue tail)
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
-  }
-  switch (best_bn) {
+  int bn = choose_bn(a->M, a->N, a->K, sm_count());
+  if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) bn = a->reserved;  // test hook: force a tile width
+  switch (bn) {
     case 256: return launch_gemm<256>(a, st);
+    case 224: return launch_gemm<224>(a, st);
+    case 192: return launch_gemm<192>(a, st);
+    case 160: return launch_gemm<160>(a, st);
     case 128: return launch_gemm<128>(a, st);
+    case 96: return launch_gemm<96>(a, st);
     default: return launch_gemm<64>(a, st);
   }
 }

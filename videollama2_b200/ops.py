@@ -44,8 +44,9 @@ def launch_count() -> int:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
-    """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous)."""
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0) -> torch.Tensor:
+    """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
+    `bn` forces the tile width (tests); 0 = library heuristic."""
     _need_cuda(a, w, bias, residual, row_scale, out)
     _bf16(a, w, residual)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1, "gemm: 2-D, unit inner stride"
@@ -66,7 +67,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     args = GemmArgs(A=a.data_ptr(), W=w.data_ptr(), C=out.data_ptr(), bias=_ptr(bias), residual=_ptr(residual),
                     row_scale=_ptr(row_scale), lda=a.stride(0), ldw=w.stride(0), ldc=out.stride(0),
                     ldr=residual.stride(0) if residual is not None else 0, M=M, N=N, K=K, act=act,
-                    out_f32=1 if out.dtype == torch.float32 else 0, reserved=0)
+                    out_f32=1 if out.dtype == torch.float32 else 0, reserved=bn)
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("gemm: out must be bf16 or fp32")
     check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
