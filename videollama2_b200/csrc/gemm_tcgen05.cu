@@ -315,9 +315,10 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   return VL2_OK;
 }
 
-// Tile-width choice.  Model: one 128 x BN x 16 MMA occupies the tensor pipe for ~BN/2 cycles; operands come from smem
-// (A 16 KB + B BN*128 B per k-block at <= 128 B/cycle), so narrow tiles are smem-bound; a launch costs
-// waves x tile time + one un-overlapped epilogue.  Ties go to the wider tile.
+// Tile-width choice.  Model (fitted to ncu launch times, profiles/r01_launches_v2_summary.txt): one 128 x BN x 16 MMA
+// occupies the tensor pipe for ~BN/2 cycles; every k-block moves A (16 KB) + B (BN*128 B) into smem (TMA write) and out
+// again (MMA read) at ~190 B/cycle combined, so tiles narrower than 256 are smem-bound (BN=128 measured 1.38x slower
+// per flop than BN=256); a launch costs waves x tile time + one un-overlapped epilogue.  Ties go to the wider tile.
 static int choose_bn(int M, int N, int K, int sms) {
   const int mt = (M + BM - 1) / BM;
   const int kb = (K + BK - 1) / BK;
@@ -330,10 +331,10 @@ static int choose_bn(int M, int N, int K, int sms) {
     const long tiles = (long)mt * ((N + bn - 1) / bn);
     const long waves = (tiles + sms - 1) / sms;
     const double mma = 4.0 * (bn / 2.0);
-    const double smem = (16384.0 + bn * 128.0) / 128.0;
+    const double smem = 2.0 * (16384.0 + bn * 128.0) / 190.0;
     const double per_kb = mma > smem ? mma : smem;
-    const double cost = waves * (kb * per_kb + 400.0) + 1500.0 + bn * 12.0;
-    if (best_cost < 0 || cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+    const double cost = waves * (kb * per_kb + 600.0) + 2000.0 + bn * 16.0;
+    if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best = bn; }
   }
   return best;
 }

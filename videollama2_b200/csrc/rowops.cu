@@ -143,6 +143,116 @@ __global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_b
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Warp-per-row variants (C <= 4096): no block barriers, 8 rows per CTA, the row stays in registers as packed bf16.
+// These are the ones the hot path uses; the CTA-per-row kernels above remain for wider rows.
+// ---------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float warp_sum(float a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                      const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
+                      __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps, int act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    v[i] = (vi < nvec) ? xr[vi] : make_uint4(0, 0, 0, 0);
+    float f[8];
+    unpack8(v[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < nvec) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  const uint4* br = reinterpret_cast<const uint4*>(beta);
+  const uint4* rr = residual ? reinterpret_cast<const uint4*>(residual + row * C) : nullptr;
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float f[8], g[8], b[8], o[8];
+      unpack8(v[i], f);
+      unpack8(__ldg(gr + vi), g);
+      unpack8(__ldg(br + vi), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * g[j] + b[j];
+      if (rr) {
+        float r[8];
+        unpack8(rr[vi], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      if (act == VL2_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = silu(o[j]);
+      }
+      yr[vi] = pack8(o);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                    __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4 v[NV];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    v[i] = (vi < nvec) ? xr[vi] : make_uint4(0, 0, 0, 0);
+    float f[8];
+    unpack8(v[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += f[j] * f[j];
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float f[8], g[8], o[8];
+      unpack8(v[i], f);
+      unpack8(__ldg(gr + vi), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = g[j] * __bfloat162float(__float2bfloat16_rn(f[j] * rstd));
+      yr[vi] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // CLIP embeddings: tok[f,0] = cls + pos[0]; tok[f,1+p] = patch[f,p] + pos[1+p]; then pre_layrnorm.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void clip_embed_finish_kernel(const __nv_bfloat16* __restrict__ patch, const __nv_bfloat16* __restrict__ cls,
@@ -377,23 +487,37 @@ __global__ void conv3d_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // RoPE (rotate-half pairing i <-> i + D/2) applied in place to the q and k heads of a fused QKV buffer.
 // One thread per (token, i); loops over heads.  cos/sin from fp32 inv_freq (HF computes them in fp32).
 // ---------------------------------------------------------------------------------------------------------
+// One CTA per token: cos/sin of the D/2 frequencies go through smem once, then each thread rotates 8 pairs of one
+// head with 16-byte accesses.
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off,
                             int k_off, int pos0, const float* __restrict__ inv_freq) {
+  extern __shared__ float cs[];  // [D/2] cos, [D/2] sin
   const int half = D / 2;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= S * half) return;
-  const int i = idx % half, s = idx / half;
-  float sn, cs;
-  sincosf((float)(pos0 + s) * inv_freq[i], &sn, &cs);
-  // HF casts cos/sin to the activation dtype before use
-  cs = __bfloat162float(__float2bfloat16_rn(cs));
-  sn = __bfloat162float(__float2bfloat16_rn(sn));
+  const int s = blockIdx.x;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float sn, c;
+    sincosf((float)(pos0 + s) * inv_freq[i], &sn, &c);
+    // HF casts cos/sin to the activation dtype before use
+    cs[i] = __bfloat162float(__float2bfloat16_rn(c));
+    cs[half + i] = __bfloat162float(__float2bfloat16_rn(sn));
+  }
+  __syncthreads();
+  const int vph = half / 8;  // 16-byte vectors per half head
   __nv_bfloat16* row = qkv + (int64_t)s * ld;
-  for (int h = 0; h < Hq + Hkv; ++h) {
-    __nv_bfloat16* p = row + (h < Hq ? q_off + h * D : k_off + (h - Hq) * D);
-    const float a = __bfloat162float(p[i]), b = __bfloat162float(p[i + half]);
-    p[i] = __float2bfloat16_rn(a * cs - b * sn);
-    p[i + half] = __float2bfloat16_rn(b * cs + a * sn);
+  for (int t = threadIdx.x; t < (Hq + Hkv) * vph; t += blockDim.x) {
+    const int h = t / vph, i0 = (t % vph) * 8;
+    __nv_bfloat16* p = row + (h < Hq ? q_off + h * D : k_off + (h - Hq) * D) + i0;
+    float a[8], b[8], oa[8], ob[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), a);
+    unpack8(*reinterpret_cast<const uint4*>(p + half), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float c = cs[i0 + j], sn = cs[half + i0 + j];
+      oa[j] = a[j] * c - b[j] * sn;
+      ob[j] = b[j] * c + a[j] * sn;
+    }
+    *reinterpret_cast<uint4*>(p) = pack8(oa);
+    *reinterpret_cast<uint4*>(p + half) = pack8(ob);
   }
 }
 
@@ -413,51 +537,82 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32
 // Skinny GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias), M <= 32.  One warp per output column n; W streams once from
 // HBM (16-byte loads), A (tiny) is re-read from L1/L2.
 // ---------------------------------------------------------------------------------------------------------
+// CTA = 8 warps x 2 output columns; the (tiny) A matrix is staged through smem in K chunks as fp32 so that W streams
+// from HBM exactly once and A costs L2 traffic only once per CTA.
+static constexpr int kSkinnyNPW = 2;
+static constexpr int kSkinnyMB = 16;
+
 template <bool A_F32>
-__global__ void gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt,
-                                   const float* __restrict__ bias, void* __restrict__ Cv, int out_f32, int M, int N,
-                                   int K, int act) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const int n = warp;
-  const uint4* wr = reinterpret_cast<const uint4*>(Wt + (int64_t)n * K);
-  const int kv = K / 8;
-  for (int m0 = 0; m0 < M; m0 += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int v = lane; v < kv; v += 32) {
-      float w[8];
-      unpack8(__ldg(wr + v), w);
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
+                   void* __restrict__ Cv, int out_f32, int M, int N, int K, int act, int KC) {
+  extern __shared__ float sA[];  // [min(M,16)][KC]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * 8 + warp) * kSkinnyNPW;
+  for (int m0 = 0; m0 < M; m0 += kSkinnyMB) {
+    const int mb = min(kSkinnyMB, M - m0);
+    float acc[kSkinnyNPW][kSkinnyMB];
 #pragma unroll
-      for (int mm = 0; mm < 4; ++mm) {
-        if (m0 + mm < M) {
-          float a[8];
-          if (A_F32) {
-            const float* ar = reinterpret_cast<const float*>(Av) + (int64_t)(m0 + mm) * K + v * 8;
-            const float4 a0 = *reinterpret_cast<const float4*>(ar), a1 = *reinterpret_cast<const float4*>(ar + 4);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-          } else {
-            unpack8(*(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + (int64_t)(m0 + mm) * K) + v), a);
+    for (int j = 0; j < kSkinnyNPW; ++j)
+#pragma unroll
+      for (int m = 0; m < kSkinnyMB; ++m) acc[j][m] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      const int kc = min(KC, K - k0);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < mb * (kc / 8); idx += blockDim.x) {
+        const int m = idx / (kc / 8), v = idx % (kc / 8);
+        float a[8];
+        if (A_F32) {
+          const float* ar = reinterpret_cast<const float*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8;
+          const float4 a0 = *reinterpret_cast<const float4*>(ar), a1 = *reinterpret_cast<const float4*>(ar + 4);
+          a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        } else {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8), a);
+        }
+        float* d = sA + m * KC + v * 8;
+        *reinterpret_cast<float4*>(d) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(a[4], a[5], a[6], a[7]);
+      }
+      __syncthreads();
+      if (n0 < N) {
+        for (int v = lane; v < kc / 8; v += 32) {
+          float w[kSkinnyNPW][8];
+#pragma unroll
+          for (int j = 0; j < kSkinnyNPW; ++j) {
+            if (n0 + j < N) unpack8(__ldg(reinterpret_cast<const uint4*>(Wt + (int64_t)(n0 + j) * K + k0) + v), w[j]);
+            else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[j][e] = 0.f;
+            }
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[mm] = fmaf(a[j], w[j], acc[mm]);
+          for (int m = 0; m < kSkinnyMB; ++m) {
+            if (m < mb) {
+              const float4 a0 = *reinterpret_cast<const float4*>(sA + m * KC + v * 8);
+              const float4 a1 = *reinterpret_cast<const float4*>(sA + m * KC + v * 8 + 4);
+#pragma unroll
+              for (int j = 0; j < kSkinnyNPW; ++j) {
+                acc[j][m] = fmaf(a0.x, w[j][0], acc[j][m]); acc[j][m] = fmaf(a0.y, w[j][1], acc[j][m]);
+                acc[j][m] = fmaf(a0.z, w[j][2], acc[j][m]); acc[j][m] = fmaf(a0.w, w[j][3], acc[j][m]);
+                acc[j][m] = fmaf(a1.x, w[j][4], acc[j][m]); acc[j][m] = fmaf(a1.y, w[j][5], acc[j][m]);
+                acc[j][m] = fmaf(a1.z, w[j][6], acc[j][m]); acc[j][m] = fmaf(a1.w, w[j][7], acc[j][m]);
+              }
+            }
+          }
         }
       }
     }
 #pragma unroll
-    for (int mm = 0; mm < 4; ++mm) {
+    for (int j = 0; j < kSkinnyNPW; ++j) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[mm] += __shfl_xor_sync(0xffffffffu, acc[mm], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int mm = 0; mm < 4; ++mm) {
-        if (m0 + mm < M) {
-          float r = acc[mm] + (bias ? bias[n] : 0.f);
+      for (int m = 0; m < kSkinnyMB; ++m) {
+        float r = warp_sum(acc[j][m]);
+        if (lane == 0 && m < mb && n0 + j < N) {
+          r += bias ? bias[n0 + j] : 0.f;
           if (act == VL2_ACT_SILU) r = silu(r);
           else if (act == 100) r = 1.f / (1.f + __expf(-r));
-          if (out_f32) reinterpret_cast<float*>(Cv)[(int64_t)(m0 + mm) * N + n] = r;
-          else reinterpret_cast<__nv_bfloat16*>(Cv)[(int64_t)(m0 + mm) * N + n] = __float2bfloat16_rn(r);
+          if (out_f32) reinterpret_cast<float*>(Cv)[(int64_t)(m0 + m) * N + n0 + j] = r;
+          else reinterpret_cast<__nv_bfloat16*>(Cv)[(int64_t)(m0 + m) * N + n0 + j] = __float2bfloat16_rn(r);
         }
       }
     }
@@ -483,8 +638,20 @@ extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta,
   VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU, VL2_E_UNSUPPORTED, "vl2_layernorm: act %d unsupported", act);
   VL2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(residual), VL2_E_BADALIGN,
               "vl2_layernorm: pointers must be 16-byte aligned");
-  layernorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (const bf16*)residual, (bf16*)y, C, eps, act);
+  const unsigned wgrid = (unsigned)((rows + 7) / 8);
+  const int nv = (C / 8 + 31) / 32;
+#define VL2_LN_WARP(NV)                                                                                   \
+  layernorm_warp_kernel<NV><<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, \
+      (const bf16*)beta, (const bf16*)residual, (bf16*)y, rows, C, eps, act)
+  if (nv <= 1) VL2_LN_WARP(1);
+  else if (nv <= 2) VL2_LN_WARP(2);
+  else if (nv <= 4) VL2_LN_WARP(4);
+  else if (nv <= 8) VL2_LN_WARP(8);
+  else if (nv <= 16) VL2_LN_WARP(16);
+  else
+    layernorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (const bf16*)residual, (bf16*)y, C, eps, act);
+#undef VL2_LN_WARP
   VL2_CHECK_LAUNCH("layernorm_kernel");
   return VL2_OK;
 }
@@ -493,8 +660,19 @@ extern "C" int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t ro
   VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE,
               "vl2_rmsnorm: rows=%lld C=%d unsupported", (long long)rows, C);
   VL2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma), VL2_E_BADALIGN, "vl2_rmsnorm: 16-byte alignment");
-  rmsnorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma,
-                                                                            (bf16*)y, C, eps);
+  const unsigned wgrid = (unsigned)((rows + 7) / 8);
+  const int nv = (C / 8 + 31) / 32;
+#define VL2_RMS_WARP(NV) \
+  rmsnorm_warp_kernel<NV><<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, C, eps)
+  if (nv <= 1) VL2_RMS_WARP(1);
+  else if (nv <= 2) VL2_RMS_WARP(2);
+  else if (nv <= 4) VL2_RMS_WARP(4);
+  else if (nv <= 8) VL2_RMS_WARP(8);
+  else if (nv <= 16) VL2_RMS_WARP(16);
+  else
+    rmsnorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma,
+                                                                              (bf16*)y, C, eps);
+#undef VL2_RMS_WARP
   VL2_CHECK_LAUNCH("rmsnorm_kernel");
   return VL2_OK;
 }
@@ -564,9 +742,12 @@ extern "C" int vl2_conv3d_im2col(const void* x, void* A, int T, int H, int W, in
 extern "C" int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off, int k_off, int pos0,
                                 const float* inv_freq, void* stream) {
   VL2_REQUIRE(S > 0 && D % 2 == 0 && Hq > 0 && Hkv >= 0 && inv_freq != nullptr, VL2_E_BADSHAPE, "vl2_rope_inplace: bad shape");
-  const int total = S * (D / 2);
-  rope_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>((bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
-                                                                    inv_freq);
+  VL2_REQUIRE(D % 16 == 0 && ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && aligned16(qkv), VL2_E_BADALIGN,
+              "vl2_rope_inplace: D %% 16 == 0 and 16-byte aligned heads required");
+  int threads = (Hq + Hkv) * (D / 16);
+  threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
+  rope_kernel<<<S, threads, D * sizeof(float), (cudaStream_t)stream>>>((bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
+                                                                      inv_freq);
   VL2_CHECK_LAUNCH("rope_kernel");
   return VL2_OK;
 }
@@ -585,12 +766,17 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
               "vl2_gemm_skinny: need 0 < M <= 32 and K %% 8 == 0 (M=%d K=%d)", M, K);
   VL2_REQUIRE(aligned16(A) && aligned16(W), VL2_E_BADALIGN, "vl2_gemm_skinny: 16-byte alignment");
   VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU || act == 100, VL2_E_UNSUPPORTED, "vl2_gemm_skinny: act %d", act);
-  const int threads = 256;
-  const int blocks = (N * 32 + threads - 1) / threads;
+  const int mb = M < kSkinnyMB ? M : kSkinnyMB;
+  int KC = (40 * 1024 / 4) / mb;      // <= 40 KB of staged A
+  KC = KC / 256 * 256;
+  if (KC > 2048) KC = 2048;
+  if (KC > K) KC = (K + 7) / 8 * 8;
+  const size_t smem = (size_t)mb * KC * sizeof(float);
+  const int blocks = (N + 8 * kSkinnyNPW - 1) / (8 * kSkinnyNPW);
   if (a_f32)
-    gemm_skinny_kernel<true><<<blocks, threads, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act);
+    gemm_skinny_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act, KC);
   else
-    gemm_skinny_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act);
+    gemm_skinny_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act, KC);
   VL2_CHECK_LAUNCH("gemm_skinny_kernel");
   return VL2_OK;
 }
