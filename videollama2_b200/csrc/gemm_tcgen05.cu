@@ -28,7 +28,8 @@ struct GemmCfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = BN * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kExtraBytes = 1024 /*align slack*/ + 2 * 256 * 4 /*bias staging*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
+  static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias staging*/ + 256 /*barriers*/;
   static constexpr int kMaxStages = (227 * 1024 - kExtraBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kAccStride = BN > 128 ? 256 : (BN > 64 ? 128 : 64);  // TMEM columns between accumulator stages
@@ -67,12 +68,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte aligned stage bases.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B operands need 1024-byte aligned stage bases: the kernel has no static smem, so the dynamic window
+  // starts at offset 0 of the CTA's shared memory (checked below; a misaligned base traps instead of corrupting).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageBytesA;
-  float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);  // [2][256]
+  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;                       // [kEpiWarps][4096]
+  float* sbias = reinterpret_cast<float*>(smem_stage + Cfg::kStagingBytes);           // [2][256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 512);
   uint64_t* full_bar = bars;                        // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::kStages;        // [kStages]  MMA -> TMA
@@ -158,13 +161,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    // warp w: TMEM lane quarter (w & 3); chunk parity ((w - 4) >> 2): even / odd 32-column chunks of the tile.
+    // warp w: TMEM lane quarter (w & 3); the two warps of a quarter take alternate 64-column spans of the tile.
+    // Accumulator rows live one per thread (TMEM lane == row), which is the wrong shape for global memory, so every
+    // 32-row x 64-column block goes through a per-warp swizzled smem buffer: residual rows come in and output rows go
+    // out as full 128-byte lines (8 lanes x 16 B per row) instead of 32 different rows per instruction.
     const int ew = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int etid = threadIdx.x - 128;
     const int row_in_tile = ew * 32 + lane;
     const bool swiglu = (p.act == VL2_ACT_SWIGLU);
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+    const uint32_t stg = smem_u32(smem_stage + (warp - 4) * 4096);
+    const uint32_t my_row = stg + lane * 128;             // this thread's row in the staging buffer
+    const int sw = lane & 7;                              // its swizzle key
+    const int t_row = lane >> 3, t_chunk = lane & 7;      // transposed role: 8 lanes per row, 4 rows per instruction
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -173,57 +183,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n0 = (tile / p.num_m_tiles) * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
-      float* sb = sbias + as * 256;
+      const uint32_t sb = smem_u32(sbias + as * 256);
       if (p.bias != nullptr) {  // stage this tile's bias slice once (broadcast LDS later instead of exposed LDG latency)
-        for (int i = etid; i < BN; i += kEpiThreads) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        for (int i = etid; i < BN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       }
       const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
-      const int64_t res_row = (int64_t)row * p.ldr;
+      const int rbase = m0 + ew * 32;  // first row of this warp's 32-row block
 
-      uint32_t v[32];
-      uint4 rr[4];
-      auto issue = [&](int c) {  // TMEM load of chunk c + its residual slice, both asynchronous
-        tmem_ld_32x32(taddr + c * 32, v);
-        if (res != nullptr && row_ok) {
-          const int col0 = n0 + c * 32;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            rr[g] = (col0 + g * 8 < p.N) ? *reinterpret_cast<const uint4*>(res + res_row + col0 + g * 8) : make_uint4(0, 0, 0, 0);
-        }
-      };
-      int c = grp;
-      if (c < Cfg::kChunks && n0 + c * 32 < p.N) issue(c);
 #pragma unroll 1
-      for (; c < Cfg::kChunks; c += 2) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        tmem_ld_wait();
-        float x[32];
+      for (int sp = grp; sp * 64 < BN; sp += 2) {
+        const int c0 = sp * 64;                       // first accumulator column of the span inside the tile
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) break;                       // warp-uniform
+        const int span = min(min(64, BN - c0), p.N - col0);   // 8..64 valid accumulator columns (multiple of 8)
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        // residual block -> smem (coalesced: 8 lanes x 16 B per row)
+        if (res != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * rs;
-        uint4 rc[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rc[g] = rr[g];
-        if (c + 2 < Cfg::kChunks && col0 + 64 < p.N) issue(c + 2);  // prefetch the next chunk while this one is processed
-        if (!row_ok) continue;
-        const int ncols = min(32, p.N - col0);  // multiple of 8
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 b = *reinterpret_cast<const float4*>(sb + c * 32 + g * 4);
-            x[g * 4 + 0] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = t_row + 4 * i;
+            const int gr = rbase + rr, gc = col0 + t_chunk * 8;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (gr < p.M && t_chunk * 8 < span) val = *reinterpret_cast<const uint4*>(res + (int64_t)gr * p.ldr + gc);
+            sts128(stg + rr * 128 + ((t_chunk ^ (rr & 7)) << 4), val);
           }
+          __syncwarp();
         }
-        if (swiglu) {
-          // columns interleave (gate, up): 32 accumulator columns -> 16 outputs
-          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + (col0 >> 1);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (g * 16 < ncols) {
+        for (int hf = 0; hf < 2; ++hf) {              // two 32-column halves of the span
+          if (hf * 32 >= span) break;                 // warp-uniform
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * rs;
+          if (hf == 0 && span > 32) tmem_ld_32x32(taddr + c0 + 32, v);   // prefetch the second half
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bq = lds_f4(sb + (c0 + hf * 32 + g * 4) * 4);
+              x[g * 4 + 0] += bq.x; x[g * 4 + 1] += bq.y; x[g * 4 + 2] += bq.z; x[g * 4 + 3] += bq.w;
+            }
+          }
+          if (swiglu) {
+            // accumulator columns interleave (gate, up): 32 columns -> 16 outputs = staging chunks 2*hf, 2*hf+1
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
               uint32_t o[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -231,41 +240,61 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const float g1 = x[g * 16 + 4 * j + 2], u1 = x[g * 16 + 4 * j + 3];
                 o[j] = pack_bf16(fast_sigmoid_mul(g0, 1.4426950408889634f) * u0, fast_sigmoid_mul(g1, 1.4426950408889634f) * u1);
               }
-              *reinterpret_cast<uint4*>(crow + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              sts128(my_row + (((hf * 2 + g) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+            }
+            continue;
+          }
+          if (p.act != VL2_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], p.act);
+          }
+          if (res != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 r = lds128(my_row + (((hf * 4 + g) ^ sw) << 4));
+              x[g * 8 + 0] += bf16_lo(r.x); x[g * 8 + 1] += bf16_hi(r.x);
+              x[g * 8 + 2] += bf16_lo(r.y); x[g * 8 + 3] += bf16_hi(r.y);
+              x[g * 8 + 4] += bf16_lo(r.z); x[g * 8 + 5] += bf16_hi(r.z);
+              x[g * 8 + 6] += bf16_lo(r.w); x[g * 8 + 7] += bf16_hi(r.w);
             }
           }
-          continue;
-        }
-        if (p.act != VL2_ACT_NONE) {
+          if (p.out_f32) {   // fp32 logits: rare, written directly (row-per-thread)
+            if (row_ok) {
+              float* crow = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0 + hf * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], p.act);
-        }
-        if (res != nullptr) {
+              for (int g = 0; g < 8; ++g)
+                if (hf * 32 + g * 4 < span)
+                  *reinterpret_cast<float4*>(crow + g * 4) = make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+            }
+          } else {
+            // own row -> smem (each thread overwrites only the chunks it just read its residual from)
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            x[g * 8 + 0] += bf16_lo(rc[g].x); x[g * 8 + 1] += bf16_hi(rc[g].x);
-            x[g * 8 + 2] += bf16_lo(rc[g].y); x[g * 8 + 3] += bf16_hi(rc[g].y);
-            x[g * 8 + 4] += bf16_lo(rc[g].z); x[g * 8 + 5] += bf16_hi(rc[g].z);
-            x[g * 8 + 6] += bf16_lo(rc[g].w); x[g * 8 + 7] += bf16_hi(rc[g].w);
+            for (int g = 0; g < 4; ++g)
+              sts128(my_row + (((hf * 4 + g) ^ sw) << 4),
+                     make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
+                                pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7])));
           }
         }
-        if (p.out_f32) {
-          float* crow = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+        if (!p.out_f32) {
+          __syncwarp();
+          // smem -> global, full lines.  Output span: `span` columns (or span/2 for SwiGLU).
+          const int out_span = swiglu ? (span >> 1) : span;
+          const int out_col0 = swiglu ? (col0 >> 1) : col0;
+          __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C);
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g * 4 < ncols)
-              *reinterpret_cast<float4*>(crow + g * 4) = make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
-        } else {
-          __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (g * 8 < ncols)
-              *reinterpret_cast<uint4*>(crow + g * 8) =
-                  make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
-                             pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+          for (int i = 0; i < 8; ++i) {
+            const int rr = t_row + 4 * i;
+            const int gr = rbase + rr;
+            if (gr < p.M && t_chunk * 8 < out_span) {
+              const uint4 val = lds128(stg + rr * 128 + ((t_chunk ^ (rr & 7)) << 4));
+              *reinterpret_cast<uint4*>(cbase + (int64_t)gr * p.ldc + out_col0 + t_chunk * 8) = val;
+            }
+          }
+          __syncwarp();  // the buffer is reused by the next span
         }
       }
       // all tcgen05.ld of this thread have completed (wait::ld above) -> hand the accumulator stage back
+      tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[as]);
     }

@@ -47,104 +47,9 @@ static inline int row_threads(int C) {
 static constexpr int kMaxVec = 4;  // vectors of 8 channels held per thread => C <= 512*8*4 = 16384
 
 // ---------------------------------------------------------------------------------------------------------
-// LayerNorm (+ residual, + SiLU), one CTA per row.  Two-pass (mean, then centred variance) in registers.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
-                                 const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
-                                 __nv_bfloat16* __restrict__ y, int C, float eps, int act) {
-  __shared__ float red[64];
-  const int64_t row = blockIdx.x;
-  const int nvec = C / 8;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
-  float v[kMaxVec][8];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
-    if (vi < nvec) {
-      unpack8(xr[vi], v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    }
-  }
-  const float mean = block_sum2(s, 0.f, red).x / (float)C;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
-    if (vi < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
-  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
-  const uint4* br = reinterpret_cast<const uint4*>(beta);
-  const uint4* rr = residual ? reinterpret_cast<const uint4*>(residual + row * C) : nullptr;
-  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
-    if (vi < nvec) {
-      float g[8], b[8], o[8];
-      unpack8(__ldg(gr + vi), g);
-      unpack8(__ldg(br + vi), b);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + b[j];
-      if (rr) {
-        float r[8];
-        unpack8(rr[vi], r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += r[j];
-      }
-      if (act == VL2_ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = silu(o[j]);
-      }
-      yr[vi] = pack8(o);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// RMSNorm with HF rounding order: y = gamma * bf16(x * rstd).
-// ---------------------------------------------------------------------------------------------------------
-__global__ void rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
-                               __nv_bfloat16* __restrict__ y, int C, float eps) {
-  __shared__ float red[64];
-  const int64_t row = blockIdx.x;
-  const int nvec = C / 8;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
-  float v[kMaxVec][8];
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
-    if (vi < nvec) {
-      unpack8(xr[vi], v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q += v[i][j] * v[i][j];
-    }
-  }
-  const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
-  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
-  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
-    if (vi < nvec) {
-      float g[8], o[8];
-      unpack8(__ldg(gr + vi), g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = g[j] * __bfloat162float(__float2bfloat16_rn(v[i][j] * rstd));
-      yr[vi] = pack8(o);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Warp-per-row variants (C <= 4096): no block barriers, 8 rows per CTA, the row stays in registers as packed bf16.
-// These are the ones the hot path uses; the CTA-per-row kernels above remain for wider rows.
+// LayerNorm (+ residual, + SiLU) and RMSNorm (HF rounding order: y = gamma * bf16(x * rstd)), one warp per row,
+// 8 rows per CTA, no block barriers.  Narrow rows (C <= 1024) stay in registers as packed bf16 (two-pass centred
+// variance); wide rows use the streaming kernels further down.
 // ---------------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ float warp_sum(float a) {
@@ -249,6 +154,84 @@ rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
       for (int j = 0; j < 8; ++j) o[j] = g[j] * __bfloat162float(__float2bfloat16_rn(f[j] * rstd));
       yr[vi] = pack8(o);
     }
+  }
+}
+
+// Wide rows (C > 1024): keep nothing in registers -> full occupancy; pass 1 accumulates sum / sum of squares
+// (fp32), pass 2 re-reads the row (L2-resident: it was streamed microseconds ago) and writes the result.
+__global__ void __launch_bounds__(256)
+layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                        const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
+                        __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps, int act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  float s = 0.f, q = 0.f;
+#pragma unroll 4
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float f[8];
+    unpack8(xr[vi], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += f[j]; q = fmaf(f[j], f[j], q); }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  const float var = fmaxf(warp_sum(q) / (float)C - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  const uint4* br = reinterpret_cast<const uint4*>(beta);
+  const uint4* rr = residual ? reinterpret_cast<const uint4*>(residual + row * C) : nullptr;
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll 2
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float f[8], g[8], b[8], o[8];
+    unpack8(xr[vi], f);
+    unpack8(__ldg(gr + vi), g);
+    unpack8(__ldg(br + vi), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * g[j] + b[j];
+    if (rr) {
+      float r[8];
+      unpack8(rr[vi], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += r[j];
+    }
+    if (act == VL2_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = silu(o[j]);
+    }
+    yr[vi] = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rmsnorm_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                      __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  float q = 0.f;
+#pragma unroll 4
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float f[8];
+    unpack8(xr[vi], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q = fmaf(f[j], f[j], q);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const uint4* gr = reinterpret_cast<const uint4*>(gamma);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll 2
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float f[8], g[8], o[8];
+    unpack8(xr[vi], f);
+    unpack8(__ldg(gr + vi), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] * __bfloat162float(__float2bfloat16_rn(f[j] * rstd));
+    yr[vi] = pack8(o);
   }
 }
 
@@ -540,9 +523,8 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32
 // CTA = 8 warps x 2 output columns; the (tiny) A matrix is staged through smem in K chunks as fp32 so that W streams
 // from HBM exactly once and A costs L2 traffic only once per CTA.
 static constexpr int kSkinnyNPW = 2;
-static constexpr int kSkinnyMB = 16;
 
-template <bool A_F32>
+template <bool A_F32, int kSkinnyMB>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
                    void* __restrict__ Cv, int out_f32, int M, int N, int K, int act, int KC) {
@@ -575,6 +557,7 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
       }
       __syncthreads();
       if (n0 < N) {
+#pragma unroll 4
         for (int v = lane; v < kc / 8; v += 32) {
           float w[kSkinnyNPW][8];
 #pragma unroll
@@ -633,8 +616,8 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta, const void* residual, void* y,
                              int64_t rows, int C, float eps, int act, void* stream) {
-  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE,
-              "vl2_layernorm: rows=%lld C=%d unsupported (C %% 8 == 0, C <= 16384)", (long long)rows, C);
+  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, VL2_E_BADSHAPE,
+              "vl2_layernorm: rows=%lld C=%d unsupported (C %% 8 == 0)", (long long)rows, C);
   VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU, VL2_E_UNSUPPORTED, "vl2_layernorm: act %d unsupported", act);
   VL2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(residual), VL2_E_BADALIGN,
               "vl2_layernorm: pointers must be 16-byte aligned");
@@ -646,18 +629,16 @@ extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta,
   if (nv <= 1) VL2_LN_WARP(1);
   else if (nv <= 2) VL2_LN_WARP(2);
   else if (nv <= 4) VL2_LN_WARP(4);
-  else if (nv <= 8) VL2_LN_WARP(8);
-  else if (nv <= 16) VL2_LN_WARP(16);
   else
-    layernorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (const bf16*)residual, (bf16*)y, C, eps, act);
+    layernorm_stream_kernel<<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta,
+                                                                   (const bf16*)residual, (bf16*)y, rows, C, eps, act);
 #undef VL2_LN_WARP
   VL2_CHECK_LAUNCH("layernorm_kernel");
   return VL2_OK;
 }
 
 extern "C" int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t rows, int C, float eps, void* stream) {
-  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE,
+  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, VL2_E_BADSHAPE,
               "vl2_rmsnorm: rows=%lld C=%d unsupported", (long long)rows, C);
   VL2_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma), VL2_E_BADALIGN, "vl2_rmsnorm: 16-byte alignment");
   const unsigned wgrid = (unsigned)((rows + 7) / 8);
@@ -667,11 +648,8 @@ extern "C" int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t ro
   if (nv <= 1) VL2_RMS_WARP(1);
   else if (nv <= 2) VL2_RMS_WARP(2);
   else if (nv <= 4) VL2_RMS_WARP(4);
-  else if (nv <= 8) VL2_RMS_WARP(8);
-  else if (nv <= 16) VL2_RMS_WARP(16);
   else
-    rmsnorm_kernel<<<(unsigned)rows, row_threads(C), 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma,
-                                                                              (bf16*)y, C, eps);
+    rmsnorm_stream_kernel<<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, C, eps);
 #undef VL2_RMS_WARP
   VL2_CHECK_LAUNCH("rmsnorm_kernel");
   return VL2_OK;
@@ -766,17 +744,19 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
               "vl2_gemm_skinny: need 0 < M <= 32 and K %% 8 == 0 (M=%d K=%d)", M, K);
   VL2_REQUIRE(aligned16(A) && aligned16(W), VL2_E_BADALIGN, "vl2_gemm_skinny: 16-byte alignment");
   VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU || act == 100, VL2_E_UNSUPPORTED, "vl2_gemm_skinny: act %d", act);
-  const int mb = M < kSkinnyMB ? M : kSkinnyMB;
+  const int MBT = M <= 2 ? 2 : 16;    // rows per pass (template instantiations)
+  const int mb = M < MBT ? M : MBT;
   int KC = (40 * 1024 / 4) / mb;      // <= 40 KB of staged A
   KC = KC / 256 * 256;
   if (KC > 2048) KC = 2048;
   if (KC > K) KC = (K + 7) / 8 * 8;
   const size_t smem = (size_t)mb * KC * sizeof(float);
   const int blocks = (N + 8 * kSkinnyNPW - 1) / (8 * kSkinnyNPW);
-  if (a_f32)
-    gemm_skinny_kernel<true><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act, KC);
-  else
-    gemm_skinny_kernel<false><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act, KC);
+#define VL2_SKINNY(AF, MB) \
+  gemm_skinny_kernel<AF, MB><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act, KC)
+  if (a_f32) { if (MBT == 2) VL2_SKINNY(true, 2); else VL2_SKINNY(true, 16); }
+  else { if (MBT == 2) VL2_SKINNY(false, 2); else VL2_SKINNY(false, 16); }
+#undef VL2_SKINNY
   VL2_CHECK_LAUNCH("gemm_skinny_kernel");
   return VL2_OK;
 }
