@@ -77,9 +77,10 @@ int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 /* Skinny GEMM (M <= 32 rows, HBM-bound weight streaming): C[M,N] = act(A[M,K] W[N,K]^T + bias).
  * Used for the SE excitation MLP of the RegStage blocks (timm SEModule, projector.py:153-161) and the last-position
  * lm_head GEMV (HF:mistral/modeling_mistral.py:463-466 with logits_to_keep=1).  act_out: VL2_ACT_NONE/SILU or
- * 100 = sigmoid.  C is fp32 if out_f32 else bf16. A is fp32 if a_f32 else bf16. */
-int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, void* C, int out_f32, int M, int N,
-                    int K, int act, void* stream);
+ * 100 = sigmoid, or VL2_ACT_SWIGLU (interleaved gate/up rows -> N/2 outputs).  C is fp32 if out_f32 else bf16; A is fp32
+ * if a_f32 else bf16.  With M = 1 this is every linear layer of a KV-cache decode step (HBM-bound weight streaming). */
+int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, const void* residual /* bf16 [M,N] or NULL */,
+                    void* C, int out_f32, int M, int N, int K, int act, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused attention (FlashAttention-style, tcgen05 QK^T / PV with TMEM accumulators, TMA-staged K/V).
@@ -101,6 +102,12 @@ typedef struct vl2_attn_args {
   int32_t reserved;
 } vl2_attn_args;
 int vl2_attention(const vl2_attn_args* args, void* stream);
+
+/* Single-token decode attention over a KV cache (HF:mistral/modeling_mistral.py:122-177 with a DynamicCache):
+ * q bf16 [Hq*D]; k_cache / v_cache bf16 rows of ldkv elements (kv head h at columns [h*D, +D)), positions 0..n_pos-1;
+ * out bf16 [Hq*D]. */
+int vl2_attention_decode(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv, int n_pos,
+                         int Hq, int Hkv, int D, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row-wise normalisations (HBM-bound, one pass).

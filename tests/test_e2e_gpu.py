@@ -124,6 +124,28 @@ def test_full_forward_and_generate(setup, cuda):
     assert int(new[0, 0]) == int(out.logits[0, -1].argmax())                  # first new token = prefill argmax
 
 
+def test_kv_cache_decode_matches_recompute(setup, cuda):
+    """KV-cache decode (GEMV + single-token attention kernels) against re-running the prefill kernels on the grown
+    sequence, and against the oracle's greedy continuation computed in fp32 on the same weights."""
+    from oracle import torch_ref
+    cfg, sd, px, ids, gold, model = setup
+    imgs = [(px.to(cuda), "video")]
+    a = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=False, use_cache=True)
+    b = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=False, use_cache=False)
+    assert a.shape == (1, 5) and torch.equal(a, b)
+    # logits of the decode step agree with a full recompute of the same sequence
+    dec = model.get_model().decoder
+    emb = gold["inputs_embeds"].to(torch.bfloat16).to(cuda)
+    logits0, _ = dec.prefill(emb, all_logits=False, keep_cache=True, max_len=emb.shape[0] + 2)
+    tok = int(logits0[0].argmax())
+    e = model.get_model().embed_tokens(torch.tensor([tok]))
+    step = dec.decode_step(e)
+    full, _ = dec.prefill(torch.cat([emb, e], 0), all_logits=False)
+    assert rel(step, full) < 1e-2
+    ref = torch_ref.decoder_forward(sd, cfg.llm, torch.cat([emb.cpu(), e.cpu()], 0), torch.float32, all_logits=False)
+    assert rel(step, ref) < 1.5e-2
+
+
 def test_no_cpu_fallback(setup):
     from videollama2_b200._lib import Vl2Error
     cfg, sd, px, ids, gold, model = setup

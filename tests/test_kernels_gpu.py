@@ -249,3 +249,36 @@ def test_embed_splice_exact(cuda):
     assert torch.equal(out[0], table[5]) and torch.equal(out[1], table[999])
     assert torch.equal(out[50], table[0]) and torch.equal(out[51], table[17])
     assert (out[2:50] == 7.0).all()  # placeholder row and untouched rows stay as they were
+
+
+def test_skinny_gemm_residual_swiglu_out(cuda):
+    from videollama2_b200 import ops
+    x = rnd((1, 512), cuda, seed=50)
+    w = rnd((256, 512), cuda, 0.05, seed=51)
+    res = rnd((1, 256), cuda, seed=52)
+    out = ops.gemm_skinny(x, w, residual=res, out_dtype=torch.bfloat16)
+    assert relerr(out, x.float() @ w.float().t() + res.float()) < 4e-3
+    gate, up = rnd((96, 512), cuda, 0.05, seed=53), rnd((96, 512), cuda, 0.05, seed=54)
+    wgu = torch.stack([gate, up], 1).reshape(192, 512).contiguous()
+    h = ops.gemm_skinny(x, wgu, act=ops.ACT_SWIGLU, out_dtype=torch.bfloat16)
+    ref = torch.nn.functional.silu(x.float() @ gate.float().t()) * (x.float() @ up.float().t())
+    assert h.shape == (1, 96) and relerr(h, ref) < 5e-3
+    buf = torch.zeros((3, 256), device=cuda, dtype=torch.bfloat16)
+    ops.gemm_skinny(x, w, out=buf[1:2])
+    assert relerr(buf[1], (x.float() @ w.float().t())[0]) < 4e-3 and buf[0].abs().max() == 0 and buf[2].abs().max() == 0
+
+
+@pytest.mark.parametrize("n_pos,Hq,Hkv,D", [(1, 4, 2, 128), (37, 4, 2, 128), (1777, 32, 8, 128), (300, 4, 4, 64), (5000, 2, 1, 128)])
+def test_attention_decode(cuda, n_pos, Hq, Hkv, D):
+    from videollama2_b200 import ops
+    width = (Hq + 2 * Hkv) * D
+    cache = rnd((n_pos + 3, width), cuda, seed=55)
+    q = cache[n_pos - 1, : Hq * D].contiguous()
+    k = cache[:, Hq * D: (Hq + Hkv) * D]
+    v = cache[:, (Hq + Hkv) * D:]
+    out = ops.attention_decode(q, k, v, n_pos=n_pos, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5)
+    qf = q.float().view(Hq, 1, D)
+    kf = k[:n_pos].float().view(n_pos, Hkv, D).permute(1, 0, 2).repeat_interleave(Hq // Hkv, 0)
+    vf = v[:n_pos].float().view(n_pos, Hkv, D).permute(1, 0, 2).repeat_interleave(Hq // Hkv, 0)
+    ref = (torch.softmax(qf @ kf.transpose(1, 2) * D ** -0.5, -1) @ vf).reshape(1, Hq * D)
+    assert relerr(out, ref) < 6e-3

@@ -383,15 +383,13 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wv[j], acc[j]);
       }
     }
+    // one fused block reduction per pixel (sum, sum of squares): conv outputs are O(1), fp32 E[x^2]-mean^2 is safe here
     float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += acc[j];  // inactive threads hold zeros
-    const float mean = block_sum2(s, 0.f, red).x / (float)C;
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = acc[j] - mean; q += d * d; }
-    }
-    const float rstd = rsqrtf(block_sum2(q, 0.f, red).x / (float)C + eps);
+    for (int j = 0; j < 8; ++j) { s += acc[j]; q = fmaf(acc[j], acc[j], q); }  // inactive threads hold zeros
+    const float2 sq = block_sum2(s, q, red);
+    const float mean = sq.x / (float)C;
+    const float rstd = rsqrtf(fmaxf(sq.y / (float)C - mean * mean, 0.f) + eps);
     if (active) {
       float o[8], g[8], b[8];
       unpack8(gp, g);
@@ -527,7 +525,8 @@ static constexpr int kSkinnyNPW = 2;
 template <bool A_F32, int kSkinnyMB>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
-                   void* __restrict__ Cv, int out_f32, int M, int N, int K, int act, int KC) {
+                   const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cv, int out_f32, int M, int N, int K,
+                   int act, int KC) {
   extern __shared__ float sA[];  // [min(M,16)][KC]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * 8 + warp) * kSkinnyNPW;
@@ -586,19 +585,103 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
       }
     }
 #pragma unroll
-    for (int j = 0; j < kSkinnyNPW; ++j) {
+    for (int m = 0; m < kSkinnyMB; ++m) {
+      float r0 = warp_sum(acc[0][m]);
+      float r1 = warp_sum(acc[1][m]);
+      if (lane == 0 && m < mb && n0 < N) {
+        r0 += bias ? bias[n0] : 0.f;
+        if (n0 + 1 < N) r1 += bias ? bias[n0 + 1] : 0.f;
+        if (act == VL2_ACT_SWIGLU) {
+          // W rows interleave (gate, up): this warp's two columns are one pair -> one output column n0/2 of N/2
+          const float o = silu(r0) * r1;
+          const int64_t oi = (int64_t)(m0 + m) * (N / 2) + (n0 >> 1);
+          if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
+          else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
+        } else {
+          float r[2] = {r0, r1};
 #pragma unroll
-      for (int m = 0; m < kSkinnyMB; ++m) {
-        float r = warp_sum(acc[j][m]);
-        if (lane == 0 && m < mb && n0 + j < N) {
-          r += bias ? bias[n0 + j] : 0.f;
-          if (act == VL2_ACT_SILU) r = silu(r);
-          else if (act == 100) r = 1.f / (1.f + __expf(-r));
-          if (out_f32) reinterpret_cast<float*>(Cv)[(int64_t)(m0 + m) * N + n0 + j] = r;
-          else reinterpret_cast<__nv_bfloat16*>(Cv)[(int64_t)(m0 + m) * N + n0 + j] = __float2bfloat16_rn(r);
+          for (int j = 0; j < 2; ++j) {
+            if (n0 + j < N) {
+              float o = r[j];
+              if (act == VL2_ACT_SILU) o = silu(o);
+              else if (act == 100) o = 1.f / (1.f + __expf(-o));
+              const int64_t oi = (int64_t)(m0 + m) * N + n0 + j;
+              if (residual) o += __bfloat162float(residual[oi]);
+              if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
+              else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
+            }
+          }
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Single-token (decode) attention over a KV cache held as rows of the fused QKV buffer: one CTA per query head.
+//   phase 1: scores[pos] = scale * q . K[pos]   (warp per position, lanes split D)      -> smem
+//   phase 2: softmax statistics (block reduce)
+//   phase 3: out[d] = sum_pos p[pos] V[pos, d]  (thread per (d pair), position-strided groups, smem combine)
+// HBM-bound (reads K and V once per kv head group member); n_pos <= 16384.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
+                   const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int64_t ldkv, int n_pos,
+                   int group, int D, float scale) {
+  extern __shared__ float sc[];  // [n_pos] scores, then [4][D] partial outputs
+  __shared__ float red[64];
+  const int h = blockIdx.x, kvh = h / group;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int epl = D / 32;  // elements per lane (2 or 4)
+  float qf[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) qf[e] = (e < epl) ? __bfloat162float(q[h * D + lane * epl + e]) : 0.f;
+  for (int pos = warp; pos < n_pos; pos += 8) {
+    const __nv_bfloat16* kr = kc + (int64_t)pos * ldkv + kvh * D + lane * epl;
+    float d = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (e < epl) d = fmaf(qf[e], __bfloat162float(kr[e]), d);
+    d = warp_sum(d);
+    if (lane == 0) sc[pos] = d * scale;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int pos = threadIdx.x; pos < n_pos; pos += blockDim.x) mx = fmaxf(mx, sc[pos]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  float sum = 0.f;
+  for (int pos = threadIdx.x; pos < n_pos; pos += blockDim.x) {
+    const float pv = __expf(sc[pos] - mx);
+    sc[pos] = pv;
+    sum += pv;
+  }
+  const float total = block_sum2(sum, 0.f, red).x;  // includes the barriers that publish sc[]
+  // phase 3: 4 position groups x (D/2) threads, each thread owns an adjacent (d, d+1) pair
+  const int dp = D / 2;
+  const int grp = threadIdx.x / dp, t = threadIdx.x % dp;
+  const int ngrp = blockDim.x / dp;  // 4 for D=128, 8 for D=64
+  float o0 = 0.f, o1 = 0.f;
+  for (int pos = grp; pos < n_pos; pos += ngrp) {
+    const uint32_t vv = *reinterpret_cast<const uint32_t*>(vc + (int64_t)pos * ldkv + kvh * D + 2 * t);
+    const float pv = sc[pos];
+    o0 = fmaf(pv, bf16_lo(vv), o0);
+    o1 = fmaf(pv, bf16_hi(vv), o1);
+  }
+  float* part = sc + ((n_pos + 3) & ~3);
+  __syncthreads();
+  part[grp * D + 2 * t] = o0;
+  part[grp * D + 2 * t + 1] = o1;
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float a = 0.f;
+    for (int g = 0; g < ngrp; ++g) a += part[g * D + threadIdx.x];
+    out[h * D + threadIdx.x] = __float2bfloat16_rn(a / total);
   }
 }
 
@@ -738,25 +821,55 @@ extern "C" int vl2_embed_splice(const int64_t* ids, const int32_t* dst_row, int 
   return VL2_OK;
 }
 
-extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, void* C, int out_f32, int M,
-                               int N, int K, int act, void* stream) {
+extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, const void* residual, void* C,
+                               int out_f32, int M, int N, int K, int act, void* stream) {
   VL2_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 8 == 0, VL2_E_BADSHAPE,
               "vl2_gemm_skinny: need 0 < M <= 32 and K %% 8 == 0 (M=%d K=%d)", M, K);
   VL2_REQUIRE(aligned16(A) && aligned16(W), VL2_E_BADALIGN, "vl2_gemm_skinny: 16-byte alignment");
-  VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU || act == 100, VL2_E_UNSUPPORTED, "vl2_gemm_skinny: act %d", act);
+  VL2_REQUIRE(act == VL2_ACT_NONE || act == VL2_ACT_SILU || act == 100 || act == VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED,
+              "vl2_gemm_skinny: act %d", act);
+  VL2_REQUIRE(act != VL2_ACT_SWIGLU || (N % 2 == 0 && residual == nullptr), VL2_E_UNSUPPORTED,
+              "vl2_gemm_skinny: SWIGLU needs even N and no residual");
   const int MBT = M <= 2 ? 2 : 16;    // rows per pass (template instantiations)
   const int mb = M < MBT ? M : MBT;
-  int KC = (40 * 1024 / 4) / mb;      // <= 40 KB of staged A
+  // stage as much of A as 128 KB allows: few, long K chunks keep many 16-byte weight loads in flight per lane
+  int KC = (128 * 1024 / 4) / mb;
   KC = KC / 256 * 256;
-  if (KC > 2048) KC = 2048;
+  if (KC > 8192) KC = 8192;
   if (KC > K) KC = (K + 7) / 8 * 8;
   const size_t smem = (size_t)mb * KC * sizeof(float);
   const int blocks = (N + 8 * kSkinnyNPW - 1) / (8 * kSkinnyNPW);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr_set = true;
+  }
 #define VL2_SKINNY(AF, MB) \
-  gemm_skinny_kernel<AF, MB><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, C, out_f32, M, N, K, act, KC)
+  gemm_skinny_kernel<AF, MB><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act, KC)
   if (a_f32) { if (MBT == 2) VL2_SKINNY(true, 2); else VL2_SKINNY(true, 16); }
   else { if (MBT == 2) VL2_SKINNY(false, 2); else VL2_SKINNY(false, 16); }
 #undef VL2_SKINNY
   VL2_CHECK_LAUNCH("gemm_skinny_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_attention_decode(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv,
+                                    int n_pos, int Hq, int Hkv, int D, float scale, void* stream) {
+  VL2_REQUIRE(n_pos > 0 && n_pos <= 16384 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && (D == 64 || D == 128), VL2_E_BADSHAPE,
+              "vl2_attention_decode: bad shape (n_pos=%d Hq=%d Hkv=%d D=%d)", n_pos, Hq, Hkv, D);
+  const size_t smem = (size_t)(((n_pos + 3) & ~3) + (256 / (D / 2)) * D) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      attr = true;
+    }
+  }
+  attn_decode_kernel<<<Hq, 256, smem, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+                                                             (bf16*)out, ldkv, n_pos, Hq / Hkv, D, scale);
+  VL2_CHECK_LAUNCH("attn_decode_kernel");
   return VL2_OK;
 }

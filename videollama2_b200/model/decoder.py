@@ -92,3 +92,29 @@ class DecoderEngine:
             hn = ops.rmsnorm(x[S - 1:].contiguous(), self.w["norm"], self.eps)
             logits = ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
         return logits, x
+
+    # ---- KV-cache decode (one token) -----------------------------------------------------------------------
+    def decode_step(self, x: torch.Tensor) -> torch.Tensor:
+        """x [1,H] bf16 (embedding of the newest token) -> logits fp32 [1,V]; appends K/V at position kv_len.
+        Every linear layer is a weight-streaming GEMV (vl2_gemm_skinny), attention is vl2_attention_decode."""
+        if not self.kv:
+            raise RuntimeError("decode_step needs prefill(keep_cache=True) first")
+        pos = self.kv_len
+        if pos >= self.kv[0].shape[0]:
+            raise RuntimeError(f"KV cache full ({pos} positions)")
+        Hq, Hkv, D = self.Hq, self.Hkv, self.D
+        for i, L in enumerate(self.layers):
+            cache = self.kv[i]
+            y = ops.rmsnorm(x, L["g1"], self.eps)
+            row = cache[pos:pos + 1]
+            ops.gemm_skinny(y, L["wqkv"], bias=L.get("bqkv"), out=row)
+            ops.rope_inplace(row, 1, Hq, Hkv, D, 0, Hq * D, pos, self.w["inv_freq"])
+            o = ops.attention_decode(row[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
+                                     n_pos=pos + 1, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5)
+            x = ops.gemm_skinny(o, L["wo"], residual=x, out_dtype=torch.bfloat16)
+            y = ops.rmsnorm(x, L["g2"], self.eps)
+            h = ops.gemm_skinny(y, L["wgu"], act=ops.ACT_SWIGLU, out_dtype=torch.bfloat16)
+            x = ops.gemm_skinny(h, L["wd"], residual=x, out_dtype=torch.bfloat16)
+        self.kv_len = pos + 1
+        hn = ops.rmsnorm(x, self.w["norm"], self.eps)
+        return ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)

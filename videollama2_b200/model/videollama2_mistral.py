@@ -132,16 +132,22 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         dec = self.get_model().decoder
         x = inputs_embeds[0].to(torch.bfloat16).contiguous()
         new_ids: List[int] = []
-        # Round-1 decode: every step re-runs the prefill kernels on the grown sequence (exact, O(n^2));
-        # the KV-cache single-token path is the next row of the scope table.
-        for _ in range(max_new):
-            logits, _ = dec.prefill(x, all_logits=False)
+        # prefill once (keeps per-layer K/V), then one weight-streaming decode step per new token
+        use_cache = kwargs.get("use_cache", True)
+        S = x.shape[0]
+        logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache, max_len=S + max_new)
+        for step in range(max_new):
             tok = int(torch.argmax(logits[0]).item())
             new_ids.append(tok)
             out_ids = torch.tensor([new_ids], dtype=torch.long)
-            if tok in eos_ids or any(sc(out_ids, None) for sc in stopping):
+            if tok in eos_ids or any(sc(out_ids, None) for sc in stopping) or step == max_new - 1:
                 break
-            x = torch.cat([x, self.get_model().embed_tokens(torch.tensor([tok]))], 0)
+            e = self.get_model().embed_tokens(torch.tensor([tok]))
+            if use_cache:
+                logits = dec.decode_step(e)
+            else:   # exact but O(n^2): re-run the prefill kernels on the grown sequence
+                x = torch.cat([x, e], 0)
+                logits, _ = dec.prefill(x, all_logits=False)
         return torch.tensor([new_ids], dtype=torch.long, device=self.device)
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):

@@ -12,7 +12,7 @@ from ._lib import (ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_SIGMOID, ACT_SILU
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "layernorm", "rmsnorm", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "layernorm", "rmsnorm", "patch_im2col", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
@@ -75,9 +75,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 
 
 def gemm_skinny(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                 out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-    _need_cuda(a, w, bias)
-    _bf16(w)
+    """out[M,Nout] = act(a[M,K] @ w[N,K]^T + bias) (+ residual), M <= 32; weight-streaming (decode / SE / lm_head)."""
+    _need_cuda(a, w, bias, residual, out)
+    _bf16(w, residual)
     assert a.is_contiguous() and w.is_contiguous() and a.dim() == 2 and w.dim() == 2
     M, K = a.shape
     N = w.shape[0]
@@ -85,10 +87,29 @@ def gemm_skinny(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor
     assert a.dtype in (torch.float32, torch.bfloat16)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
-    out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
+    assert out.is_contiguous() and out.numel() == M * n_out and out.dtype in (torch.float32, torch.bfloat16)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.numel() == M * n_out
     check(_lib.load().vl2_gemm_skinny(a.data_ptr(), 1 if a.dtype == torch.float32 else 0, w.data_ptr(), _ptr(bias),
-                                      out.data_ptr(), 1 if out_dtype == torch.float32 else 0, M, N, K, act, _stream()),
-          "vl2_gemm_skinny")
+                                      _ptr(residual), out.data_ptr(), 1 if out.dtype == torch.float32 else 0, M, N, K,
+                                      act, _stream()), "vl2_gemm_skinny")
+    return out
+
+
+def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, *, n_pos: int, Hq: int, Hkv: int,
+                     D: int, scale: float) -> torch.Tensor:
+    """q [Hq*D]; k_cache / v_cache: row-strided views [>=n_pos, Hkv*D] of the per-layer cache."""
+    _need_cuda(q, k_cache, v_cache)
+    _bf16(q, k_cache, v_cache)
+    assert q.is_contiguous() and q.numel() == Hq * D and k_cache.stride(1) == 1 and v_cache.stride(1) == 1
+    assert k_cache.stride(0) == v_cache.stride(0) and k_cache.shape[0] >= n_pos
+    out = torch.empty((1, Hq * D), device=q.device, dtype=torch.bfloat16)
+    check(_lib.load().vl2_attention_decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+                                           k_cache.stride(0), n_pos, Hq, Hkv, D, float(scale), _stream()),
+          "vl2_attention_decode")
     return out
 
 
