@@ -186,6 +186,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     llm = presets.MISTRAL_7B if args.model == "mistral7b" else presets.QWEN2_7B
     cfg = presets.make_config(llm, FRAMES)

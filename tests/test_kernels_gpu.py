@@ -54,6 +54,35 @@ def test_gemm_every_tile_width(cuda, bn):
     assert relerr(out, ref) < 6e-3, bn
 
 
+@pytest.mark.parametrize("bn", [128, 160, 192, 224, 256])
+@pytest.mark.parametrize("M,N,K", [(1100, 2072, 328), (100, 512, 64), (130, 264, 136), (256, 256, 64), (9232, 1024, 192)])
+def test_gemm_cta_pair_kernel(cuda, bn, M, N, K):
+    """cta_group::2 kernel (two CTAs per 256 x BN tile): every width; persistent multi-tile loops; M tails where the
+    peer CTA's half is partly or entirely out of bounds; N/K tails."""
+    from videollama2_b200 import ops
+    a = rnd((M, K), cuda, seed=60)
+    w = rnd((N, K), cuda, 0.06, seed=61)
+    bias = torch.randn(N, device=cuda)
+    res = rnd((M, N), cuda, seed=62)
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_QUICK_GELU, residual=res, bn=1000 + bn)
+    x = a.float() @ w.float().t() + bias
+    ref = x * torch.sigmoid(1.702 * x) + res.float()
+    assert relerr(out, ref) < 6e-3, (bn, M, N, K)
+
+
+def test_gemm_cta_pair_swiglu_and_f32(cuda):
+    from videollama2_b200 import ops
+    M, I, K = 1776, 640, 256
+    a = rnd((M, K), cuda, seed=63)
+    gate, up = rnd((I, K), cuda, 0.1, seed=64), rnd((I, K), cuda, 0.1, seed=65)
+    w = torch.stack([gate, up], dim=1).reshape(2 * I, K).contiguous()
+    out = ops.gemm(a, w, act=ops.ACT_SWIGLU, bn=1256)
+    ref = torch.nn.functional.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    assert relerr(out, ref) < 8e-3
+    o32 = ops.gemm(a, gate, out_dtype=torch.float32, bn=1224)
+    assert relerr(o32, a.float() @ gate.float().t()) < 2e-3
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_gemm_epilogue(cuda, act, with_res):

@@ -11,6 +11,8 @@
 // BLOCK_K = 64 bf16 = one 128-byte swizzle atom; the grid is persistent
 // (<= #SMs CTAs, static round-robin over tiles, M fastest so that a wave shares W tiles through L2).
 // M/N/K tails: TMA zero-fills out-of-bounds reads, stores are predicated.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -22,11 +24,15 @@ static constexpr int kEpiWarps = 8;                       // 2 per TMEM lane qua
 static constexpr int kEpiThreads = kEpiWarps * 32;
 static constexpr int kGemmThreads = 128 + kEpiThreads;    // warps 0..3: TMA / MMA / TMEM alloc / spare
 
-template <int BN>
+// PAIR = true: two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 on a 256 x BN tile; each CTA stages its own
+// 128 rows of A and HALF of the B tile, so a k-block costs 16 KB + BN*64 B of smem/L2 traffic per CTA instead of
+// 16 KB + BN*128 B, and the ring is deep enough (6 stages at BN=256) to cover the L2/HBM latency at the full MMA rate.
+template <int BN, bool PAIR>
 struct GemmCfg {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 32 in [64,256]");
+  static constexpr int kRowsB = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
   static constexpr int kStageBytesA = BM * BK * 2;
-  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytesB = kRowsB * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
   static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias staging*/ + 256 /*barriers*/;
@@ -63,11 +69,15 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs), 1 = peer
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent tile loop start / stride
+  const int tile_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kTileM = PAIR ? 2 * BM : BM;
   // SWIZZLE_128B operands need 1024-byte aligned stage bases: the kernel has no static smem, so the dynamic window
   // starts at offset 0 of the CTA's shared memory (checked below; a misaligned base traps instead of corrupting).
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,16 +109,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiThreads);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues arrive on the leader's
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_base_ptr, Cfg::kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_base_ptr, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // barrier inits + TMEM address visible (cluster-wide for a pair)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_ptr;
 
@@ -117,26 +127,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.num_m_tiles) * BM;
-        const int n0 = (tile / p.num_m_tiles) * BN;
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+        const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
+        const int n0 = (tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (PAIR) {
+            // both CTAs' bytes land on the leader's full barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only for a pair) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue drained this accumulator stage
@@ -151,12 +168,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
       }
     }
   } else if (warp >= 4) {
@@ -176,10 +196,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int sw = lane & 7;                              // its swizzle key
     const int t_row = lane >> 3, t_chunk = lane & 7;      // transposed role: 8 lanes per row, 4 rows per instruction
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile % p.num_m_tiles) * BM;
+      const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
       const int n0 = (tile / p.num_m_tiles) * BN;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
@@ -296,21 +316,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // all tcgen05.ld of this thread have completed (wait::ld above) -> hand the accumulator stage back
       tmem_ld_wait();
       tc_fence_before_sync();
-      mbar_arrive(&tmem_empty[as]);
+      if (PAIR) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]);
     }
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // nobody may still be using the pair's TMEM / barriers
   if (warp == 2) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
@@ -322,50 +342,88 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)a->ldw * 2};
-    uint32_t box[2] = {BK, BN};
+    uint32_t box[2] = {BK, (uint32_t)Cfg::kRowsB};
     int rc = make_tmap_bf16(&tb, a->W, 2, dims, str, box);
     if (rc) return rc;
   }
   GemmParams p;
   p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
   p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
-  p.num_m_tiles = (a->M + BM - 1) / BM;
+  const int tile_m = PAIR ? 2 * BM : BM;
+  p.num_m_tiles = (a->M + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + BN - 1) / BN;
   static bool attr_set = false;
   if (!attr_set) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  const int slots = PAIR ? sm_count() / 2 : sm_count();
+  const int units = tiles < slots ? tiles : slots;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? 2 * units : units);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VL2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, PAIR>, ta, tb, p));
   VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return VL2_OK;
 }
 
-// Tile-width choice.  Model (fitted to ncu launch times, profiles/r01_launches_v2_summary.txt): one 128 x BN x 16 MMA
-// occupies the tensor pipe for ~BN/2 cycles; every k-block moves A (16 KB) + B (BN*128 B) into smem (TMA write) and out
-// again (MMA read) at ~190 B/cycle combined, so tiles narrower than 256 are smem-bound (BN=128 measured 1.38x slower
-// per flop than BN=256); a launch costs waves x tile time + one un-overlapped epilogue.  Ties go to the wider tile.
-static int choose_bn(int M, int N, int K, int sms) {
-  const int mt = (M + BM - 1) / BM;
+// Tile choice.  Cost model fitted to ncu launch times (profiles/r01_launches_v4_summary.txt):
+//   * one 128 x BN x 16 MMA occupies the tensor pipe for ~BN/2 cycles (same per CTA for a cta_group::2 pair);
+//   * every k-block moves A (16 KB) + the staged part of B into smem and out again at ~190 B/cycle combined;
+//   * the smem ring must cover the L2/HBM latency (~3000 cycles): a k-block cannot retire faster than L / stages
+//     (this is what holds the 4-stage 128x256 single-CTA tile at ~750 cycles per k-block = 83 % tensor-active);
+//   * a launch costs waves x tile time + one un-overlapped epilogue.
+struct TileChoice { int bn; bool pair; };
+
+static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair) {
   const int kb = (K + BK - 1) / BK;
+  const double L = 3000.0;
+  const int extra = 8 * 4096 + 2048 + 256;
   static const int cands[7] = {256, 224, 192, 160, 128, 96, 64};
-  int best = 256;
+  TileChoice best = {256, false};
   double best_cost = -1;
-  for (int i = 0; i < 7; ++i) {
-    const int bn = cands[i];
-    if (bn > 64 && N <= bn - 32) continue;  // do not pick a tile much wider than the matrix
-    const long tiles = (long)mt * ((N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    const double mma = 4.0 * (bn / 2.0);
-    const double smem = 2.0 * (16384.0 + bn * 128.0) / 190.0;
-    const double per_kb = mma > smem ? mma : smem;
-    const double cost = waves * (kb * per_kb + 600.0) + 2000.0 + bn * 16.0;
-    if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best = bn; }
+  for (int pair = (allow_pair ? 1 : 0); pair >= 0; --pair) {
+    for (int i = 0; i < 7; ++i) {
+      const int bn = cands[i];
+      if (pair && bn < 128) continue;
+      if (bn > 64 && N <= bn - 32) continue;  // do not pick a tile much wider than the matrix
+      const int tile_m = pair ? 256 : 128;
+      const long tiles = (long)((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
+      const long slots = pair ? sms / 2 : sms;
+      const long waves = (tiles + slots - 1) / slots;
+      const double stage_bytes = 16384.0 + (pair ? bn / 2 : bn) * 128.0;
+      int stages = (int)((227 * 1024 - extra) / stage_bytes);
+      if (stages > 8) stages = 8;
+      const double mma = 2.0 * bn;
+      const double smem = 2.0 * stage_bytes / 190.0;
+      const double lat = L / stages;
+      double per_kb = mma > smem ? mma : smem;
+      if (lat > per_kb) per_kb = lat;
+      const double cost = waves * (kb * per_kb + 600.0) + 2000.0 + bn * 16.0;
+      if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best.bn = bn; best.pair = pair != 0; }
+    }
   }
   return best;
+}
+
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VL2_GEMM_PAIR");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 }  // namespace vl2
@@ -389,15 +447,26 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
                 "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int bn = choose_bn(a->M, a->N, a->K, sm_count());
-  if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) bn = a->reserved;  // test hook: force a tile width
-  switch (bn) {
-    case 256: return launch_gemm<256>(a, st);
-    case 224: return launch_gemm<224>(a, st);
-    case 192: return launch_gemm<192>(a, st);
-    case 160: return launch_gemm<160>(a, st);
-    case 128: return launch_gemm<128>(a, st);
-    case 96: return launch_gemm<96>(a, st);
-    default: return launch_gemm<64>(a, st);
+  TileChoice t = choose_tile(a->M, a->N, a->K, sm_count(), pair_enabled());
+  // test hook: reserved = BN forces a single-CTA tile width, 1000 + BN forces the cta_group::2 pair kernel
+  if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) { t.bn = a->reserved; t.pair = false; }
+  if (a->reserved >= 1128 && a->reserved <= 1256 && (a->reserved - 1000) % 32 == 0) { t.bn = a->reserved - 1000; t.pair = true; }
+  if (t.pair) {
+    switch (t.bn) {
+      case 256: return launch_gemm<256, true>(a, st);
+      case 224: return launch_gemm<224, true>(a, st);
+      case 192: return launch_gemm<192, true>(a, st);
+      case 160: return launch_gemm<160, true>(a, st);
+      default: return launch_gemm<128, true>(a, st);
+    }
+  }
+  switch (t.bn) {
+    case 256: return launch_gemm<256, false>(a, st);
+    case 224: return launch_gemm<224, false>(a, st);
+    case 192: return launch_gemm<192, false>(a, st);
+    case 160: return launch_gemm<160, false>(a, st);
+    case 128: return launch_gemm<128, false>(a, st);
+    case 96: return launch_gemm<96, false>(a, st);
+    default: return launch_gemm<64, false>(a, st);
   }
 }
