@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -197,6 +198,8 @@ def main():
     model = VLLMs[cfg.model_type].from_state_dict(cfg, sd, device=dev)
     del sd
     torch.cuda.empty_cache()
+    if not args.no_graphs and not args.profile_one_step:
+        model.enable_cuda_graphs(True)
 
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     px_host = torch.randn((FRAMES, 3, 336, 336), generator=g).to(torch.bfloat16).pin_memory()
@@ -247,14 +250,20 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ops.launch_count()
     ms_step, t0, t1 = timed(step_resident, args.steps)
-    launches = (ops.launch_count() - l0) // args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # dominant-kernel roofline: every tcgen05 GEMM launch of one step bracketed by CUDA events on the launch stream
+    roof = None
+    model.enable_cuda_graphs(False)      # per-kernel event timing needs eager launches
+    l0 = ops.launch_count()
+    step_resident()                      # the same step launched eagerly: how many libvl2 kernels one step runs
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - l0
 
     # stage split (device events, same stream)
     def stage_times():
@@ -275,8 +284,6 @@ def main():
     t_vis = statistics.median(s[1] for s in st)      # ViT + STC + splice (encode_images_or_videos inside)
     t_llm = statistics.median(s[2] for s in st)
 
-    # dominant-kernel roofline: every tcgen05 GEMM launch of one step bracketed by CUDA events on the launch stream
-    roof = None
     if not args.no_kernel_profile and rank == 0:
         recs = []
         orig = ops.gemm
@@ -313,6 +320,8 @@ def main():
     # frame-parallel vision stage (strong scaling of ONE video): frames sharded over ranks + NCCL all-gather
     fp = None
     if world > 1:
+        if not args.no_graphs:
+            model.get_vision_tower().enable_cuda_graphs(True)
         fp = parallel.bench_frame_parallel(model, px_dev, rank, world, dev, iters=max(3, args.steps))
         fp["vit_1gpu_ms"] = t_vit
 
@@ -333,6 +342,7 @@ def main():
             "config": {"workload": f"VideoLLaMA2-7B ({args.model}) 16 frames@336 + 256-token prompt -> S={S} prefill, last-position logits; "
                                    "one video per GPU", "frames": FRAMES, "prompt": PROMPT, "seq": S, "global_batch": world,
                        "parallelism": f"replicas x{world} (+ frame-sharded ViT reported separately)",
+                       "cuda_graphs": not args.no_graphs,
                        "l2": "weights (16 GB) >> L2 (126 MB): every step streams them from HBM; no explicit flush",
                        "flops_per_step": fl["total"]},
             "frames_per_s": world * FRAMES / (t_vis * 1e-3), "vit_frames_per_s": world * FRAMES / (t_vit * 1e-3),

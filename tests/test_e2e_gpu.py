@@ -146,6 +146,29 @@ def test_kv_cache_decode_matches_recompute(setup, cuda):
     assert rel(step, ref) < 1.5e-2
 
 
+def test_cuda_graph_replay_is_bit_exact(setup, cuda):
+    """Graph-replayed stages (tower, connector, last-position prefill) must reproduce the eager launches bit for bit,
+    also on the second replay and after a different input went through the same graph."""
+    cfg, sd, px, ids, gold, model = setup
+    imgs = [(px.to(cuda), "video")]
+    eager_mm = model.encode_images_or_videos(imgs).clone()
+    eager_tok = model.generate(ids, images=imgs, max_new_tokens=1, do_sample=False)
+    model.enable_cuda_graphs(True)
+    try:
+        for _ in range(2):
+            assert torch.equal(model.encode_images_or_videos(imgs), eager_mm)
+            assert torch.equal(model.generate(ids, images=imgs, max_new_tokens=1, do_sample=False), eager_tok)
+        other = [((px * 0.5).to(cuda), "video")]
+        model.enable_cuda_graphs(False)
+        ref_other = model.encode_images_or_videos(other).clone()
+        model.enable_cuda_graphs(True)
+        model.encode_images_or_videos(imgs)
+        assert torch.equal(model.encode_images_or_videos(other), ref_other)
+        assert torch.equal(model.encode_images_or_videos(imgs), eager_mm)
+    finally:
+        model.enable_cuda_graphs(False)
+
+
 def test_no_cpu_fallback(setup):
     from videollama2_b200._lib import Vl2Error
     cfg, sd, px, ids, gold, model = setup

@@ -27,6 +27,16 @@ class DecoderEngine:
         self.is_loaded = False
         self.kv: List[torch.Tensor] = []   # per layer [S_max, (Hq+2Hkv)*D] fused qkv rows (K,V columns = cache)
         self.kv_len = 0
+        self._graphed = None
+
+    def enable_cuda_graphs(self, on: bool = True):
+        """Graph the cache-less last-position prefill (the bench / first-token path)."""
+        from ..graphs import GraphedStage
+        self._graphed = GraphedStage(lambda e: self._prefill_last(e)) if on else None
+        return self
+
+    def _prefill_last(self, embeds: torch.Tensor) -> torch.Tensor:
+        return self.prefill(embeds, all_logits=False, keep_cache=False, _no_graph=True)[0]
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device) -> "DecoderEngine":
         dev = torch.device(device)
@@ -72,10 +82,12 @@ class DecoderEngine:
         return ops.gemm(h, L["wd"], residual=x)
 
     def prefill(self, embeds: torch.Tensor, all_logits: bool = False, keep_cache: bool = False,
-                max_len: Optional[int] = None):
-        """embeds [S,H] bf16 -> (logits fp32 [S,V] or [1,V], final hidden [S,H])."""
+                max_len: Optional[int] = None, _no_graph: bool = False):
+        """embeds [S,H] bf16 -> (logits fp32 [S,V] or [1,V], final hidden [S,H] or None when graph-replayed)."""
         if not self.is_loaded:
             raise RuntimeError("DecoderEngine: weights not loaded")
+        if self._graphed is not None and not _no_graph and not all_logits and not keep_cache:
+            return self._graphed(embeds.contiguous()), None
         S = embeds.shape[0]
         x = embeds
         if keep_cache:

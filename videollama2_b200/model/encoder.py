@@ -40,6 +40,13 @@ class CLIPVisionTower:
         self._device = torch.device("cpu")
         self.w: Dict[str, torch.Tensor] = {}
         self.layers: List[Dict[str, torch.Tensor]] = []
+        self._graphed = None
+
+    def enable_cuda_graphs(self, on: bool = True):
+        """Replay the tower as one CUDA graph per input shape (see videollama2_b200/graphs.py)."""
+        from ..graphs import GraphedStage
+        self._graphed = GraphedStage(self._features) if on else None
+        return self
 
     # ---- weights -------------------------------------------------------------------------------------------
     @property
@@ -120,8 +127,12 @@ class CLIPVisionTower:
         if not images.is_cuda:
             raise ops._lib.Vl2Error("CLIPVisionTower needs CUDA tensors (no CPU fallback)")
         dt = images.dtype
-        feats = self.feature_select(self.hidden_states(images.to(torch.bfloat16))).contiguous()
+        x = images.to(torch.bfloat16).contiguous()
+        feats = self._graphed(x) if self._graphed is not None else self._features(x)
         return feats.to(dt)
+
+    def _features(self, images: torch.Tensor) -> torch.Tensor:
+        return self.feature_select(self.hidden_states(images)).contiguous()
 
     __call__ = forward
 

@@ -46,6 +46,12 @@ class STCConnector:
         self.blocks: Dict[str, List[Dict[str, torch.Tensor]]] = {"s1": [], "s2": []}
         self.w: Dict[str, torch.Tensor] = {}
         self.is_loaded = False
+        self._graphed = None
+
+    def enable_cuda_graphs(self, on: bool = True):
+        from ..graphs import GraphedStage
+        self._graphed = GraphedStage(lambda x: self._forward_one(x, None)) if on else None
+        return self
 
     # ---- weights -------------------------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device, prefix: str = "") -> "STCConnector":
@@ -154,7 +160,10 @@ class STCConnector:
         if out is None:
             out = torch.empty((b, n, self.output_hidden_size), device=x.device, dtype=torch.bfloat16)
         for i in range(b):
-            self._forward_one(x[i], out[i])
+            if self._graphed is not None:
+                out[i].copy_(self._graphed(x[i]))
+            else:
+                self._forward_one(x[i], out[i])
         return out.to(dt)
 
     __call__ = forward

@@ -64,6 +64,15 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
     def eval(self):
         return self
 
+    def enable_cuda_graphs(self, on: bool = True):
+        """Replay tower / connector / prefill as CUDA graphs (one per input shape)."""
+        m = self.model
+        if m.vision_tower is not None:
+            m.vision_tower.enable_cuda_graphs(on)
+            m.mm_projector.enable_cuda_graphs(on)
+        m.decoder.enable_cuda_graphs(on)
+        return self
+
     # ---- forward (videollama2_mistral.py:63-108) -----------------------------------------------------------------
     @torch.no_grad()
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
@@ -135,7 +144,7 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         # prefill once (keeps per-layer K/V), then one weight-streaming decode step per new token
         use_cache = kwargs.get("use_cache", True)
         S = x.shape[0]
-        logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache, max_len=S + max_new)
+        logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache and max_new > 1, max_len=S + max_new)
         for step in range(max_new):
             tok = int(torch.argmax(logits[0]).item())
             new_ids.append(tok)
