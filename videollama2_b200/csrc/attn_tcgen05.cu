@@ -1,22 +1,23 @@
 // FlashAttention-style fused attention for sm_100a (non-causal ViT heads and causal GQA decoder heads).
 //
-// One CTA = one 128-row query tile of one (batch, head).  192 threads:
-//   warps 0..3  softmax / output warps: thread r owns query row r (TMEM lane r) -> no cross-thread reductions
-//   warp 4      TMA producer (one lane): Q once, then K/V tiles of 128 keys into a 2-stage smem ring
-//   warp 5      TMEM allocator + MMA issuer (one lane):
-//                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
-//                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
-//                                     B = V tile as MN-major SW128 operand (no transpose pass needed)
-// Online softmax state (m, l) lives in registers of the row's thread; O accumulates in TMEM over all key tiles and is
-// rescaled in place only when a row maximum grows by more than 2^8 (lazy rescale).  S is read from TMEM once per tile.
-// QK^T of tile j+1 is issued before the softmax of tile j finishes, so tensor-core and MUFU work overlap.
+// One CTA = TWO 128-row query tiles (A, B) of one (batch, head), sharing every K/V tile.  320 threads:
+//   warps 0..3  softmax group A, warps 4..7 softmax group B: thread r of a group owns query row r of its tile
+//               (TMEM lane r) -> no cross-thread reductions; two warps per SM sub-partition hide each other's latency
+//   warp 8      TMA producer (one lane): Q_A, Q_B once, then K tiles (2-stage ring) and V tiles (1 or 2 stages)
+//   warp 9      TMEM allocator + MMA issuer (one lane), per key tile j and group g:
+//                 S_g = Q_g K_j^T     tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM
+//                 O_g += P_g V_j      tcgen05.mma 128xDx16,   A = P_g (bf16, written to smem by the group's warps),
+//                                     B = V tile as MN-major SW128 operand (no transpose pass); accumulates in TMEM
+// The issue order  PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)  staggers the groups: while group A runs its softmax the
+// tensor core works for group B and vice versa.  Online-softmax state (m, l) lives in registers; O is rescaled in place
+// in TMEM only when a row maximum grows by more than 2^8 (lazy rescale).  S is read from TMEM once per tile.
 #include "host_common.h"
 #include "ptx.cuh"
 
 namespace vl2 {
 
-static constexpr int kAttnThreads = 192;
-static constexpr int BQ = 128;
+static constexpr int kAttnThreads = 320;
+static constexpr int BQ = 128;   // rows per query tile (two tiles per CTA)
 static constexpr int BKV = 128;
 
 template <int D>
@@ -24,17 +25,19 @@ struct AttnCfg {
   static constexpr int kAtoms = D / 64;                 // 64-column (128-byte) swizzle atoms per row
   static constexpr int kTileBytes = BKV * D * 2;        // one Q / K / V tile
   static constexpr int kAtomBytes = 128 * 128;          // 128 rows x 128 B
-  static constexpr int kPBytes = BQ * BKV * 2;          // 32 KB
-  static constexpr int kOffQ = 0;
-  static constexpr int kOffK = kTileBytes;              // 2 stages
-  static constexpr int kOffV = 3 * kTileBytes;          // 2 stages
-  static constexpr int kOffP = 5 * kTileBytes;
-  static constexpr int kOffBar = kOffP + kPBytes;
+  static constexpr int kPBytes = BQ * BKV * 2;          // 32 KB per group
+  static constexpr int kVStages = (D == 64) ? 2 : 1;    // D=128: 2*Q + 2*K + 1*V + 2*P = 224 KB
+  static constexpr int kOffQ = 0;                       // [2] tiles
+  static constexpr int kOffK = 2 * kTileBytes;          // [2] stages
+  static constexpr int kOffV = 4 * kTileBytes;          // [kVStages]
+  static constexpr int kOffP = (4 + kVStages) * kTileBytes;   // [2] groups
+  static constexpr int kOffBar = kOffP + 2 * kPBytes;
   static constexpr int kSmemUsed = kOffBar + 256;
   // at least 116 KB so that only one CTA is resident per SM (each CTA allocates all 512 TMEM columns)
-  static constexpr int kSmemBytes = (kSmemUsed + 1024 > 116 * 1024) ? (kSmemUsed + 1024) : 116 * 1024;
+  static constexpr int kSmemBytes = kSmemUsed > 116 * 1024 ? kSmemUsed : 116 * 1024;
   static constexpr int kTmemCols = 512;
-  static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
+  static constexpr int kColS = 0;     // S_A at 0, S_B at 128
+  static constexpr int kColO = 256;   // O_A at 256, O_B at 256 + D
 };
 
 struct AttnParams {
@@ -46,52 +49,62 @@ struct AttnParams {
 };
 
 template <int D>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __maxnreg__(200)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
   uint8_t* sQ = smem + Cfg::kOffQ;
   uint8_t* sK = smem + Cfg::kOffK;
   uint8_t* sV = smem + Cfg::kOffV;
-  uint8_t* sP = smem + Cfg::kOffP;
+  uint8_t* sPall = smem + Cfg::kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* v_full = bars + 3;    // [2]
-  uint64_t* kv_empty = bars + 5;  // [2]
-  uint64_t* s_full = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] per group
+  uint64_t* p_full = bars + 11;   // [2] per group
+  uint64_t* o_full = bars + 13;   // [2] per group
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // heavy (late) causal tiles first
-  const int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  // heavy (late) causal tile pairs first
+  const int qp = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int kvh = head / p.group;
-  const int q0 = qt * BQ;
-  const int n_kv = p.causal ? (qt + 1) : (p.S + BKV - 1) / BKV;
+  const int q0 = qp * 2 * BQ;
+  const int n_tiles_total = (p.S + BKV - 1) / BKV;
+  // key tiles each group needs (0 = the group's query tile lies entirely past the sequence)
+  int n_kv[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int qt = 2 * qp + g;
+    n_kv[g] = (qt * BQ >= p.S) ? 0 : (p.causal ? (qt + 1) : n_tiles_total);
+  }
+  const int n_max = n_kv[0] > n_kv[1] ? n_kv[0] : n_kv[1];
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -100,86 +113,103 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
+      mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
 #pragma unroll
-      for (int a = 0; a < Cfg::kAtoms; ++a)
-        tma_load_3d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, head * D + a * 64, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
+      for (int g = 0; g < 2; ++g)
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
-          tma_load_3d(sK + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[st], kvh * D + a * 64, j * BKV, b);
-        mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
+          tma_load_3d(sQ + g * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_q, q_full, head * D + a * 64, q0 + g * BQ, b);
+      for (int j = 0; j < n_max; ++j) {
+        const int ks = j & 1;
+        mbar_wait(&k_empty[ks], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
-          tma_load_3d(sV + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[st], kvh * D + a * 64, j * BKV, b);
+          tma_load_3d(sK + ks * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[ks], kvh * D + a * 64, j * BKV, b);
+        const int vs = j % Cfg::kVStages;
+        const uint32_t vph = (j / Cfg::kVStages) & 1;
+        mbar_wait(&v_empty[vs], vph ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_3d(sV + vs * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[vs], kvh * D + a * 64, j * BKV, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
-        tc_fence_after_sync();
-        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
-        const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
+      auto issue_qk = [&](int g, int j) {  // S_g = Q_g K_j^T ; K_j must have landed (caller waited)
+        const uint32_t q_addr = smem_u32(sQ + g * Cfg::kTileBytes);
+        const uint32_t k_addr = smem_u32(sK + (j & 1) * Cfg::kTileBytes);
+        const uint32_t d_tmem = tmem_base + Cfg::kColS + g * 128;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32;
           umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + off, 16, 1024), umma_desc_sw128(k_addr + off, 16, 1024),
                        idesc_qk, kk != 0);
         }
-        umma_commit(&s_full[st]);
+        umma_commit(&s_full[g]);
       };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
-        tc_fence_after_sync();
-        const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
+      auto issue_pv = [&](int g, int j) {  // O_g += P_g V_j
+        const uint32_t p_addr = smem_u32(sPall + g * Cfg::kPBytes);
+        const uint32_t v_addr = smem_u32(sV + (j % Cfg::kVStages) * Cfg::kTileBytes);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
           // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
           const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
-          umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
+          umma_bf16_ss(tmem_base + Cfg::kColO + g * D, da, db, idesc_pv, (j | kk) != 0);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&o_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after_sync();
+      if (n_kv[0] > 0) issue_qk(0, 0);
+      if (n_kv[1] > 0) issue_qk(1, 0);
+      umma_commit(&k_empty[0]);   // (K_0 is re-read by nobody else; stage reusable once these MMAs finish)
+      for (int j = 0; j < n_max; ++j) {
+        bool v_ready = false, k_ready = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (j < n_kv[g]) {
+            mbar_wait(&p_full[g], j & 1);
+            if (!v_ready) { mbar_wait(&v_full[j % Cfg::kVStages], (j / Cfg::kVStages) & 1); v_ready = true; }
+            tc_fence_after_sync();
+            issue_pv(g, j);
+            if (j + 1 < n_kv[g]) {
+              if (!k_ready) { mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1); k_ready = true; }
+              tc_fence_after_sync();
+              issue_qk(g, j + 1);
+            }
+          }
+        }
+        umma_commit(&v_empty[j % Cfg::kVStages]);           // V_j free once both groups' P V have read it
+        if (j + 1 < n_max) umma_commit(&k_empty[(j + 1) & 1]);  // K_{j+1} free once both groups' Q K^T have read it
       }
     }
   } else {
-    // ===================== softmax / output warps (thread == query row) =====================
-    // One TMEM pass over S per tile; O accumulates in TMEM across tiles (tcgen05.mma accumulate) and is rescaled
-    // in place only when a row maximum grows by more than 2^8 (lazy rescale: probabilities stay <= 256, exact after
-    // the final division by l).
-    const int r = warp * 32 + lane;
-    const int qi = q0 + r;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO;
+    // ===================== softmax / output warps (thread == query row of its group's tile) =====================
+    const int g = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const int qi = q0 + g * BQ + r;
+    const int nk = n_kv[g];
+    uint8_t* sP = sPall + g * Cfg::kPBytes;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t s_taddr = tmem_base + lane_sel + Cfg::kColS + g * 128;
+    const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO + g * D;
     float m = -INFINITY, l = 0.f;
     constexpr float kRescaleThreshold = 8.f;
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1;
-      const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0);
+    for (int j = 0; j < nk; ++j) {
       const int kv0 = j * BKV;
-      const bool need_mask = (kv0 + BKV > p.S) || (p.causal && (kv0 + BKV - 1 > q0));
-      mbar_wait(&s_full[st], (j >> 1) & 1);
+      const bool need_mask = (kv0 + BKV > p.S) || (p.causal && (kv0 + BKV - 1 > q0 + g * BQ));
+      mbar_wait(&s_full[g], j & 1);
       tc_fence_after_sync();
       uint32_t sv[4][32];
 #pragma unroll
@@ -211,7 +241,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       // the previous P V must be complete before P (smem) is overwritten or O (TMEM) is rescaled
       if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+        mbar_wait(&o_full[g], (j - 1) & 1);
         tc_fence_after_sync();
         if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
@@ -235,14 +265,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { rs0 += pr[i]; rs1 += pr[i + 1]; rs2 += pr[i + 2]; rs3 += pr[i + 3]; }
-        // 32 columns = 4 chunks of 16 B inside atom (c >> 1), chunk index (c & 1) * 4 + g
+        // 32 columns = 4 chunks of 16 B inside atom (c >> 1), chunk index (c & 1) * 4 + q
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = (c & 1) * 4 + g;
-          uint8_t* dst = sP + (c >> 1) * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) =
-              make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
-                         pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (c & 1) * 4 + q;
+          sts128(smem_u32(sP) + (c >> 1) * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4),
+                 make_uint4(pack_bf16(pr[q * 8 + 0], pr[q * 8 + 1]), pack_bf16(pr[q * 8 + 2], pr[q * 8 + 3]),
+                            pack_bf16(pr[q * 8 + 4], pr[q * 8 + 5]), pack_bf16(pr[q * 8 + 6], pr[q * 8 + 7])));
         }
       }
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
@@ -250,25 +279,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[g]);
     }
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after_sync();
-    const float inv = 1.f / l;
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
+    if (nk > 0) {
+      mbar_wait(&o_full[g], (nk - 1) & 1);
+      tc_fence_after_sync();
+      const float inv = 1.f / l;
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t ov[32];
-      tmem_ld_32x32(o_taddr + c * 32, ov);
-      tmem_ld_wait();
-      if (qi < p.S) {
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32(o_taddr + c * 32, ov);
+        tmem_ld_wait();
+        if (qi < p.S) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(
-              pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv),
-              pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv),
-              pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv),
-              pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv));
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = make_uint4(
+                pack_bf16(__uint_as_float(ov[q * 8 + 0]) * inv, __uint_as_float(ov[q * 8 + 1]) * inv),
+                pack_bf16(__uint_as_float(ov[q * 8 + 2]) * inv, __uint_as_float(ov[q * 8 + 3]) * inv),
+                pack_bf16(__uint_as_float(ov[q * 8 + 4]) * inv, __uint_as_float(ov[q * 8 + 5]) * inv),
+                pack_bf16(__uint_as_float(ov[q * 8 + 6]) * inv, __uint_as_float(ov[q * 8 + 7]) * inv));
+          }
         }
       }
     }
@@ -276,7 +307,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -313,7 +344,7 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((a->S + BQ - 1) / BQ, a->Hq, a->B);
+  dim3 grid((a->S + 2 * BQ - 1) / (2 * BQ), a->Hq, a->B);
   attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   VL2_CHECK_LAUNCH("attn_fwd_kernel");
   return VL2_OK;
