@@ -518,16 +518,17 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32
 // Skinny GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias), M <= 32.  One warp per output column n; W streams once from
 // HBM (16-byte loads), A (tiny) is re-read from L1/L2.
 // ---------------------------------------------------------------------------------------------------------
-// CTA = 8 warps x 2 output columns; the (tiny) A matrix is staged through smem in K chunks as fp32 so that W streams
-// from HBM exactly once and A costs L2 traffic only once per CTA.
-static constexpr int kSkinnyNPW = 2;
+// CTA = 8 warps x 4 output columns; the (tiny) A matrix is staged through smem in long K chunks as bf16 so that W
+// streams from HBM exactly once, A costs L2 traffic once per CTA, and one 16-byte LDS of A feeds 4 columns x 8 FMAs.
+static constexpr int kSkinnyNPW = 4;
 
 template <bool A_F32, int kSkinnyMB>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
                    const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cv, int out_f32, int M, int N, int K,
                    int act, int KC) {
-  extern __shared__ float sA[];  // [min(M,16)][KC]
+  extern __shared__ __align__(16) uint8_t sA_raw[];  // [min(M,MB)][KC] bf16
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(sA_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * 8 + warp) * kSkinnyNPW;
   for (int m0 = 0; m0 < M; m0 += kSkinnyMB) {
@@ -542,21 +543,19 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
       __syncthreads();
       for (int idx = threadIdx.x; idx < mb * (kc / 8); idx += blockDim.x) {
         const int m = idx / (kc / 8), v = idx % (kc / 8);
-        float a[8];
+        uint4 packed;
         if (A_F32) {
           const float* ar = reinterpret_cast<const float*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8;
           const float4 a0 = *reinterpret_cast<const float4*>(ar), a1 = *reinterpret_cast<const float4*>(ar + 4);
-          a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+          packed = make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
         } else {
-          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8), a);
+          packed = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8);
         }
-        float* d = sA + m * KC + v * 8;
-        *reinterpret_cast<float4*>(d) = make_float4(a[0], a[1], a[2], a[3]);
-        *reinterpret_cast<float4*>(d + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        *reinterpret_cast<uint4*>(sA + m * KC + v * 8) = packed;
       }
       __syncthreads();
       if (n0 < N) {
-#pragma unroll 4
+#pragma unroll 2
         for (int v = lane; v < kc / 8; v += 32) {
           float w[kSkinnyNPW][8];
 #pragma unroll
@@ -570,15 +569,12 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
 #pragma unroll
           for (int m = 0; m < kSkinnyMB; ++m) {
             if (m < mb) {
-              const float4 a0 = *reinterpret_cast<const float4*>(sA + m * KC + v * 8);
-              const float4 a1 = *reinterpret_cast<const float4*>(sA + m * KC + v * 8 + 4);
+              float a[8];
+              unpack8(*reinterpret_cast<const uint4*>(sA + m * KC + v * 8), a);
 #pragma unroll
-              for (int j = 0; j < kSkinnyNPW; ++j) {
-                acc[j][m] = fmaf(a0.x, w[j][0], acc[j][m]); acc[j][m] = fmaf(a0.y, w[j][1], acc[j][m]);
-                acc[j][m] = fmaf(a0.z, w[j][2], acc[j][m]); acc[j][m] = fmaf(a0.w, w[j][3], acc[j][m]);
-                acc[j][m] = fmaf(a1.x, w[j][4], acc[j][m]); acc[j][m] = fmaf(a1.y, w[j][5], acc[j][m]);
-                acc[j][m] = fmaf(a1.z, w[j][6], acc[j][m]); acc[j][m] = fmaf(a1.w, w[j][7], acc[j][m]);
-              }
+              for (int j = 0; j < kSkinnyNPW; ++j)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[j][m] = fmaf(a[e], w[j][e], acc[j][m]);
             }
           }
         }
@@ -586,21 +582,27 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
     }
 #pragma unroll
     for (int m = 0; m < kSkinnyMB; ++m) {
-      float r0 = warp_sum(acc[0][m]);
-      float r1 = warp_sum(acc[1][m]);
-      if (lane == 0 && m < mb && n0 < N) {
-        r0 += bias ? bias[n0] : 0.f;
-        if (n0 + 1 < N) r1 += bias ? bias[n0 + 1] : 0.f;
-        if (act == VL2_ACT_SWIGLU) {
-          // W rows interleave (gate, up): this warp's two columns are one pair -> one output column n0/2 of N/2
-          const float o = silu(r0) * r1;
-          const int64_t oi = (int64_t)(m0 + m) * (N / 2) + (n0 >> 1);
-          if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
-          else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
-        } else {
-          float r[2] = {r0, r1};
+      float r[kSkinnyNPW];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < kSkinnyNPW; ++j) r[j] = warp_sum(acc[j][m]);
+      if (lane == 0 && m < mb && n0 < N) {
+#pragma unroll
+        for (int j = 0; j < kSkinnyNPW; ++j)
+          if (n0 + j < N && bias) r[j] += bias[n0 + j];
+        if (act == VL2_ACT_SWIGLU) {
+          // W rows interleave (gate, up): columns (n0, n0+1) and (n0+2, n0+3) are pairs -> outputs n0/2, n0/2+1 of N/2
+#pragma unroll
+          for (int pj = 0; pj < kSkinnyNPW / 2; ++pj) {
+            if (n0 + 2 * pj + 1 < N) {
+              const float o = silu(r[2 * pj]) * r[2 * pj + 1];
+              const int64_t oi = (int64_t)(m0 + m) * (N / 2) + (n0 >> 1) + pj;
+              if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
+              else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kSkinnyNPW; ++j) {
             if (n0 + j < N) {
               float o = r[j];
               if (act == VL2_ACT_SILU) o = silu(o);
@@ -832,19 +834,19 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
               "vl2_gemm_skinny: SWIGLU needs even N and no residual");
   const int MBT = M <= 2 ? 2 : 16;    // rows per pass (template instantiations)
   const int mb = M < MBT ? M : MBT;
-  // stage as much of A as 128 KB allows: few, long K chunks keep many 16-byte weight loads in flight per lane
-  int KC = (128 * 1024 / 4) / mb;
+  // stage A (as bf16) in long K chunks: few chunks keep many 16-byte weight loads in flight per lane
+  int KC = (64 * 1024 / 2) / mb;
   KC = KC / 256 * 256;
   if (KC > 8192) KC = 8192;
   if (KC > K) KC = (K + 7) / 8 * 8;
-  const size_t smem = (size_t)mb * KC * sizeof(float);
+  const size_t smem = (size_t)mb * KC * sizeof(__nv_bfloat16);
   const int blocks = (N + 8 * kSkinnyNPW - 1) / (8 * kSkinnyNPW);
   static bool attr_set = false;
   if (!attr_set) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
 #define VL2_SKINNY(AF, MB) \
