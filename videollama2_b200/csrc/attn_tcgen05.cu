@@ -49,7 +49,7 @@ struct AttnParams {
 };
 
 template <int D>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<D>;
