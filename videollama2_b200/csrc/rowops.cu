@@ -518,99 +518,103 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32
 // Skinny GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias), M <= 32.  One warp per output column n; W streams once from
 // HBM (16-byte loads), A (tiny) is re-read from L1/L2.
 // ---------------------------------------------------------------------------------------------------------
-// CTA = 8 warps x 4 output columns; the (tiny) A matrix is staged through smem in long K chunks as bf16 so that W
-// streams from HBM exactly once, A costs L2 traffic once per CTA, and one 16-byte LDS of A feeds 4 columns x 8 FMAs.
-static constexpr int kSkinnyNPW = 4;
+// Skinny GEMM on the legacy tensor path (mma.sync m16n8k16, bf16 -> fp32): the whole A matrix (M <= 16 rows) is one
+// m16 tile, so a warp streams W rows with 16-byte loads and multiplies them against A fragments it reads straight from
+// L2 (A is a few hundred KB).  CTA = 16 output columns; its 8 warps split K and reduce through smem.  The k index is
+// permuted consistently for A and B so that one 16-byte load supplies two k16 steps (lane quad q holds physical
+// k = 32*kb + 8q .. 8q+7).  HBM-bound on W; this is the SE excitation MLP and every linear layer of a decode step.
+static constexpr int kSkinnyNT8 = 2;  // n8 tiles per CTA
 
-template <bool A_F32, int kSkinnyMB>
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <bool A_F32>
+__device__ __forceinline__ uint4 skinny_load_a(const void* A, int row, int M, int64_t K, int k) {
+  if (row >= M) return make_uint4(0, 0, 0, 0);
+  if (A_F32) {
+    const float* ar = reinterpret_cast<const float*>(A) + (int64_t)row * K + k;
+    const float4 x = *reinterpret_cast<const float4*>(ar), y = *reinterpret_cast<const float4*>(ar + 4);
+    return make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+  }
+  return *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(A) + (int64_t)row * K + k);
+}
+
+template <bool A_F32>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
                    const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cv, int out_f32, int M, int N, int K,
-                   int act, int KC) {
-  extern __shared__ __align__(16) uint8_t sA_raw[];  // [min(M,MB)][KC] bf16
-  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(sA_raw);
+                   int act) {
+  __shared__ float red[8][kSkinnyNT8][4][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 8 + warp) * kSkinnyNPW;
-  for (int m0 = 0; m0 < M; m0 += kSkinnyMB) {
-    const int mb = min(kSkinnyMB, M - m0);
-    float acc[kSkinnyNPW][kSkinnyMB];
+  const int g = lane >> 2, q = lane & 3;
+  const int n_base = blockIdx.x * (8 * kSkinnyNT8);
+  const int nkb = (K + 31) / 32;
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    float acc[kSkinnyNT8][4];
 #pragma unroll
-    for (int j = 0; j < kSkinnyNPW; ++j)
+    for (int t = 0; t < kSkinnyNT8; ++t)
 #pragma unroll
-      for (int m = 0; m < kSkinnyMB; ++m) acc[j][m] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += KC) {
-      const int kc = min(KC, K - k0);
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < mb * (kc / 8); idx += blockDim.x) {
-        const int m = idx / (kc / 8), v = idx % (kc / 8);
-        uint4 packed;
-        if (A_F32) {
-          const float* ar = reinterpret_cast<const float*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8;
-          const float4 a0 = *reinterpret_cast<const float4*>(ar), a1 = *reinterpret_cast<const float4*>(ar + 4);
-          packed = make_uint4(pack_bf16(a0.x, a0.y), pack_bf16(a0.z, a0.w), pack_bf16(a1.x, a1.y), pack_bf16(a1.z, a1.w));
-        } else {
-          packed = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + (int64_t)(m0 + m) * K + k0 + v * 8);
-        }
-        *reinterpret_cast<uint4*>(sA + m * KC + v * 8) = packed;
-      }
-      __syncthreads();
-      if (n0 < N) {
-#pragma unroll 2
-        for (int v = lane; v < kc / 8; v += 32) {
-          float w[kSkinnyNPW][8];
+      for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll 4
+    for (int kb = warp; kb < nkb; kb += 8) {
+      const int k = kb * 32 + q * 8;
+      const bool k_ok = k < K;
+      const uint4 a_lo = k_ok ? skinny_load_a<A_F32>(Av, m0 + g, M, K, k) : make_uint4(0, 0, 0, 0);
+      const uint4 a_hi = k_ok ? skinny_load_a<A_F32>(Av, m0 + g + 8, M, K, k) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int j = 0; j < kSkinnyNPW; ++j) {
-            if (n0 + j < N) unpack8(__ldg(reinterpret_cast<const uint4*>(Wt + (int64_t)(n0 + j) * K + k0) + v), w[j]);
-            else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w[j][e] = 0.f;
-            }
-          }
-#pragma unroll
-          for (int m = 0; m < kSkinnyMB; ++m) {
-            if (m < mb) {
-              float a[8];
-              unpack8(*reinterpret_cast<const uint4*>(sA + m * KC + v * 8), a);
-#pragma unroll
-              for (int j = 0; j < kSkinnyNPW; ++j)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[j][m] = fmaf(a[e], w[j][e], acc[j][m]);
-            }
-          }
-        }
+      for (int t = 0; t < kSkinnyNT8; ++t) {
+        const int n = n_base + t * 8 + g;
+        uint4 bw = make_uint4(0, 0, 0, 0);
+        if (k_ok && n < N) bw = __ldg(reinterpret_cast<const uint4*>(Wt + (int64_t)n * K + k));
+        mma_bf16_16816(acc[t], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bw.x, bw.y);
+        mma_bf16_16816(acc[t], a_lo.z, a_hi.z, a_lo.w, a_hi.w, bw.z, bw.w);
       }
     }
+    __syncthreads();  // red[] is reused across m0 passes
 #pragma unroll
-    for (int m = 0; m < kSkinnyMB; ++m) {
-      float r[kSkinnyNPW];
+    for (int t = 0; t < kSkinnyNT8; ++t)
 #pragma unroll
-      for (int j = 0; j < kSkinnyNPW; ++j) r[j] = warp_sum(acc[j][m]);
-      if (lane == 0 && m < mb && n0 < N) {
+      for (int e = 0; e < 4; ++e) red[warp][t][e][lane] = acc[t][e];
+    __syncthreads();
+    if (warp < kSkinnyNT8) {
+      const int t = warp;
+      float c[4];
 #pragma unroll
-        for (int j = 0; j < kSkinnyNPW; ++j)
-          if (n0 + j < N && bias) r[j] += bias[n0 + j];
-        if (act == VL2_ACT_SWIGLU) {
-          // W rows interleave (gate, up): columns (n0, n0+1) and (n0+2, n0+3) are pairs -> outputs n0/2, n0/2+1 of N/2
+      for (int e = 0; e < 4; ++e) {
+        float v = 0.f;
 #pragma unroll
-          for (int pj = 0; pj < kSkinnyNPW / 2; ++pj) {
-            if (n0 + 2 * pj + 1 < N) {
-              const float o = silu(r[2 * pj]) * r[2 * pj + 1];
-              const int64_t oi = (int64_t)(m0 + m) * (N / 2) + (n0 >> 1) + pj;
-              if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
-              else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
-            }
-          }
-        } else {
+        for (int w = 0; w < 8; ++w) v += red[w][t][e][lane];
+        c[e] = v;
+      }
+      const int n = n_base + t * 8 + q * 2;  // c0,c1: (row g, cols n, n+1); c2,c3: (row g+8, cols n, n+1)
 #pragma unroll
-          for (int j = 0; j < kSkinnyNPW; ++j) {
-            if (n0 + j < N) {
-              float o = r[j];
-              if (act == VL2_ACT_SILU) o = silu(o);
-              else if (act == 100) o = 1.f / (1.f + __expf(-o));
-              const int64_t oi = (int64_t)(m0 + m) * N + n0 + j;
-              if (residual) o += __bfloat162float(residual[oi]);
-              if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
-              else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
+      for (int h = 0; h < 2; ++h) {
+        const int row = m0 + g + 8 * h;
+        if (row < M && n < N) {
+          float r0 = c[2 * h], r1 = c[2 * h + 1];
+          if (bias) { r0 += bias[n]; if (n + 1 < N) r1 += bias[n + 1]; }
+          if (act == VL2_ACT_SWIGLU) {  // (n, n+1) is a (gate, up) pair -> output column n/2 of N/2
+            const float o = silu(r0) * r1;
+            const int64_t oi = (int64_t)row * (N / 2) + (n >> 1);
+            if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
+            else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
+          } else {
+            float r[2] = {r0, r1};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (n + j < N) {
+                float o = r[j];
+                if (act == VL2_ACT_SILU) o = silu(o);
+                else if (act == 100) o = 1.f / (1.f + __expf(-o));
+                const int64_t oi = (int64_t)row * N + n + j;
+                if (residual) o += __bfloat162float(residual[oi]);
+                if (out_f32) reinterpret_cast<float*>(Cv)[oi] = o;
+                else reinterpret_cast<__nv_bfloat16*>(Cv)[oi] = __float2bfloat16_rn(o);
+              }
             }
           }
         }
@@ -832,28 +836,11 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
               "vl2_gemm_skinny: act %d", act);
   VL2_REQUIRE(act != VL2_ACT_SWIGLU || (N % 2 == 0 && residual == nullptr), VL2_E_UNSUPPORTED,
               "vl2_gemm_skinny: SWIGLU needs even N and no residual");
-  const int MBT = M <= 2 ? 2 : 16;    // rows per pass (template instantiations)
-  const int mb = M < MBT ? M : MBT;
-  // stage A (as bf16) in long K chunks: few chunks keep many 16-byte weight loads in flight per lane
-  int KC = (64 * 1024 / 2) / mb;
-  KC = KC / 256 * 256;
-  if (KC > 8192) KC = 8192;
-  if (KC > K) KC = (K + 7) / 8 * 8;
-  const size_t smem = (size_t)mb * KC * sizeof(__nv_bfloat16);
-  const int blocks = (N + 8 * kSkinnyNPW - 1) / (8 * kSkinnyNPW);
-  static bool attr_set = false;
-  if (!attr_set) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
-#define VL2_SKINNY(AF, MB) \
-  gemm_skinny_kernel<AF, MB><<<blocks, 256, smem, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act, KC)
-  if (a_f32) { if (MBT == 2) VL2_SKINNY(true, 2); else VL2_SKINNY(true, 16); }
-  else { if (MBT == 2) VL2_SKINNY(false, 2); else VL2_SKINNY(false, 16); }
-#undef VL2_SKINNY
+  const int blocks = (N + 8 * kSkinnyNT8 - 1) / (8 * kSkinnyNT8);
+  if (a_f32)
+    gemm_skinny_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act);
+  else
+    gemm_skinny_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act);
   VL2_CHECK_LAUNCH("gemm_skinny_kernel");
   return VL2_OK;
 }
