@@ -2,7 +2,8 @@
 //
 // One CTA = one 128-row query tile of one (batch, head).  192 threads:
 //   warps 0..3  softmax / output warps: thread r owns query row r (TMEM lane r) -> no cross-thread reductions
-//   warp 4      TMA producer (one lane): Q once, then K/V tiles of 128 keys into a 2-stage smem ring
+//   warp 4      TMA producers: lane 0 loads Q and the K ring (2 stages, freed right after Q K^T), lane 1 the V ring
+//               (2 stages, freed after P V); P is double buffered so softmax(j) never waits for P V(j-1)
 //   warp 5      TMEM allocator + MMA issuer (one lane):
 //                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
 //                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
@@ -26,13 +27,13 @@ struct AttnCfg {
   static constexpr int kAtomBytes = 128 * 128;          // 128 rows x 128 B
   static constexpr int kPBytes = BQ * BKV * 2;          // 32 KB
   static constexpr int kOffQ = 0;
-  static constexpr int kOffK = kTileBytes;              // 2 stages
-  static constexpr int kOffV = 3 * kTileBytes;          // 2 stages
-  static constexpr int kOffP = 5 * kTileBytes;
-  static constexpr int kOffBar = kOffP + kPBytes;
+  static constexpr int kOffK = kTileBytes;              // 2 stages, released as soon as Q K^T of the tile has run
+  static constexpr int kOffV = 3 * kTileBytes;          // 2 stages, released after P V of the tile
+  static constexpr int kOffP = 5 * kTileBytes;          // 2 buffers: softmax(j) never waits for P V(j-1)
+  static constexpr int kOffBar = kOffP + 2 * kPBytes;
   static constexpr int kSmemUsed = kOffBar + 256;
   // at least 116 KB so that only one CTA is resident per SM (each CTA allocates all 512 TMEM columns)
-  static constexpr int kSmemBytes = (kSmemUsed + 1024 > 116 * 1024) ? (kSmemUsed + 1024) : 116 * 1024;
+  static constexpr int kSmemBytes = (kSmemUsed > 116 * 1024) ? kSmemUsed : 116 * 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
 };
@@ -50,8 +51,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
   uint8_t* sQ = smem + Cfg::kOffQ;
   uint8_t* sK = smem + Cfg::kOffK;
   uint8_t* sV = smem + Cfg::kOffV;
@@ -59,12 +60,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* v_full = bars + 3;    // [2]
-  uint64_t* kv_empty = bars + 5;  // [2]
-  uint64_t* s_full = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t* o_full = bars + 13;   // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,6 +78,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int q0 = qt * BQ;
   const int n_kv = p.causal ? (qt + 1) : (p.S + BKV - 1) / BKV;
 
+  pdl_launch_dependents();
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -83,14 +86,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
+  pdl_wait();
   if (warp == 5) {
     tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
     tmem_relinquish();
@@ -101,20 +106,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_base_ptr;
 
   if (warp == 4) {
+    // ===================== TMA producers: lane 0 = Q + K ring, lane 1 = V ring (independent, never block each other)
     if (lane == 0) {
-      // ===================== TMA producer =====================
       mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
       for (int a = 0; a < Cfg::kAtoms; ++a)
         tma_load_3d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, head * D + a * 64, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
           tma_load_3d(sK + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[st], kvh * D + a * 64, j * BKV, b);
+      }
+    } else if (lane == 1) {
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
@@ -127,7 +136,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
@@ -141,16 +149,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                        idesc_qk, kk != 0);
         }
         umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[st], (j >> 1) & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
+        const uint32_t p_addr = smem_u32(sP + st * Cfg::kPBytes);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
@@ -158,8 +168,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
           umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&o_full[st]);
+        umma_commit(&v_empty[st]);
       }
     }
   } else {
@@ -209,11 +219,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         m_use = (m_tile == -INFINITY) ? 0.f : m_tile;   // fully masked rows stay finite
         alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
       }
-      // the previous P V must be complete before P (smem) is overwritten or O (TMEM) is rescaled
+      // P is double buffered: buffer (j & 1) was last read by P V(j-2); O (TMEM) may only be rescaled once P V(j-1)
+      // is complete
+      if (j > 1) mbar_wait(&o_full[st], ((j >> 1) & 1) ^ 1);
       if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after_sync();
         if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after_sync();
 #pragma unroll
           for (int c = 0; c < D / 32; ++c) {
             uint32_t ov[32];
@@ -239,7 +251,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int chunk = (c & 1) * 4 + g;
-          uint8_t* dst = sP + (c >> 1) * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+          uint8_t* dst = sP + st * Cfg::kPBytes + (c >> 1) * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
           *reinterpret_cast<uint4*>(dst) =
               make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
                          pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
@@ -250,9 +262,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[st]);
     }
-    mbar_wait(o_full, (n_kv - 1) & 1);
+    mbar_wait(&o_full[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after_sync();
     const float inv = 1.f / l;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
@@ -314,7 +326,7 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a->S + BQ - 1) / BQ, a->Hq, a->B);
-  attn_fwd_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  VL2_CHECK_CUDA(launch_kernel(attn_fwd_kernel<D>, grid, dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, p));
   VL2_CHECK_LAUNCH("attn_fwd_kernel");
   return VL2_OK;
 }

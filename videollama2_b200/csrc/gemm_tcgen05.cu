@@ -98,6 +98,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_k_blocks = (p.K + BK - 1) / BK;
 
+  pdl_launch_dependents();   // let the next kernel's CTAs take the SMs this kernel's last wave leaves idle
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -113,6 +114,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     fence_barrier_init();
   }
+  pdl_wait();                // predecessors complete + visible: nothing above touched global memory or TMEM
   if (warp == 2) {
     if (PAIR) { tmem_alloc_pair(tmem_base_ptr, Cfg::kTmemCols); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_base_ptr, Cfg::kTmemCols); tmem_relinquish(); }
@@ -361,19 +363,8 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
   const int units = tiles < slots ? tiles : slots;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PAIR ? 2 * units : units);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VL2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, PAIR>, ta, tb, p));
+  VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
+                               Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, p));
   VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return VL2_OK;
 }

@@ -2,6 +2,8 @@
 // libvl2.so does not link libcuda directly and still loads on a CPU-only box for the symbol-export test).
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -18,6 +20,15 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VL2_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int sm_count() {
   static int cached = -1;

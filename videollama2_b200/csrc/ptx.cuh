@@ -24,6 +24,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and starts with  pdl_launch_dependents(); ...local setup...; pdl_wait();
+// so the NEXT kernel's CTAs are scheduled (and run their prologue) while this kernel's last wave drains, and a kernel
+// never touches global memory before all of its predecessors have completed and flushed.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256)
 layernorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                       const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
                       __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -124,6 +126,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                     __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -163,6 +167,8 @@ __global__ void __launch_bounds__(256)
 layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                         const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
                         __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -208,6 +214,8 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
 __global__ void __launch_bounds__(256)
 rmsnorm_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                       __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -242,6 +250,8 @@ __global__ void clip_embed_finish_kernel(const __nv_bfloat16* __restrict__ patch
                                          const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ gamma,
                                          const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ tok, int np,
                                          int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[64];
   const int t = blockIdx.x % (np + 1);
   const int f = blockIdx.x / (np + 1);
@@ -298,6 +308,8 @@ __global__ void clip_embed_finish_kernel(const __nv_bfloat16* __restrict__ patch
 // ---------------------------------------------------------------------------------------------------------
 __global__ void patch_im2col_kernel(const __nv_bfloat16* __restrict__ px, __nv_bfloat16* __restrict__ A, int F, int H,
                                     int W, int P, int Kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gw = W / P, gh = H / P;
   const int K = 3 * P * P;
   const int64_t total = (int64_t)F * gh * gw * (Kpad / 2);
@@ -336,6 +348,8 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
                          const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                          __nv_bfloat16* __restrict__ y, float* __restrict__ pool_partial, int H, int W, int C,
                          float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[64];
   const int h = blockIdx.x % H;
   const int f = blockIdx.x / H;
@@ -416,6 +430,8 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
 // pooled[f,c] = (sum_h partial[f,h,c]) / (H*W)
 __global__ void se_pool_reduce_kernel(const float* __restrict__ partial, float* __restrict__ pooled, int H, int C,
                                       float inv_hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -426,6 +442,8 @@ __global__ void se_pool_reduce_kernel(const float* __restrict__ partial, float* 
 
 __global__ void se_scale_kernel(__nv_bfloat16* __restrict__ y, const float* __restrict__ s, int HW, int C,
                                 int64_t total_vec) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C / 8;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total_vec;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -448,6 +466,8 @@ __global__ void se_scale_kernel(__nv_bfloat16* __restrict__ y, const float* __re
 // ---------------------------------------------------------------------------------------------------------
 __global__ void conv3d_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int T, int H,
                                      int W, int C, int pad, int To, int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C / 8;
   const int64_t total = (int64_t)To * Ho * Wo * 8 * cv;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -472,6 +492,8 @@ __global__ void conv3d_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // head with 16-byte accesses.
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off,
                             int k_off, int pos0, const float* __restrict__ inv_freq) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float cs[];  // [D/2] cos, [D/2] sin
   const int half = D / 2;
   const int s = blockIdx.x;
@@ -506,6 +528,8 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, 
 __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ dst_row,
                                     const __nv_bfloat16* __restrict__ table, int64_t vocab,
                                     __nv_bfloat16* __restrict__ out, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x;
   int64_t id = ids[i];
   if (id < 0 || id >= vocab) return;  // modal placeholder or invalid id: row is written by the connector
@@ -548,6 +572,8 @@ __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
                    const __nv_bfloat16* __restrict__ residual, void* __restrict__ Cv, int out_f32, int M, int N, int K,
                    int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][kSkinnyNT8][4][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
@@ -634,6 +660,8 @@ __global__ void __launch_bounds__(256)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                    const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int64_t ldkv, int n_pos,
                    int group, int D, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sc[];  // [n_pos] scores, then [4][D] partial outputs
   __shared__ float red[64];
   const int h = blockIdx.x, kvh = h / group;
@@ -713,13 +741,13 @@ extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta,
   const unsigned wgrid = (unsigned)((rows + 7) / 8);
   const int nv = (C / 8 + 31) / 32;
 #define VL2_LN_WARP(NV)                                                                                   \
-  layernorm_warp_kernel<NV><<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, \
+  launch_kernel(layernorm_warp_kernel<NV>, dim3(wgrid), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (const bf16*)gamma, \
       (const bf16*)beta, (const bf16*)residual, (bf16*)y, rows, C, eps, act)
   if (nv <= 1) VL2_LN_WARP(1);
   else if (nv <= 2) VL2_LN_WARP(2);
   else if (nv <= 4) VL2_LN_WARP(4);
   else
-    layernorm_stream_kernel<<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta,
+    launch_kernel(layernorm_stream_kernel, dim3(wgrid), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (const bf16*)gamma, (const bf16*)beta,
                                                                    (const bf16*)residual, (bf16*)y, rows, C, eps, act);
 #undef VL2_LN_WARP
   VL2_CHECK_LAUNCH("layernorm_kernel");
@@ -733,12 +761,12 @@ extern "C" int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t ro
   const unsigned wgrid = (unsigned)((rows + 7) / 8);
   const int nv = (C / 8 + 31) / 32;
 #define VL2_RMS_WARP(NV) \
-  rmsnorm_warp_kernel<NV><<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, C, eps)
+  launch_kernel(rmsnorm_warp_kernel<NV>, dim3(wgrid), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, C, eps)
   if (nv <= 1) VL2_RMS_WARP(1);
   else if (nv <= 2) VL2_RMS_WARP(2);
   else if (nv <= 4) VL2_RMS_WARP(4);
   else
-    rmsnorm_stream_kernel<<<wgrid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, C, eps);
+    launch_kernel(rmsnorm_stream_kernel, dim3(wgrid), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (const bf16*)gamma, (bf16*)y, rows, C, eps);
 #undef VL2_RMS_WARP
   VL2_CHECK_LAUNCH("rmsnorm_kernel");
   return VL2_OK;
@@ -749,7 +777,7 @@ extern "C" int vl2_patch_im2col(const void* pixels, void* A, int F, int H, int W
   VL2_REQUIRE(Kpad % 8 == 0 && Kpad >= 3 * P * P && W % 2 == 0, VL2_E_BADSHAPE,
               "vl2_patch_im2col: Kpad %% 8 == 0, Kpad >= 3*P*P and even W required");
   const int64_t total = (int64_t)F * (H / P) * (W / P) * (Kpad / 2);
-  patch_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)pixels, (bf16*)A, F, H, W, P,
+  launch_kernel(patch_im2col_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)pixels, (bf16*)A, F, H, W, P,
                                                                              Kpad);
   VL2_CHECK_LAUNCH("patch_im2col_kernel");
   return VL2_OK;
@@ -760,7 +788,7 @@ extern "C" int vl2_clip_embed_finish(const void* patch, const void* cls, const v
   VL2_REQUIRE(F > 0 && np > 0 && C % 8 == 0 && C <= 512 * 8 * kMaxVec, VL2_E_BADSHAPE, "vl2_clip_embed_finish: bad shape");
   VL2_REQUIRE(aligned16(patch) && aligned16(cls) && aligned16(pos) && aligned16(tok), VL2_E_BADALIGN,
               "vl2_clip_embed_finish: 16-byte alignment");
-  clip_embed_finish_kernel<<<(unsigned)(F * (np + 1)), row_threads(C), 0, (cudaStream_t)stream>>>(
+  launch_kernel(clip_embed_finish_kernel, dim3((unsigned)(F * (np + 1))), dim3(row_threads(C)), 0, (cudaStream_t)stream, 1, 
       (const bf16*)patch, (const bf16*)cls, (const bf16*)pos, (const bf16*)gamma, (const bf16*)beta, (bf16*)tok, np, C,
       eps);
   VL2_CHECK_LAUNCH("clip_embed_finish_kernel");
@@ -776,12 +804,12 @@ extern "C" int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void*
   // `pooled` layout: [F*C] pooled means followed by [F*H*C] per-row partial sums (workspace); see vl2.h.
   int threads = (C / 8 + 31) / 32 * 32;
   float* partial = pooled ? pooled + (int64_t)F * C : nullptr;
-  dwconv3x3_ln_silu_kernel<<<(unsigned)(F * H), threads, 0, (cudaStream_t)stream>>>(
+  launch_kernel(dwconv3x3_ln_silu_kernel, dim3((unsigned)(F * H)), dim3(threads), 0, (cudaStream_t)stream, 1, 
       (const bf16*)x, (const bf16*)w9c, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, partial, H, W, C, eps);
   VL2_CHECK_LAUNCH("dwconv3x3_ln_silu_kernel");
   if (pooled) {
     dim3 grid((C + 255) / 256, F);
-    se_pool_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, pooled, H, C, 1.f / (float)(H * W));
+    launch_kernel(se_pool_reduce_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 1, partial, pooled, H, C, 1.f / (float)(H * W));
     VL2_CHECK_LAUNCH("se_pool_reduce_kernel");
   }
   return VL2_OK;
@@ -790,7 +818,7 @@ extern "C" int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void*
 extern "C" int vl2_se_scale(void* y, const float* s, int F, int HW, int C, void* stream) {
   VL2_REQUIRE(F > 0 && HW > 0 && C % 8 == 0, VL2_E_BADSHAPE, "vl2_se_scale: bad shape");
   const int64_t total = (int64_t)F * HW * (C / 8);
-  se_scale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)y, s, HW, C, total);
+  launch_kernel(se_scale_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, (bf16*)y, s, HW, C, total);
   VL2_CHECK_LAUNCH("se_scale_kernel");
   return VL2_OK;
 }
@@ -800,7 +828,7 @@ extern "C" int vl2_conv3d_im2col(const void* x, void* A, int T, int H, int W, in
   VL2_REQUIRE(T > 0 && H > 0 && W > 0 && C % 8 == 0 && To > 0 && Ho > 0 && Wo > 0 && (pad == 0 || pad == 1),
               VL2_E_BADSHAPE, "vl2_conv3d_im2col: bad shape");
   const int64_t total = (int64_t)To * Ho * Wo * 8 * (C / 8);
-  conv3d_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)A, T, H, W, C, pad,
+  launch_kernel(conv3d_im2col_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (bf16*)A, T, H, W, C, pad,
                                                                               To, Ho, Wo);
   VL2_CHECK_LAUNCH("conv3d_im2col_kernel");
   return VL2_OK;
@@ -813,7 +841,7 @@ extern "C" int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, i
               "vl2_rope_inplace: D %% 16 == 0 and 16-byte aligned heads required");
   int threads = (Hq + Hkv) * (D / 16);
   threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
-  rope_kernel<<<S, threads, D * sizeof(float), (cudaStream_t)stream>>>((bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
+  launch_kernel(rope_kernel, dim3(S), dim3(threads), D * sizeof(float), (cudaStream_t)stream, 1, (bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
                                                                       inv_freq);
   VL2_CHECK_LAUNCH("rope_kernel");
   return VL2_OK;
@@ -822,7 +850,7 @@ extern "C" int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, i
 extern "C" int vl2_embed_splice(const int64_t* ids, const int32_t* dst_row, int n, const void* table, int64_t vocab,
                                 void* out, int H, void* stream) {
   VL2_REQUIRE(n > 0 && H % 8 == 0, VL2_E_BADSHAPE, "vl2_embed_splice: bad shape");
-  embed_splice_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(ids, dst_row, (const bf16*)table, vocab, (bf16*)out, H);
+  launch_kernel(embed_splice_kernel, dim3(n), dim3(128), 0, (cudaStream_t)stream, 1, ids, dst_row, (const bf16*)table, vocab, (bf16*)out, H);
   VL2_CHECK_LAUNCH("embed_splice_kernel");
   return VL2_OK;
 }
@@ -838,9 +866,9 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
               "vl2_gemm_skinny: SWIGLU needs even N and no residual");
   const int blocks = (N + 8 * kSkinnyNT8 - 1) / (8 * kSkinnyNT8);
   if (a_f32)
-    gemm_skinny_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act);
+    launch_kernel(gemm_skinny_kernel<true>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act);
   else
-    gemm_skinny_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act);
+    launch_kernel(gemm_skinny_kernel<false>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, A, (const bf16*)W, bias, (const bf16*)residual, C, out_f32, M, N, K, act);
   VL2_CHECK_LAUNCH("gemm_skinny_kernel");
   return VL2_OK;
 }
@@ -857,7 +885,7 @@ extern "C" int vl2_attention_decode(const void* q, const void* k_cache, const vo
       attr = true;
     }
   }
-  attn_decode_kernel<<<Hq, 256, smem, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+  launch_kernel(attn_decode_kernel, dim3(Hq), dim3(256), smem, (cudaStream_t)stream, 1, (const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
                                                              (bf16*)out, ldkv, n_pos, Hq / Hkv, D, scale);
   VL2_CHECK_LAUNCH("attn_decode_kernel");
   return VL2_OK;
