@@ -70,7 +70,16 @@ typedef struct vl2_gemm_args {
   int32_t M, N, K;
   int32_t act;
   int32_t out_f32;
-  int32_t reserved; /* 0 = choose the N tile width by the library's cost model; 64..256 (step 32) forces it (tests) */
+  int32_t reserved; /* 0 = choose the tile by the library's cost model; 64..256 (step 32) forces a single-CTA tile width,
+                       1000 + (128..256) forces the cta_group::2 pair kernel (tests) */
+  /* Fused compute + collective (frame-parallel ViT): every output vector of C is ALSO stored at the same
+   * element offset into up to 8 peer buffers (other GPUs' symmetric memory mapped over NVLink), or once to an NVSwitch
+   * multicast address (multimem.st) when mc_out != NULL — the all-gather of visual tokens happens inside the epilogue
+   * of the producing GEMM, tile by tile, instead of in a separate collective.  bf16, non-SwiGLU outputs only. */
+  void* bcast_out[8];
+  void* mc_out;
+  int32_t n_bcast;
+  int32_t reserved2;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 

@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("lda", C.c_int64), ("ldw", C.c_int64), ("ldc", C.c_int64), ("ldr", C.c_int64),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("act", C.c_int32), ("out_f32", C.c_int32), ("reserved", C.c_int32),
+        ("bcast_out", C.c_void_p * 8), ("mc_out", C.c_void_p), ("n_bcast", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -54,7 +54,18 @@ struct GemmParams {
   int act;
   int out_f32;
   int num_m_tiles, num_n_tiles;
+  // epilogue-fused all-gather: peers' copies of C (NVLink P2P stores) or one NVSwitch multicast address
+  __nv_bfloat16* bcast[8];
+  __nv_bfloat16* mc;
+  int n_bcast;
 };
+
+// one 16-byte store replicated by the NVSwitch to every GPU of the multicast group
+__device__ __forceinline__ void multimem_st128(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
 
 __device__ __forceinline__ float fast_sigmoid_mul(float x, float k_log2e) {
   // x * sigmoid(k x) = x / (1 + 2^(-k*log2e*x)); approximate reciprocal on the MUFU pipe
@@ -309,7 +320,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int gr = rbase + rr;
             if (gr < p.M && t_chunk * 8 < out_span) {
               const uint4 val = lds128(stg + rr * 128 + ((t_chunk ^ (rr & 7)) << 4));
-              *reinterpret_cast<uint4*>(cbase + (int64_t)gr * p.ldc + out_col0 + t_chunk * 8) = val;
+              const int64_t off = (int64_t)gr * p.ldc + out_col0 + t_chunk * 8;
+              *reinterpret_cast<uint4*>(cbase + off) = val;
+              if (p.mc != nullptr) {
+                multimem_st128(p.mc + off, val);
+              } else {
+                for (int pi = 0; pi < p.n_bcast; ++pi) *reinterpret_cast<uint4*>(p.bcast[pi] + off) = val;
+              }
             }
           }
           __syncwarp();  // the buffer is reused by the next span
@@ -351,6 +368,9 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
   p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
+  p.n_bcast = a->n_bcast;
+  p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
+  for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
   const int tile_m = PAIR ? 2 * BM : BM;
   p.num_m_tiles = (a->M + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + BN - 1) / BN;
@@ -433,6 +453,14 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
               VL2_E_BADALIGN, "vl2_gemm_bf16: pointers must be 16-byte aligned");
   VL2_REQUIRE(a->act >= VL2_ACT_NONE && a->act <= VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: unknown act %d",
               a->act);
+  VL2_REQUIRE(a->n_bcast >= 0 && a->n_bcast <= 8, VL2_E_BADSHAPE, "vl2_gemm_bf16: n_bcast must be in [0,8]");
+  if (a->n_bcast > 0 || a->mc_out != nullptr) {
+    VL2_REQUIRE(!a->out_f32 && a->act != VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: the broadcast epilogue supports bf16, non-SwiGLU outputs only");
+    for (int i = 0; i < a->n_bcast; ++i)
+      VL2_REQUIRE(a->bcast_out[i] != nullptr && aligned16(a->bcast_out[i]), VL2_E_BADALIGN,
+                  "vl2_gemm_bf16: broadcast target %d must be a 16-byte aligned device pointer", i);
+  }
   if (a->act == VL2_ACT_SWIGLU) {
     VL2_REQUIRE(a->residual == nullptr && !a->out_f32 && a->N % 16 == 0, VL2_E_UNSUPPORTED,
                 "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");

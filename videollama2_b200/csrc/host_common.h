@@ -42,7 +42,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-bool pdl_enabled();  // VL2_PDL=0 disables programmatic dependent launch (default on)
+bool pdl_enabled();  // VL2_PDL=1 enables programmatic dependent launch (default off: profiles/r01_bench_v10_*.json)
 
 // One launch path for every kernel: optional thread-block cluster, programmatic dependent launch attribute.
 template <typename... KArgs, typename... Args>

@@ -24,8 +24,8 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Programmatic dependent launch (PDL): every kernel of the library is launched with the programmatic-stream-
-// serialization attribute and starts with  pdl_launch_dependents(); ...local setup...; pdl_wait();
+// Programmatic dependent launch (PDL, opt-in with VL2_PDL=1): every kernel of the library can be launched with the
+// programmatic-stream-serialization attribute and starts with  pdl_launch_dependents(); ...local setup...; pdl_wait();
 // so the NEXT kernel's CTAs are scheduled (and run their prologue) while this kernel's last wave drains, and a kernel
 // never touches global memory before all of its predecessors have completed and flushed.
 // ----------------------------------------------------------------------------------------------

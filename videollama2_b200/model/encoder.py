@@ -90,8 +90,12 @@ class CLIPVisionTower:
         return self
 
     # ---- forward -------------------------------------------------------------------------------------------
-    def hidden_states(self, images: torch.Tensor) -> torch.Tensor:
-        """[F,3,H,W] bf16 -> residual stream after the selected layer, [F, np+1, C]."""
+    def hidden_states(self, images: torch.Tensor, last_out: Optional[torch.Tensor] = None, bcast_ptrs=None,
+                      mc_ptr: int = 0) -> torch.Tensor:
+        """[F,3,H,W] bf16 -> residual stream after the selected layer, [F, np+1, C].
+        `last_out` ([F*(np+1), C] view, e.g. this rank's rows of a symmetric-memory gather buffer) receives the final
+        GEMM's output; `bcast_ptrs` / `mc_ptr` make that GEMM's epilogue also store every tile into the peers' buffers
+        (NVLink P2P) or an NVSwitch multicast address: the all-gather of visual tokens fused into the last ViT GEMM."""
         c = self._config
         Fn = images.shape[0]
         C = c.hidden_size
@@ -102,7 +106,8 @@ class CLIPVisionTower:
         patch = ops.gemm(A, self.w["patch"])
         x = ops.clip_embed_finish(patch, self.w["cls"], self.w["pos"], self.w["pre_g"], self.w["pre_b"], Fn,
                                   c.layer_norm_eps)
-        for L in self.layers:
+        for li, L in enumerate(self.layers):
+            last = li == len(self.layers) - 1
             y = ops.layernorm(x, L["ln1_g"], L["ln1_b"], c.layer_norm_eps)
             qkv = ops.gemm(y, L["wqkv"], bias=L["bqkv"])
             o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B=Fn, S=S, Hq=H, Hkv=H, D=D, causal=False,
@@ -110,7 +115,10 @@ class CLIPVisionTower:
             x = ops.gemm(o, L["wo"], bias=L["bo"], residual=x)
             y = ops.layernorm(x, L["ln2_g"], L["ln2_b"], c.layer_norm_eps)
             h = ops.gemm(y, L["w1"], bias=L["b1"], act=ops.ACT_QUICK_GELU)
-            x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x)
+            if last and (last_out is not None or bcast_ptrs or mc_ptr):
+                x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x, out=last_out, bcast_ptrs=bcast_ptrs, mc_ptr=mc_ptr)
+            else:
+                x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x)
         return x.view(Fn, S, C)
 
     def feature_select(self, hidden: torch.Tensor) -> torch.Tensor:

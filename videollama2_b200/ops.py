@@ -44,9 +44,12 @@ def launch_count() -> int:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
+         bcast_ptrs: Optional[list] = None, mc_ptr: int = 0) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
-    `bn` forces the tile width (tests); 0 = library heuristic."""
+    `bn` forces the tile width (tests); 0 = library heuristic.
+    `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
+    (epilogue-fused all-gather over NVLink); `mc_ptr`: NVSwitch multicast address used instead when non-zero."""
     _need_cuda(a, w, bias, residual, row_scale, out)
     _bf16(a, w, residual)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1, "gemm: 2-D, unit inner stride"
@@ -70,6 +73,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
                     out_f32=1 if out.dtype == torch.float32 else 0, reserved=bn)
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("gemm: out must be bf16 or fp32")
+    if bcast_ptrs or mc_ptr:
+        if out.dtype != torch.bfloat16 or act == ACT_SWIGLU:
+            raise NotImplementedError("gemm: broadcast epilogue supports bf16, non-SwiGLU outputs")
+        ptrs = list(bcast_ptrs or [])
+        if len(ptrs) > 8:
+            raise ValueError("gemm: at most 8 broadcast targets")
+        for i, ptr in enumerate(ptrs):
+            args.bcast_out[i] = ptr
+        args.n_bcast = len(ptrs)
+        args.mc_out = mc_ptr or None
     check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
     return out
 
