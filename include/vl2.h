@@ -80,6 +80,18 @@ typedef struct vl2_gemm_args {
   void* mc_out;
   int32_t n_bcast;
   int32_t reserved2;
+  /* RMSNorm folded into the GEMMs around it (HF:mistral/modeling_mistral.py:182-199): with gamma pre-multiplied into
+   * W's columns, rmsnorm(x) W^T = rsqrt(mean(x^2) + eps) * (x W'^T).
+   *   rms_sumsq_in  fp32 [M]: sum_k x[m,k]^2 of THIS GEMM's A rows -> the accumulator is scaled by
+   *                 rsqrt(rms_sumsq_in[m] * rms_inv_dim + rms_eps) before bias/activation (NULL = off)
+   *   sumsq_out     fp32 [M]: the epilogue atomically adds sum_n C[m,n]^2 of the bf16-rounded outputs it writes (the
+   *                 next norm's statistics come for free from the producing residual GEMM)
+   *   sumsq_zero    fp32 [M]: zeroed by this launch (the buffer the NEXT producer will accumulate into). */
+  const float* rms_sumsq_in;
+  float* sumsq_out;
+  float* sumsq_zero;
+  float rms_inv_dim;
+  float rms_eps;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 
@@ -128,6 +140,8 @@ int vl2_attention_decode(const void* q, const void* k_cache, const void* v_cache
 int vl2_layernorm(const void* x, const void* gamma, const void* beta, const void* residual, void* y, int64_t rows,
                   int C, float eps, int act, void* stream);
 int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t rows, int C, float eps, void* stream);
+/* out[r] = sum_c x[r,c]^2 (fp32): seeds the folded-RMSNorm statistics for the first decoder layer. */
+int vl2_row_sumsq(const void* x, float* out, int64_t rows, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * CLIP patch embedding front/back ends (HF:clip/modeling_clip.py:202-218).

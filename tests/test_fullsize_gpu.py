@@ -47,9 +47,15 @@ def test_mistral_layer_real_dims(cuda):
     sd_full["model.norm.weight"] = torch.ones((l.hidden,), dtype=torch.bfloat16)
     sd_full["lm_head.weight"] = torch.zeros((8, l.hidden), dtype=torch.bfloat16)
     eng.load_state_dict(sd_full, cuda)
-    out = eng._layer(eng.layers[0], x.to(cuda), S, 0, None)
+    from videollama2_b200 import ops
+    xd = x.to(cuda)
+    ss_x = ops.row_sumsq(xd)
+    ss_h = torch.zeros_like(ss_x)
+    out = eng._layer(eng.layers[0], xd, S, 0, None, ss_x, ss_h)
     assert out.shape == (S, l.hidden)
     assert rel(out, ref) < 1e-2
+    # the folded-RMSNorm bookkeeping: ss_x now holds sum(out^2) per row, the scratch buffer is back to zero
+    assert rel(ss_x, out.float().pow(2).sum(-1)) < 1e-4 and float(ss_h.abs().max()) == 0.0
 
 
 def test_stc_block_real_dims(cuda):

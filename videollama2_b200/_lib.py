@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libvl2.so")
 SYMBOLS = [
     "vl2_version", "vl2_last_error", "vl2_launch_count",
     "vl2_gemm_bf16", "vl2_gemm_skinny", "vl2_attention", "vl2_attention_decode",
-    "vl2_layernorm", "vl2_rmsnorm",
+    "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq",
     "vl2_patch_im2col", "vl2_clip_embed_finish",
     "vl2_dwconv3x3_ln_silu", "vl2_se_scale", "vl2_conv3d_im2col",
     "vl2_rope_inplace", "vl2_embed_splice",
@@ -30,6 +30,8 @@ class GemmArgs(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("act", C.c_int32), ("out_f32", C.c_int32), ("reserved", C.c_int32),
         ("bcast_out", C.c_void_p * 8), ("mc_out", C.c_void_p), ("n_bcast", C.c_int32), ("reserved2", C.c_int32),
+        ("rms_sumsq_in", C.c_void_p), ("sumsq_out", C.c_void_p), ("sumsq_zero", C.c_void_p),
+        ("rms_inv_dim", C.c_float), ("rms_eps", C.c_float),
     ]
 
 
@@ -70,6 +72,7 @@ def load() -> C.CDLL:
         "vl2_attention": [C.POINTER(AttnArgs), vp],
         "vl2_layernorm": [vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
         "vl2_rmsnorm": [vp, vp, vp, i64, i32, f32, vp],
+        "vl2_row_sumsq": [vp, vp, i64, i32, vp],
         "vl2_patch_im2col": [vp, vp, i32, i32, i32, i32, i32, vp],
         "vl2_clip_embed_finish": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
         "vl2_dwconv3x3_ln_silu": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],

@@ -58,6 +58,11 @@ struct GemmParams {
   __nv_bfloat16* bcast[8];
   __nv_bfloat16* mc;
   int n_bcast;
+  // folded RMSNorm (see vl2.h)
+  const float* rms_sumsq_in;
+  float* sumsq_out;
+  float* sumsq_zero;
+  float rms_inv_dim, rms_eps;
 };
 
 // one 16-byte store replicated by the NVSwitch to every GPU of the multicast group
@@ -220,7 +225,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (p.bias != nullptr) {  // stage this tile's bias slice once (broadcast LDS later instead of exposed LDG latency)
         for (int i = etid; i < BN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       }
-      const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
+      float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
+      if (p.rms_sumsq_in != nullptr && row_ok) rs *= rsqrtf(p.rms_sumsq_in[row] * p.rms_inv_dim + p.rms_eps);
+      if (p.sumsq_zero != nullptr && row_ok && grp == 0 && tile < p.num_m_tiles) p.sumsq_zero[row] = 0.f;  // n-tile 0 only
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
@@ -234,6 +241,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (col0 >= p.N) break;                       // warp-uniform
         const int span = min(min(64, BN - c0), p.N - col0);   // 8..64 valid accumulator columns (multiple of 8)
         uint32_t v[32];
+        float ssq = 0.f;                              // sum of squares of this thread's (row's) outputs in the span
         tmem_ld_32x32(taddr + c0, v);
         // residual block -> smem (coalesced: 8 lanes x 16 B per row)
         if (res != nullptr) {
@@ -302,12 +310,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           } else {
             // own row -> smem (each thread overwrites only the chunks it just read its residual from)
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              sts128(my_row + (((hf * 4 + g) ^ sw) << 4),
-                     make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
-                                pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7])));
+            for (int g = 0; g < 4; ++g) {
+              const uint4 pk = make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
+                                          pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+              sts128(my_row + (((hf * 4 + g) ^ sw) << 4), pk);
+              if (p.sumsq_out != nullptr && hf * 32 + g * 8 < span) {   // statistics of what the consumer will read
+                const float a0 = bf16_lo(pk.x), a1 = bf16_hi(pk.x), a2 = bf16_lo(pk.y), a3 = bf16_hi(pk.y);
+                const float a4 = bf16_lo(pk.z), a5 = bf16_hi(pk.z), a6 = bf16_lo(pk.w), a7 = bf16_hi(pk.w);
+                ssq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+              }
+            }
           }
         }
+        if (p.sumsq_out != nullptr && row_ok && !swiglu && !p.out_f32) atomicAdd(p.sumsq_out + row, ssq);
         if (!p.out_f32) {
           __syncwarp();
           // smem -> global, full lines.  Output span: `span` columns (or span/2 for SwiGLU).
@@ -368,6 +383,8 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
   p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
+  p.rms_sumsq_in = a->rms_sumsq_in; p.sumsq_out = a->sumsq_out; p.sumsq_zero = a->sumsq_zero;
+  p.rms_inv_dim = a->rms_inv_dim; p.rms_eps = a->rms_eps;
   p.n_bcast = a->n_bcast;
   p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
   for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
@@ -453,6 +470,8 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
               VL2_E_BADALIGN, "vl2_gemm_bf16: pointers must be 16-byte aligned");
   VL2_REQUIRE(a->act >= VL2_ACT_NONE && a->act <= VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: unknown act %d",
               a->act);
+  VL2_REQUIRE(a->sumsq_out == nullptr || (!a->out_f32 && a->act != VL2_ACT_SWIGLU), VL2_E_UNSUPPORTED,
+              "vl2_gemm_bf16: sumsq_out supports bf16, non-SwiGLU outputs only");
   VL2_REQUIRE(a->n_bcast >= 0 && a->n_bcast <= 8, VL2_E_BADSHAPE, "vl2_gemm_bf16: n_bcast must be in [0,8]");
   if (a->n_bcast > 0 || a->mc_out != nullptr) {
     VL2_REQUIRE(!a->out_f32 && a->act != VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED,

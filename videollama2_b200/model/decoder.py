@@ -3,7 +3,9 @@
 Arithmetic of HF MistralModel / Qwen2Model (HF:mistral/modeling_mistral.py:35-48,51-82,122-239,262-470;
 HF:qwen2/modeling_qwen2.py:187-246): RMSNorm -> fused QKV GEMM (+bias for Qwen2) -> RoPE -> causal GQA flash attention
 -> o_proj(+residual) -> RMSNorm -> gate/up GEMM with SwiGLU epilogue -> down_proj(+residual) -> norm -> lm_head.
-Weights are repacked once: q/k/v concatenated, gate/up rows interleaved so SwiGLU happens inside the GEMM tile."""
+Weights are repacked once: q/k/v concatenated, gate/up rows interleaved so SwiGLU happens inside the GEMM tile, and the
+RMSNorm gains multiplied into the weight columns: the per-layer norms cost no kernel (row statistics are produced by
+the residual GEMM epilogues, the 1/rms factor is applied in the consuming GEMM's epilogue)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional
@@ -46,18 +48,26 @@ class DecoderEngine:
         for i in range(self.config.num_hidden_layers):
             p = f"model.layers.{i}."
             names = ("q_proj", "k_proj", "v_proj")
+            # RMSNorm gains are folded into the columns of the weight that consumes the normalised activations:
+            # rmsnorm(x; g) W^T = rstd(x) * (x (W * g)^T); rstd is applied per row in the GEMM epilogue.
+            g1 = sd[p + "input_layernorm.weight"].to(device=dev, dtype=torch.float32)
+            g2 = sd[p + "post_attention_layernorm.weight"].to(device=dev, dtype=torch.float32)
+            wqkv = torch.cat([sd[p + f"self_attn.{n}.weight"] for n in names], 0).to(device=dev, dtype=torch.float32)
+            wgu = torch.stack([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], 1).reshape(
+                2 * self.I, self.H).to(device=dev, dtype=torch.float32)
             L = {
-                "g1": bf(sd[p + "input_layernorm.weight"]), "g2": bf(sd[p + "post_attention_layernorm.weight"]),
-                "wqkv": bf(torch.cat([sd[p + f"self_attn.{n}.weight"] for n in names], 0)),
+                "wqkv": (wqkv * g1[None, :]).to(torch.bfloat16).contiguous(),
                 "wo": bf(sd[p + "self_attn.o_proj.weight"]),
-                "wgu": bf(torch.stack([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], 1).reshape(2 * self.I, self.H)),
+                "wgu": (wgu * g2[None, :]).to(torch.bfloat16).contiguous(),
                 "wd": bf(sd[p + "mlp.down_proj.weight"]),
             }
+            del wqkv, wgu
             if p + "self_attn.q_proj.bias" in sd:
                 L["bqkv"] = f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in names], 0))
             self.layers.append(L)
         self.w = {"embed": bf(sd["model.embed_tokens.weight"]), "norm": bf(sd["model.norm.weight"]),
-                  "lm_head": bf(sd["lm_head.weight"])}
+                  "lm_head": bf(sd["lm_head.weight"]),
+                  "ones": torch.ones((self.H,), device=dev, dtype=torch.bfloat16)}
         inv = 1.0 / (self.config.rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))
         self.w["inv_freq"] = inv.to(dev)
         self.device = dev
@@ -69,17 +79,19 @@ class DecoderEngine:
         return self.w["embed"]
 
     # ---- prefill ---------------------------------------------------------------------------------------------
-    def _layer(self, L, x: torch.Tensor, S: int, pos0: int, qkv_out: Optional[torch.Tensor]) -> torch.Tensor:
+    def _layer(self, L, x: torch.Tensor, S: int, pos0: int, qkv_out: Optional[torch.Tensor], ss_x: torch.Tensor,
+               ss_h: torch.Tensor) -> torch.Tensor:
+        """One decoder layer.  ss_x holds sum(x^2) per row of the incoming residual stream; on return it holds the
+        statistics of the outgoing stream (accumulated by the down_proj epilogue).  ss_h is scratch of the same shape,
+        all zeros on entry and on return."""
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
-        y = ops.rmsnorm(x, L["g1"], self.eps)
-        qkv = ops.gemm(y, L["wqkv"], bias=L.get("bqkv"), out=qkv_out)
+        qkv = ops.gemm(x, L["wqkv"], bias=L.get("bqkv"), out=qkv_out, rms_in=ss_x, rms_eps=self.eps)
         ops.rope_inplace(qkv, S, Hq, Hkv, D, 0, Hq * D, pos0, self.w["inv_freq"])
         o = ops.attention(qkv[:, : Hq * D], qkv[:, Hq * D: (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], B=1, S=S, Hq=Hq,
                           Hkv=Hkv, D=D, causal=True, scale=D ** -0.5)
-        x = ops.gemm(o, L["wo"], residual=x)
-        y = ops.rmsnorm(x, L["g2"], self.eps)
-        h = ops.gemm(y, L["wgu"], act=ops.ACT_SWIGLU)
-        return ops.gemm(h, L["wd"], residual=x)
+        x = ops.gemm(o, L["wo"], residual=x, sumsq_out=ss_h, sumsq_zero=ss_x)     # stats of the mid-layer stream
+        h = ops.gemm(x, L["wgu"], act=ops.ACT_SWIGLU, rms_in=ss_h, rms_eps=self.eps)
+        return ops.gemm(h, L["wd"], residual=x, sumsq_out=ss_x, sumsq_zero=ss_h)  # stats for the next layer
 
     def prefill(self, embeds: torch.Tensor, all_logits: bool = False, keep_cache: bool = False,
                 max_len: Optional[int] = None, _no_graph: bool = False):
@@ -95,8 +107,10 @@ class DecoderEngine:
             width = (self.Hq + 2 * self.Hkv) * self.D
             self.kv = [torch.empty((cap, width), device=x.device, dtype=torch.bfloat16) for _ in self.layers]
             self.kv_len = S
+        ss_x = ops.row_sumsq(x)
+        ss_h = torch.zeros_like(ss_x)
         for i, L in enumerate(self.layers):
-            x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None)
+            x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None, ss_x, ss_h)
         if all_logits:
             hn = ops.rmsnorm(x, self.w["norm"], self.eps)
             logits = ops.gemm(hn, self.w["lm_head"], out_dtype=torch.float32)
@@ -117,14 +131,14 @@ class DecoderEngine:
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
         for i, L in enumerate(self.layers):
             cache = self.kv[i]
-            y = ops.rmsnorm(x, L["g1"], self.eps)
+            y = ops.rmsnorm(x, self.w["ones"], self.eps)       # gamma lives in the weight columns
             row = cache[pos:pos + 1]
             ops.gemm_skinny(y, L["wqkv"], bias=L.get("bqkv"), out=row)
             ops.rope_inplace(row, 1, Hq, Hkv, D, 0, Hq * D, pos, self.w["inv_freq"])
             o = ops.attention_decode(row[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
                                      n_pos=pos + 1, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5)
             x = ops.gemm_skinny(o, L["wo"], residual=x, out_dtype=torch.bfloat16)
-            y = ops.rmsnorm(x, L["g2"], self.eps)
+            y = ops.rmsnorm(x, self.w["ones"], self.eps)
             h = ops.gemm_skinny(y, L["wgu"], act=ops.ACT_SWIGLU, out_dtype=torch.bfloat16)
             x = ops.gemm_skinny(h, L["wd"], residual=x, out_dtype=torch.bfloat16)
         self.kv_len = pos + 1

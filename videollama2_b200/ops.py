@@ -12,7 +12,7 @@ from ._lib import (ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_SIGMOID, ACT_SILU
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "attention_decode", "layernorm", "rmsnorm", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
@@ -45,11 +45,16 @@ def launch_count() -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
-         bcast_ptrs: Optional[list] = None, mc_ptr: int = 0) -> torch.Tensor:
+         bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
+         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None,
+         sumsq_zero: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
     `bn` forces the tile width (tests); 0 = library heuristic.
     `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
-    (epilogue-fused all-gather over NVLink); `mc_ptr`: NVSwitch multicast address used instead when non-zero."""
+    (epilogue-fused all-gather over NVLink); `mc_ptr`: NVSwitch multicast address used instead when non-zero.
+    `rms_in` (fp32 [M] row sums of squares of `a`) scales row m by rsqrt(rms_in[m]/K + rms_eps): RMSNorm folded into the
+    GEMM (gamma must already be folded into w); `sumsq_out` accumulates the row sums of squares of the outputs,
+    `sumsq_zero` is cleared."""
     _need_cuda(a, w, bias, residual, row_scale, out)
     _bf16(a, w, residual)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1, "gemm: 2-D, unit inner stride"
@@ -73,6 +78,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
                     out_f32=1 if out.dtype == torch.float32 else 0, reserved=bn)
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("gemm: out must be bf16 or fp32")
+    for t in (rms_in, sumsq_out, sumsq_zero):
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32 and t.numel() == M and t.is_contiguous()
+    if rms_in is not None:
+        args.rms_sumsq_in = rms_in.data_ptr()
+        args.rms_inv_dim = 1.0 / K
+        args.rms_eps = float(rms_eps)
+    if sumsq_out is not None:
+        if out.dtype != torch.bfloat16 or act == ACT_SWIGLU:
+            raise NotImplementedError("gemm: sumsq_out supports bf16, non-SwiGLU outputs")
+        args.sumsq_out = sumsq_out.data_ptr()
+    if sumsq_zero is not None:
+        args.sumsq_zero = sumsq_zero.data_ptr()
     if bcast_ptrs or mc_ptr:
         if out.dtype != torch.bfloat16 or act == ACT_SWIGLU:
             raise NotImplementedError("gemm: broadcast epilogue supports bf16, non-SwiGLU outputs")
@@ -167,6 +185,15 @@ def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torc
         out = torch.empty_like(x)
     check(_lib.load().vl2_rmsnorm(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), x.numel() // Cc, Cc, float(eps),
                                   _stream()), "vl2_rmsnorm")
+    return out
+
+
+def row_sumsq(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    _bf16(x)
+    assert x.is_contiguous() and x.dim() == 2
+    out = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+    check(_lib.load().vl2_row_sumsq(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_sumsq")
     return out
 
 
