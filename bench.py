@@ -309,9 +309,13 @@ def main():
         g_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
         g_fl = sum(f for _, _, f in recs)
         pk = peaks()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")
+        if os.path.exists(tp):   # dram__bytes_read + dram__bytes_write per GEMM launch from the committed ncu capture
+            traffic = json.load(open(tp)).get("traffic_bytes_per_launch")
         ach = g_fl / (g_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": ach, "peak": pk["bf16_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None, "launches": len(recs),
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic, "launches": len(recs),
                 "avg_launch_ms": g_ms / max(1, len(recs)), "flops_per_launch": g_fl / max(1, len(recs)),
                 "gemm_ms_per_step": g_ms, "gemm_share_of_step": g_ms / ms_step, "peak_src": pk["src"] + " sustained",
                 "whole_step": {"achieved": fl["total"] / (ms_step * 1e-3) / 1e12,

@@ -285,9 +285,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
             continue;
           }
-          if (p.act != VL2_ACT_NONE) {
+          // one branch per activation (warp-uniform), each with a fully unrolled body
+          if (p.act == VL2_ACT_QUICK_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = act_apply(x[j], p.act);
+            for (int j = 0; j < 32; ++j) x[j] = fast_sigmoid_mul(x[j], 1.702f * 1.4426950408889634f);
+          } else if (p.act == VL2_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fast_sigmoid_mul(x[j], 1.4426950408889634f);
+          } else if (p.act == VL2_ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752f));
           }
           if (res != nullptr) {
 #pragma unroll
