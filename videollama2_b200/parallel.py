@@ -139,7 +139,8 @@ def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev
     tot, vit, gat = times[len(times) // 2]
     fused = None
     try:
-        fg = FusedFrameGather(tower, F)
+        import os
+        fg = FusedFrameGather(tower, F, use_multicast=os.environ.get("VL2_BENCH_MULTICAST", "0") == "1")
         ref = encode_frames_sharded(tower, px_dev)
         got = fg.encode(px_dev)
         exact = bool(torch.equal(got, ref))
