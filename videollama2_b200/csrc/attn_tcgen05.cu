@@ -1,10 +1,12 @@
 // FlashAttention-style fused attention for sm_100a (non-causal ViT heads and causal GQA decoder heads).
 //
-// One CTA = one 128-row query tile of one (batch, head).  192 threads:
-//   warps 0..3  softmax / output warps: thread r owns query row r (TMEM lane r) -> no cross-thread reductions
-//   warp 4      TMA producers: lane 0 loads Q and the K ring (2 stages, freed right after Q K^T), lane 1 the V ring
+// One CTA = one 128-row query tile of one (batch, head).  320 threads:
+//   warps 0..7  softmax / output warps: TWO threads per query row (warps w and w+4 share TMEM lane quarter w & 3 and
+//               take key columns [0,64) / [64,128) of every S tile), so each SM sub-partition has two warps to overlap
+//               TMEM loads, MUFU exp2 and packing; the row maximum is exchanged through smem once per tile
+//   warp 8      TMA producers: lane 0 loads Q and the K ring (2 stages, freed right after Q K^T), lane 1 the V ring
 //               (2 stages, freed after P V); P is double buffered so softmax(j) never waits for P V(j-1)
-//   warp 5      TMEM allocator + MMA issuer (one lane):
+//   warp 9      TMEM allocator + MMA issuer (one lane):
 //                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
 //                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
 //                                     B = V tile as MN-major SW128 operand (no transpose pass needed)
@@ -16,7 +18,8 @@
 
 namespace vl2 {
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 320;
+static constexpr int kSoftmaxThreads = 256;
 static constexpr int BQ = 128;
 static constexpr int BKV = 128;
 
@@ -31,7 +34,8 @@ struct AttnCfg {
   static constexpr int kOffV = 3 * kTileBytes;          // 2 stages, released after P V of the tile
   static constexpr int kOffP = 5 * kTileBytes;          // 2 buffers: softmax(j) never waits for P V(j-1)
   static constexpr int kOffBar = kOffP + 2 * kPBytes;
-  static constexpr int kSmemUsed = kOffBar + 256;
+  static constexpr int kOffMax = kOffBar + 256;         // float [2 parities][2 halves][128 rows]
+  static constexpr int kSmemUsed = kOffMax + 2 * 2 * 128 * 4;
   // at least 116 KB so that only one CTA is resident per SM (each CTA allocates all 512 TMEM columns)
   static constexpr int kSmemBytes = (kSmemUsed > 116 * 1024) ? kSmemUsed : 116 * 1024;
   static constexpr int kTmemCols = 512;
@@ -67,6 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* p_full = bars + 11;   // [2]
   uint64_t* o_full = bars + 13;   // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  float* smax = reinterpret_cast<float*>(smem + Cfg::kOffMax);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -79,7 +84,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int n_kv = p.causal ? (qt + 1) : (p.S + BKV - 1) / BKV;
 
   pdl_launch_dependents();
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
@@ -90,13 +95,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], kSoftmaxThreads);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
   }
   pdl_wait();
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -105,7 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producers: lane 0 = Q + K ring, lane 1 = V ring (independent, never block each other)
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
@@ -130,7 +135,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tma_load_3d(sV + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[st], kvh * D + a * 64, j * BKV, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
@@ -173,45 +178,50 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else {
-    // ===================== softmax / output warps (thread == query row) =====================
+    // ===================== softmax / output warps (two threads per query row) =====================
     // One TMEM pass over S per tile; O accumulates in TMEM across tiles (tcgen05.mma accumulate) and is rescaled
     // in place only when a row maximum grows by more than 2^8 (lazy rescale: probabilities stay <= 256, exact after
-    // the final division by l).
-    const int r = warp * 32 + lane;
+    // the final division by l).  Thread (r, hf) owns columns [64 hf, 64 hf + 64) of row r's scores and columns
+    // [hf D/2, (hf+1) D/2) of its output; both threads of a row make identical rescale decisions from the exchanged
+    // row maximum, so their partial sums l share one scale and are added once at the end.
+    const int hf = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
     const int qi = q0 + r;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO + hf * (D / 2);
     float m = -INFINITY, l = 0.f;
     constexpr float kRescaleThreshold = 8.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
-      const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0);
-      const int kv0 = j * BKV;
-      const bool need_mask = (kv0 + BKV > p.S) || (p.causal && (kv0 + BKV - 1 > q0));
+      const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
+      const int kv0 = j * BKV + hf * 64;
+      const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after_sync();
-      uint32_t sv[4][32];
+      uint32_t sv[2][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
+      for (int c = 0; c < 2; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
       tmem_ld_wait();
       if (need_mask) {  // warp-uniform; predicated selects, no per-element branches
         const int lim = p.causal ? min(p.S - 1, qi) : (p.S - 1);   // last visible key index for this row
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             sv[c][i] = (kv0 + c * 32 + i <= lim) ? sv[c][i] : 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
         mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
-        mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
-        mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
       }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      // exchange the half-row maxima (double-buffered by tile parity: one named barrier per tile)
+      float* sm = smax + st * 256;
+      sm[hf * 128 + r] = fmaxf(mx0, mx1);
+      asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+      const float m_tile = fmaxf(sm[r], sm[128 + r]) * p.scale_log2;
       // reference maximum for this tile: keep the old one unless it is too stale
       float m_use = m, alpha = 1.f;
       const bool grow = (m_tile > m + kRescaleThreshold) || (m == -INFINITY);
@@ -227,7 +237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after_sync();
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < D / 64; ++c) {
             uint32_t ov[32];
             tmem_ld_32x32(o_taddr + c * 32, ov);
             tmem_ld_wait();
@@ -238,20 +248,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tmem_st_wait();
         }
       }
-      // probabilities -> smem (bf16, K-major SW128 A operand), row sum
+      // probabilities -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float pr[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { rs0 += pr[i]; rs1 += pr[i + 1]; rs2 += pr[i + 2]; rs3 += pr[i + 3]; }
-        // 32 columns = 4 chunks of 16 B inside atom (c >> 1), chunk index (c & 1) * 4 + g
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int chunk = (c & 1) * 4 + g;
-          uint8_t* dst = sP + st * Cfg::kPBytes + (c >> 1) * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+          const int chunk = c * 4 + g;
+          uint8_t* dst = sP + st * Cfg::kPBytes + hf * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
           *reinterpret_cast<uint4*>(dst) =
               make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
                          pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
@@ -264,12 +273,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before_sync();
       mbar_arrive(&p_full[st]);
     }
+    // combine the two half-row sums, then each thread normalises and stores its half of the output columns
+    float* sl = smax;   // reuse: all max exchanges are complete once every thread passed its last bar.sync
+    asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+    sl[hf * 128 + r] = l;
+    asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+    const float inv = 1.f / (sl[r] + sl[128 + r]);
     mbar_wait(&o_full[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after_sync();
-    const float inv = 1.f / l;
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D + hf * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < D / 64; ++c) {
       uint32_t ov[32];
       tmem_ld_32x32(o_taddr + c * 32, ov);
       tmem_ld_wait();
@@ -288,7 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }

@@ -370,20 +370,22 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
                          float eps) {
   pdl_launch_dependents();
   pdl_wait();
+  extern __shared__ __align__(16) uint8_t dw_smem[];   // [9][C] bf16 weights (registers are spent on the pixel window)
   __shared__ float red[64];
   const int h = blockIdx.x % H;
   const int f = blockIdx.x / H;
   const int c0 = threadIdx.x * 8;
   const bool active = c0 < C;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  uint4 wt[9];  // packed bf16 (register budget: 512 threads x <=128 regs)
+  for (int i = threadIdx.x; i < 9 * (C / 8); i += blockDim.x)
+    reinterpret_cast<uint4*>(dw_smem)[i] = __ldg(reinterpret_cast<const uint4*>(w9c) + i);
   uint4 gp = zero4, bp = zero4;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) wt[k] = active ? __ldg(reinterpret_cast<const uint4*>(w9c + (int64_t)k * C + c0)) : zero4;
   if (active) {
     gp = __ldg(reinterpret_cast<const uint4*>(gamma + c0));
     bp = __ldg(reinterpret_cast<const uint4*>(beta + c0));
   }
+  __syncthreads();
+  const uint32_t wbase = smem_u32(dw_smem) + c0 * 2;
   const __nv_bfloat16* xf = x + (int64_t)f * H * W * C;
   auto load_col = [&](int wcol, uint4 (&col)[3]) {
 #pragma unroll
@@ -395,14 +397,16 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
         col[dh] = zero4;
     }
   };
-  uint4 win[3][3];  // [dw][dh], packed bf16
+  // window of 3 columns + one column prefetched a full iteration ahead (its L2 latency hides behind a pixel's work)
+  uint4 win[4][3];  // [column slot][dh], packed bf16
   load_col(-1, win[0]);
   load_col(0, win[1]);
+  load_col(1, win[2]);
   float pool[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) pool[j] = 0.f;
   for (int wc = 0; wc < W; ++wc) {
-    load_col(wc + 1, win[2]);
+    load_col(wc + 2, win[3]);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -412,7 +416,7 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
       for (int dh = 0; dh < 3; ++dh) {
         float xv[8], wv[8];
         unpack8(win[dw][dh], xv);
-        unpack8(wt[dh * 3 + dw], wv);
+        unpack8(active ? lds128(wbase + (dh * 3 + dw) * C * 2) : zero4, wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j], wv[j], acc[j]);
       }
@@ -438,7 +442,7 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
       for (int j = 0; j < 8; ++j) pool[j] += r[j];
     }
 #pragma unroll
-    for (int dh = 0; dh < 3; ++dh) { win[0][dh] = win[1][dh]; win[1][dh] = win[2][dh]; }
+    for (int dh = 0; dh < 3; ++dh) { win[0][dh] = win[1][dh]; win[1][dh] = win[2][dh]; win[2][dh] = win[3][dh]; }
   }
   if (active && pool_partial != nullptr) {
     float* pp = pool_partial + ((int64_t)f * H + h) * C + c0;
@@ -832,7 +836,15 @@ extern "C" int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void*
   // `pooled` layout: [F*C] pooled means followed by [F*H*C] per-row partial sums (workspace); see vl2.h.
   int threads = (C / 8 + 31) / 32 * 32;
   float* partial = pooled ? pooled + (int64_t)F * C : nullptr;
-  launch_kernel(dwconv3x3_ln_silu_kernel, dim3((unsigned)(F * H)), dim3(threads), 0, (cudaStream_t)stream, 1, 
+  const size_t dw_smem = (size_t)9 * C * sizeof(bf16);
+  if (dw_smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VL2_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_ln_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 4096 * 2));
+      attr_set = true;
+    }
+  }
+  launch_kernel(dwconv3x3_ln_silu_kernel, dim3((unsigned)(F * H)), dim3(threads), dw_smem, (cudaStream_t)stream, 1, 
       (const bf16*)x, (const bf16*)w9c, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, partial, H, W, C, eps);
   VL2_CHECK_LAUNCH("dwconv3x3_ln_silu_kernel");
   if (pooled) {
