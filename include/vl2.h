@@ -123,6 +123,11 @@ typedef struct vl2_attn_args {
   int32_t reserved;
 } vl2_attn_args;
 int vl2_attention(const vl2_attn_args* args, void* stream);
+/* Debug aid: with args->reserved == 777 one softmax thread of CTA (0,0,0) accumulates the cycles it spends in each
+ * phase of the key-tile loop; this call synchronises the device and copies the 16 counters to host memory
+ * ([0] wait S, [1] TMEM load, [2] mask+max+exchange, [3] wait PV / rescale, [4] exp2+pack+st.shared, [5] fence+arrive,
+ *  [6] number of key tiles). */
+int vl2_debug_attn_trace(long long* host_out16);
 
 /* Single-token decode attention over a KV cache (HF:mistral/modeling_mistral.py:122-177 with a DynamicCache):
  * q bf16 [Hq*D]; k_cache / v_cache bf16 rows of ldkv elements (kv head h at columns [h*D, +D)), positions 0..n_pos-1;

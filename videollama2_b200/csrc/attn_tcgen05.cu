@@ -42,7 +42,12 @@ struct AttnCfg {
   static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
 };
 
+// Debug cycle trace (vl2_attn_args.reserved == 777): block (0,0,0), softmax thread 0 accumulates the cycles it spends
+// in each phase of the key-tile loop; read back with vl2_debug_attn_trace().
+__device__ long long g_attn_trace[16];
+
 struct AttnParams {
+  int trace;
   void* out;
   int64_t ldo;
   int S, Hq, group;  // group = Hq / Hkv
@@ -192,17 +197,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     float m = -INFINITY, l = 0.f;
     constexpr float kRescaleThreshold = 8.f;
 
+    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    long long t0 = 0, acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VL2_TR(i) do { if (tr) { const long long t1 = clock64(); acc_t[i] += t1 - t0; t0 = t1; } } while (0)
     for (int j = 0; j < n_kv; ++j) {
+      if (tr) t0 = clock64();
       const int st = j & 1;
       const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
       const int kv0 = j * BKV + hf * 64;
       const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after_sync();
+      VL2_TR(0);   // waiting for S_j
       uint32_t sv[2][32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
       tmem_ld_wait();
+      VL2_TR(1);   // TMEM load
       if (need_mask) {  // warp-uniform; predicated selects, no per-element branches
         const int lim = p.causal ? min(p.S - 1, qi) : (p.S - 1);   // last visible key index for this row
 #pragma unroll
@@ -221,6 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       float* sm = smax + st * 256;
       sm[hf * 128 + r] = fmaxf(mx0, mx1);
       asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+      VL2_TR(2);   // mask + max + exchange barrier
       const float m_tile = fmaxf(sm[r], sm[128 + r]) * p.scale_log2;
       // reference maximum for this tile: keep the old one unless it is too stale
       float m_use = m, alpha = 1.f;
@@ -248,6 +260,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tmem_st_wait();
         }
       }
+      VL2_TR(3);   // waiting for P V(j-2) / rescale
       // probabilities -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
@@ -268,11 +281,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
+      VL2_TR(4);   // exp2 + pack + st.shared
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&p_full[st]);
+      VL2_TR(5);   // proxy fence + arrive
     }
+    if (tr) {
+      for (int i = 0; i < 6; ++i) g_attn_trace[i] = acc_t[i];
+      g_attn_trace[6] = n_kv;
+    }
+#undef VL2_TR
     // combine the two half-row sums, then each thread normalises and stores its half of the output columns
     float* sl = smax;   // reuse: all max exchanges are complete once every thread passed its last bar.sync
     asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
@@ -332,6 +352,7 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   AttnParams p;
+  p.trace = (a->reserved == 777) ? 1 : 0;
   p.out = a->out; p.ldo = a->ldo; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
@@ -360,4 +381,11 @@ extern "C" int vl2_attention(const vl2_attn_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->D == 64) return launch_attn<64>(a, st);
   return launch_attn<128>(a, st);
+}
+
+// Debug: copy the cycle trace of the last traced vl2_attention launch (see g_attn_trace) to host memory.
+extern "C" int vl2_debug_attn_trace(long long* host_out16) {
+  VL2_CHECK_CUDA(cudaDeviceSynchronize());
+  VL2_CHECK_CUDA(cudaMemcpyFromSymbol(host_out16, vl2::g_attn_trace, 16 * sizeof(long long)));
+  return VL2_OK;
 }
