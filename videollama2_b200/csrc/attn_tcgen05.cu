@@ -4,8 +4,8 @@
 //   warps 0..7  softmax / output warps: TWO threads per query row (warps w and w+4 share TMEM lane quarter w & 3 and
 //               take key columns [0,64) / [64,128) of every S tile), so each SM sub-partition has two warps to overlap
 //               TMEM loads, MUFU exp2 and packing; the row maximum is exchanged through smem once per tile
-//   warp 8      TMA producers: lane 0 loads Q and the K ring (2 stages, freed right after Q K^T), lane 1 the V ring
-//               (2 stages, freed after P V); P is double buffered so softmax(j) never waits for P V(j-1)
+//   warp 8      TMA producers: lane 0 loads Q and the K ring (3 stages, freed right after Q K^T: K_{j+2} is requested two
+//               tiles ahead), lane 1 the V ring (2 stages, freed after P V); P is double buffered for D=64
 //   warp 9      TMEM allocator + MMA issuer (one lane):
 //                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
 //                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
@@ -29,11 +29,14 @@ struct AttnCfg {
   static constexpr int kTileBytes = BKV * D * 2;        // one Q / K / V tile
   static constexpr int kAtomBytes = 128 * 128;          // 128 rows x 128 B
   static constexpr int kPBytes = BQ * BKV * 2;          // 32 KB
+  static constexpr int kKStages = 3;                    // K_{j+2} is requested two tiles ahead (TMA latency > one tile)
+  static constexpr int kVStages = 2;
+  static constexpr int kPBufs = (D == 64) ? 2 : 1;      // D=128: Q + 3K + 2V + P = 224 KB
   static constexpr int kOffQ = 0;
-  static constexpr int kOffK = kTileBytes;              // 2 stages, released as soon as Q K^T of the tile has run
-  static constexpr int kOffV = 3 * kTileBytes;          // 2 stages, released after P V of the tile
-  static constexpr int kOffP = 5 * kTileBytes;          // 2 buffers: softmax(j) never waits for P V(j-1)
-  static constexpr int kOffBar = kOffP + 2 * kPBytes;
+  static constexpr int kOffK = kTileBytes;              // released as soon as Q K^T of the tile has run
+  static constexpr int kOffV = (1 + kKStages) * kTileBytes;               // released after P V of the tile
+  static constexpr int kOffP = (1 + kKStages + kVStages) * kTileBytes;
+  static constexpr int kOffBar = kOffP + kPBufs * kPBytes;
   static constexpr int kOffMax = kOffBar + 256;         // float [2 parities][2 halves][128 rows]
   static constexpr int kSmemUsed = kOffMax + 2 * 2 * 128 * 4;
   // at least 116 KB so that only one CTA is resident per SM (each CTA allocates all 512 TMEM columns)
@@ -68,14 +71,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sP = smem + Cfg::kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* p_full = bars + 11;   // [2]
-  uint64_t* o_full = bars + 13;   // [2]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;   // [2]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* o_full = bars + 15;   // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 17);
   float* smax = reinterpret_cast<float*>(smem + Cfg::kOffMax);
 
   const int warp = threadIdx.x >> 5;
@@ -94,9 +97,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Cfg::kKStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
@@ -123,8 +128,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int a = 0; a < Cfg::kAtoms; ++a)
         tma_load_3d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, head * D + a * 64, q0, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        const int st = j % Cfg::kKStages;
+        mbar_wait(&k_empty[st], ((j / Cfg::kKStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
@@ -148,9 +153,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t q_addr = smem_u32(sQ);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
+        const int ks = j % Cfg::kKStages;
+        mbar_wait(&k_full[ks], (j / Cfg::kKStages) & 1);
         tc_fence_after_sync();
-        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
+        const uint32_t k_addr = smem_u32(sK + ks * Cfg::kTileBytes);
         const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -159,18 +165,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                        idesc_qk, kk != 0);
         }
         umma_commit(&s_full[st]);
-        umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
+        umma_commit(&k_empty[ks]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(&p_full[st], (j >> 1) & 1);
+        const int pb = (Cfg::kPBufs == 2) ? st : 0;
+        mbar_wait(&p_full[pb], (Cfg::kPBufs == 2) ? ((j >> 1) & 1) : (j & 1));
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
-        const uint32_t p_addr = smem_u32(sP + st * Cfg::kPBytes);
+        const uint32_t p_addr = smem_u32(sP + pb * Cfg::kPBytes);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
@@ -241,52 +248,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         m_use = (m_tile == -INFINITY) ? 0.f : m_tile;   // fully masked rows stay finite
         alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
       }
-      // P is double buffered: buffer (j & 1) was last read by P V(j-2); O (TMEM) may only be rescaled once P V(j-1)
-      // is complete
-      if (j > 1) mbar_wait(&o_full[st], ((j >> 1) & 1) ^ 1);
-      if (j > 0) {
-        if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc_fence_after_sync();
+      // O (TMEM) may only be rescaled once P V(j-1) is complete
+      bool pv_prev_done = false;
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        pv_prev_done = true;
+        tc_fence_after_sync();
 #pragma unroll
-          for (int c = 0; c < D / 64; ++c) {
-            uint32_t ov[32];
-            tmem_ld_32x32(o_taddr + c * 32, ov);
-            tmem_ld_wait();
+        for (int c = 0; c < D / 64; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32(o_taddr + c * 32, ov);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st_32x32(o_taddr + c * 32, ov);
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st_32x32(o_taddr + c * 32, ov);
         }
+        tmem_st_wait();
       }
-      VL2_TR(3);   // waiting for P V(j-2) / rescale
-      // probabilities -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
+      VL2_TR(3);   // rescale (rare)
+      // probabilities: even columns on the MUFU pipe (ex2.approx), odd columns on the FMA pipe (degree-3 polynomial,
+      // rel. error 7.5e-5, far below bf16's 3.9e-3) so that the 16/clk/SM MUFU limit covers only half of the tile
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      uint4 pk[8];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         float pr[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
+        for (int i = 0; i < 32; i += 2) {
+          pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
+          pr[i + 1] = poly_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_use));
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { rs0 += pr[i]; rs1 += pr[i + 1]; rs2 += pr[i + 2]; rs3 += pr[i + 3]; }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = c * 4 + g;
-          uint8_t* dst = sP + st * Cfg::kPBytes + hf * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) =
-              make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
-                         pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
-        }
+        for (int g = 0; g < 4; ++g)
+          pk[c * 4 + g] = make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
+                                     pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
       }
+      VL2_TR(4);   // exp2 + pack
+      // the P buffer being overwritten was last read by P V(j - kPBufs)
+      const int pb = (Cfg::kPBufs == 2) ? st : 0;
+      if (Cfg::kPBufs == 2) {
+        if (j > 1) mbar_wait(&o_full[st], ((j >> 1) & 1) ^ 1);
+      } else if (j > 0 && !pv_prev_done) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+      }
+      // -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        sts128(smem_u32(sP) + pb * Cfg::kPBytes + hf * Cfg::kAtomBytes + r * 128 + ((ch ^ (r & 7)) << 4), pk[ch]);
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
-      VL2_TR(4);   // exp2 + pack + st.shared
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&p_full[st]);
-      VL2_TR(5);   // proxy fence + arrive
+      mbar_arrive(&p_full[pb]);
+      VL2_TR(5);   // wait P V(j - kPBufs) + st.shared + proxy fence + arrive
     }
     if (tr) {
       for (int i = 0; i < 6; ++i) g_attn_trace[i] = acc_t[i];
