@@ -125,7 +125,7 @@ typedef struct vl2_attn_args {
 int vl2_attention(const vl2_attn_args* args, void* stream);
 /* Debug aid: with args->reserved == 777 one softmax thread of CTA (0,0,0) accumulates the cycles it spends in each
  * phase of the key-tile loop; this call synchronises the device and copies the 16 counters to host memory
- * ([0] wait S, [1] TMEM load, [2] mask+max+exchange, [3] rescale, [4] exp2+pack, [5] wait PV+st.shared+fence+arrive,
+ * ([0] wait S, [1] TMEM load, [2] mask+max+exchange, [3] wait PV / rescale, [4] exp2+pack+st.shared, [5] fence+arrive,
  *  [6] number of key tiles). */
 int vl2_debug_attn_trace(long long* host_out16);
 

@@ -271,20 +271,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (x <= ~8): round-to-nearest split x = i + f, f in [-0.5, 0.5], degree-3 minimax polynomial
-// for 2^f (max rel. error 7.5e-5), exponent add for 2^i.  Used for half of the softmax probabilities so that the MUFU
-// pipe (16 ex2/clk/SM) is no longer the attention kernel's floor.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;   // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);
-  float pq = fmaf(0.05517166769f, f, 0.24261112209f);
-  pq = fmaf(pq, f, 0.69326098571f);
-  pq = fmaf(pq, f, 0.99992807355f);
-  const int i = __float_as_int(t) - 0x4B400000;
-  return __int_as_float(__float_as_int(pq) + (i << 23));
-}
-
 // explicit shared-space 16-byte accesses on 32-bit shared addresses (keeps the compiler from emitting generic LD/ST)
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
