@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--decode-tokens", type=int, default=16, help="extra (untimed-region) KV-cache decode measurement; 0 = skip")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
@@ -187,9 +188,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created: keep fd 1 clean (rank 0 prints
+        # ONE JSON line) by pointing it at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     llm = presets.MISTRAL_7B if args.model == "mistral7b" else presets.QWEN2_7B
     cfg = presets.make_config(llm, FRAMES)
     fl = presets.flops(cfg, FRAMES, PROMPT)
@@ -256,6 +267,22 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # KV-cache decode: greedy tokens after the prefill through the public generate() API
+    decode = None
+    if args.decode_tokens > 0 and rank == 0:
+        n_new = args.decode_tokens + 1
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        out_ids = model.generate(ids_host, images=[(px_dev, "video")], attention_mask=mask, max_new_tokens=n_new,
+                                 do_sample=False, use_cache=True, eos_token_id=None)
+        torch.cuda.synchronize()
+        t_b = time.perf_counter()
+        got = int(out_ids.shape[1])
+        if got > 1:
+            ms_tok = ((t_b - t_a) * 1e3 - ms_e2e) / (got - 1)
+            decode = {"new_tokens": got, "ms_per_token": ms_tok, "tok_per_s": 1e3 / ms_tok if ms_tok > 0 else None,
+                      "note": "greedy, batch 1, weight-streaming GEMV + single-token attention kernels; host loop, no graph"}
 
     # dominant-kernel roofline: every tcgen05 GEMM launch of one step bracketed by CUDA events on the launch stream
     roof = None
@@ -355,7 +382,7 @@ def main():
             "e2e": {"value": world * S / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": px_host.numel() * 2 + ids_host.numel() * 8, "d2h_bytes_per_step": 8,
                     "api": "Videollama2MistralForCausalLM.generate(ids, images=[(frames,'video')], max_new_tokens=1)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "decode": decode,
         }
         if fp is not None:
             line["frame_parallel"] = fp

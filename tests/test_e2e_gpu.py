@@ -174,3 +174,44 @@ def test_no_cpu_fallback(setup):
     cfg, sd, px, ids, gold, model = setup
     with pytest.raises(Vl2Error):
         model.get_vision_tower()(px)                                           # CPU tensor must be refused loudly
+
+
+@pytest.mark.parametrize("frames", [1, 7, 32])
+def test_frame_count_edges(cuda, frames):
+    """T = 1 (a single frame: every Conv3d window touches the zero padding), odd T, and the reference's MAX_FRAMES = 32
+    (videollama2/constants.py:21) at tiny width, against the fp32 oracle; token count follows (T//2+1) * 3 * 3 here."""
+    import dataclasses
+    from oracle import synth, torch_ref
+    cfg = dataclasses.replace(synth.CONFIGS["tiny"], frames=frames, name=f"tiny_f{frames}")
+    sd = synth.state_dict(cfg)
+    px, ids = synth.inputs(cfg)
+    gold = torch_ref.full_forward(sd, cfg, px, ids, torch.float32)
+    noise = torch_ref.full_forward(sd, cfg, px, ids, torch.bfloat16)
+    model = build_engine(cfg, sd, cuda)
+    mm = model.encode_images_or_videos([(px.to(cuda), "video")])
+    assert mm.shape == (1, cfg.vis_tokens, cfg.llm.hidden) and cfg.vis_tokens == (frames // 2 + 1) * 9
+    assert rel(mm[0], gold["mm"]) < _tol(rel(noise["mm"], gold["mm"]))
+    out = model(input_ids=ids, attention_mask=torch.ones_like(ids), images=[(px.to(cuda), "video")])
+    assert rel(out.logits[0], gold["logits"]) < _tol(rel(noise["logits"], gold["logits"]))
+
+
+def test_batch_of_two_videos_and_ragged_prompts(setup, cuda):
+    """encode_images_or_videos with b = 2 (videollama2_arch.py:117-132) and a ragged batch through forward():
+    per-sample results equal the single-sample runs bit for bit, padded logits rows are zero."""
+    cfg, sd, px, ids, gold, model = setup
+    px2 = (px * 0.7).to(cuda)
+    both = model.encode_images_or_videos([(px.to(cuda), "video"), (px2, "video")])
+    assert both.shape[0] == 2
+    assert torch.equal(both[0], model.encode_images_or_videos([(px.to(cuda), "video")])[0])
+    assert torch.equal(both[1], model.encode_images_or_videos([(px2, "video")])[0])
+    ids_b = torch.stack([ids[0], ids[0].clone()])
+    ids_b[1, 4] = 9            # second sample: text only (consumes a feature slot, inserts nothing: arch.py:181-191)
+    mask_b = torch.ones_like(ids_b, dtype=torch.bool)
+    out = model(input_ids=ids_b, attention_mask=mask_b, images=[(px.to(cuda), "video"), (px2, "video")])
+    S_long, S_short = cfg.seq, cfg.prompt
+    assert out.logits.shape == (2, S_long, cfg.llm.vocab)
+    single = model(input_ids=ids, attention_mask=torch.ones_like(ids), images=[(px.to(cuda), "video")])
+    assert torch.equal(out.logits[0], single.logits[0])
+    assert float(out.logits[1, S_short:].abs().max()) == 0.0
+    text_only = model(inputs_embeds=model.get_model().embed_tokens(ids_b[1:2]))
+    assert torch.equal(out.logits[1, :S_short], text_only.logits[0])
