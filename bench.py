@@ -355,6 +355,14 @@ def main():
             model.get_vision_tower().enable_cuda_graphs(True)
         fp = parallel.bench_frame_parallel(model, px_dev, rank, world, dev, iters=max(3, args.steps))
         fp["vit_1gpu_ms"] = t_vit
+        fp["speedup_vs_1gpu"] = t_vit / fp["vit_shard_plus_gather_ms"]
+        # the same stage on a batch of `world` videos (16 frames per GPU): the shape at which frame sharding scales
+        px_many = px_dev.repeat(world, 1, 1, 1)
+        fpb = parallel.bench_frame_parallel(model, px_many, rank, world, dev, iters=3, fused=False)
+        fp["batched_videos"] = {"videos": world, "frames": int(px_many.shape[0]), "ms": fpb["vit_shard_plus_gather_ms"],
+                                "frames_per_s": fpb["frames_per_s"], "all_gather_ms": fpb["all_gather_ms"],
+                                "speedup_vs_1gpu_frames_per_s": fpb["frames_per_s"] / (FRAMES / (t_vit * 1e-3))}
+        del px_many
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -82,14 +82,16 @@ typedef struct vl2_gemm_args {
   int32_t reserved2;
   /* RMSNorm folded into the GEMMs around it (HF:mistral/modeling_mistral.py:182-199): with gamma pre-multiplied into
    * W's columns, rmsnorm(x) W^T = rsqrt(mean(x^2) + eps) * (x W'^T).
-   *   rms_sumsq_in  fp32 [M]: sum_k x[m,k]^2 of THIS GEMM's A rows -> the accumulator is scaled by
-   *                 rsqrt(rms_sumsq_in[m] * rms_inv_dim + rms_eps) before bias/activation (NULL = off)
-   *   sumsq_out     fp32 [M]: the epilogue atomically adds sum_n C[m,n]^2 of the bf16-rounded outputs it writes (the
-   *                 next norm's statistics come for free from the producing residual GEMM)
-   *   sumsq_zero    fp32 [M]: zeroed by this launch (the buffer the NEXT producer will accumulate into). */
+   *   rms_sumsq_in  fp32 [M, rms_nparts]: partial sums of squares of THIS GEMM's A rows (summed in a fixed order) ->
+   *                 the accumulator is scaled by rsqrt(sum_p rms_sumsq_in[m,p] * rms_inv_dim + rms_eps) before
+   *                 bias/activation (NULL = off)
+   *   sumsq_out     fp32 [M, N/32]: the epilogue writes, per 32 output columns, sum C[m,n]^2 of the bf16-rounded outputs
+   *                 (a 64-column span writes its sum to the first slot and 0 to the second): the next norm's statistics
+   *                 come for free from the producing residual GEMM, with no atomics (bit-reproducible). */
   const float* rms_sumsq_in;
   float* sumsq_out;
-  float* sumsq_zero;
+  int32_t rms_nparts;
+  int32_t reserved3;
   float rms_inv_dim;
   float rms_eps;
 } vl2_gemm_args;

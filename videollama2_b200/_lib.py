@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("act", C.c_int32), ("out_f32", C.c_int32), ("reserved", C.c_int32),
         ("bcast_out", C.c_void_p * 8), ("mc_out", C.c_void_p), ("n_bcast", C.c_int32), ("reserved2", C.c_int32),
-        ("rms_sumsq_in", C.c_void_p), ("sumsq_out", C.c_void_p), ("sumsq_zero", C.c_void_p),
+        ("rms_sumsq_in", C.c_void_p), ("sumsq_out", C.c_void_p), ("rms_nparts", C.c_int32), ("reserved3", C.c_int32),
         ("rms_inv_dim", C.c_float), ("rms_eps", C.c_float),
     ]
 

@@ -61,7 +61,7 @@ struct GemmParams {
   // folded RMSNorm (see vl2.h)
   const float* rms_sumsq_in;
   float* sumsq_out;
-  float* sumsq_zero;
+  int rms_nparts;
   float rms_inv_dim, rms_eps;
 };
 
@@ -226,8 +226,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int i = etid; i < BN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       }
       float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
-      if (p.rms_sumsq_in != nullptr && row_ok) rs *= rsqrtf(p.rms_sumsq_in[row] * p.rms_inv_dim + p.rms_eps);
-      if (p.sumsq_zero != nullptr && row_ok && grp == 0 && tile < p.num_m_tiles) p.sumsq_zero[row] = 0.f;  // n-tile 0 only
+      if (p.rms_sumsq_in != nullptr && row_ok) {
+        // sum the producer's per-32-column partials in a fixed order (deterministic: no atomics anywhere)
+        const float* pp = p.rms_sumsq_in + (int64_t)row * p.rms_nparts;
+        float q = 0.f;
+        int i = 0;
+        for (; i + 4 <= p.rms_nparts; i += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(pp + i);
+          q += (t4.x + t4.y) + (t4.z + t4.w);
+        }
+        for (; i < p.rms_nparts; ++i) q += pp[i];
+        rs *= rsqrtf(q * p.rms_inv_dim + p.rms_eps);
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
@@ -329,7 +339,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
           }
         }
-        if (p.sumsq_out != nullptr && row_ok && !swiglu && !p.out_f32) atomicAdd(p.sumsq_out + row, ssq);
+        if (p.sumsq_out != nullptr && row_ok && !swiglu && !p.out_f32) {
+          // one slot per 32 output columns: this span owns slots col0/32 (its sum) and col0/32 + 1 (zero)
+          float* slot = p.sumsq_out + (int64_t)row * (p.N >> 5) + (col0 >> 5);
+          slot[0] = ssq;
+          if (span > 32) slot[1] = 0.f;
+        }
         if (!p.out_f32) {
           __syncwarp();
           // smem -> global, full lines.  Output span: `span` columns (or span/2 for SwiGLU).
@@ -390,7 +405,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
   p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
-  p.rms_sumsq_in = a->rms_sumsq_in; p.sumsq_out = a->sumsq_out; p.sumsq_zero = a->sumsq_zero;
+  p.rms_sumsq_in = a->rms_sumsq_in; p.sumsq_out = a->sumsq_out; p.rms_nparts = a->rms_nparts;
   p.rms_inv_dim = a->rms_inv_dim; p.rms_eps = a->rms_eps;
   p.n_bcast = a->n_bcast;
   p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
@@ -477,8 +492,9 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
               VL2_E_BADALIGN, "vl2_gemm_bf16: pointers must be 16-byte aligned");
   VL2_REQUIRE(a->act >= VL2_ACT_NONE && a->act <= VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: unknown act %d",
               a->act);
-  VL2_REQUIRE(a->sumsq_out == nullptr || (!a->out_f32 && a->act != VL2_ACT_SWIGLU), VL2_E_UNSUPPORTED,
-              "vl2_gemm_bf16: sumsq_out supports bf16, non-SwiGLU outputs only");
+  VL2_REQUIRE(a->sumsq_out == nullptr || (!a->out_f32 && a->act != VL2_ACT_SWIGLU && a->N % 32 == 0), VL2_E_UNSUPPORTED,
+              "vl2_gemm_bf16: sumsq_out supports bf16, non-SwiGLU outputs with N %% 32 == 0 only");
+  VL2_REQUIRE(a->rms_sumsq_in == nullptr || a->rms_nparts > 0, VL2_E_BADSHAPE, "vl2_gemm_bf16: rms_nparts must be positive");
   VL2_REQUIRE(a->n_bcast >= 0 && a->n_bcast <= 8, VL2_E_BADSHAPE, "vl2_gemm_bf16: n_bcast must be in [0,8]");
   if (a->n_bcast > 0 || a->mc_out != nullptr) {
     VL2_REQUIRE(!a->out_f32 && a->act != VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED,

@@ -79,19 +79,20 @@ class DecoderEngine:
         return self.w["embed"]
 
     # ---- prefill ---------------------------------------------------------------------------------------------
-    def _layer(self, L, x: torch.Tensor, S: int, pos0: int, qkv_out: Optional[torch.Tensor], ss_x: torch.Tensor,
-               ss_h: torch.Tensor) -> torch.Tensor:
-        """One decoder layer.  ss_x holds sum(x^2) per row of the incoming residual stream; on return it holds the
-        statistics of the outgoing stream (accumulated by the down_proj epilogue).  ss_h is scratch of the same shape,
-        all zeros on entry and on return."""
+    def _layer(self, L, x: torch.Tensor, S: int, pos0: int, qkv_out: Optional[torch.Tensor], ss_x: torch.Tensor):
+        """One decoder layer.  ss_x [S, parts]: partial sums of squares of the incoming residual stream's rows.
+        Returns (outgoing stream, its partial sums of squares [S, H/32] written by the down_proj epilogue)."""
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
         qkv = ops.gemm(x, L["wqkv"], bias=L.get("bqkv"), out=qkv_out, rms_in=ss_x, rms_eps=self.eps)
         ops.rope_inplace(qkv, S, Hq, Hkv, D, 0, Hq * D, pos0, self.w["inv_freq"])
         o = ops.attention(qkv[:, : Hq * D], qkv[:, Hq * D: (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], B=1, S=S, Hq=Hq,
                           Hkv=Hkv, D=D, causal=True, scale=D ** -0.5)
-        x = ops.gemm(o, L["wo"], residual=x, sumsq_out=ss_h, sumsq_zero=ss_x)     # stats of the mid-layer stream
-        h = ops.gemm(x, L["wgu"], act=ops.ACT_SWIGLU, rms_in=ss_h, rms_eps=self.eps)
-        return ops.gemm(h, L["wd"], residual=x, sumsq_out=ss_x, sumsq_zero=ss_h)  # stats for the next layer
+        ss_mid = torch.empty((S, self.H // 32), device=x.device, dtype=torch.float32)
+        x = ops.gemm(o, L["wo"], residual=x, sumsq_out=ss_mid)                      # stats of the mid-layer stream
+        h = ops.gemm(x, L["wgu"], act=ops.ACT_SWIGLU, rms_in=ss_mid, rms_eps=self.eps)
+        ss_out = torch.empty((S, self.H // 32), device=x.device, dtype=torch.float32)
+        x = ops.gemm(h, L["wd"], residual=x, sumsq_out=ss_out)                      # stats for the next layer
+        return x, ss_out
 
     def prefill(self, embeds: torch.Tensor, all_logits: bool = False, keep_cache: bool = False,
                 max_len: Optional[int] = None, _no_graph: bool = False):
@@ -108,9 +109,8 @@ class DecoderEngine:
             self.kv = [torch.empty((cap, width), device=x.device, dtype=torch.bfloat16) for _ in self.layers]
             self.kv_len = S
         ss_x = ops.row_sumsq(x)
-        ss_h = torch.zeros_like(ss_x)
         for i, L in enumerate(self.layers):
-            x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None, ss_x, ss_h)
+            x, ss_x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None, ss_x)
         if all_logits:
             hn = ops.rmsnorm(x, self.w["norm"], self.eps)
             logits = ops.gemm(hn, self.w["lm_head"], out_dtype=torch.float32)

@@ -46,15 +46,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
          bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
-         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None,
-         sumsq_zero: Optional[torch.Tensor] = None) -> torch.Tensor:
+         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
     `bn` forces the tile width (tests); 0 = library heuristic.
     `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
     (epilogue-fused all-gather over NVLink); `mc_ptr`: NVSwitch multicast address used instead when non-zero.
-    `rms_in` (fp32 [M] row sums of squares of `a`) scales row m by rsqrt(rms_in[m]/K + rms_eps): RMSNorm folded into the
-    GEMM (gamma must already be folded into w); `sumsq_out` accumulates the row sums of squares of the outputs,
-    `sumsq_zero` is cleared."""
+    `rms_in` (fp32 [M, parts] partial row sums of squares of `a`) scales row m by rsqrt(sum(rms_in[m])/K + rms_eps):
+    RMSNorm folded into the GEMM (gamma must already be folded into w); `sumsq_out` (fp32 [M, N/32]) receives the
+    per-32-column sums of squares of the bf16 outputs (no atomics: bit-reproducible)."""
     _need_cuda(a, w, bias, residual, row_scale, out)
     _bf16(a, w, residual)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1, "gemm: 2-D, unit inner stride"
@@ -78,19 +77,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
                     out_f32=1 if out.dtype == torch.float32 else 0, reserved=bn)
     if out.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("gemm: out must be bf16 or fp32")
-    for t in (rms_in, sumsq_out, sumsq_zero):
-        if t is not None:
-            assert t.is_cuda and t.dtype == torch.float32 and t.numel() == M and t.is_contiguous()
     if rms_in is not None:
+        assert rms_in.is_cuda and rms_in.dtype == torch.float32 and rms_in.is_contiguous() and rms_in.shape[0] == M
         args.rms_sumsq_in = rms_in.data_ptr()
+        args.rms_nparts = rms_in.numel() // M
         args.rms_inv_dim = 1.0 / K
         args.rms_eps = float(rms_eps)
     if sumsq_out is not None:
-        if out.dtype != torch.bfloat16 or act == ACT_SWIGLU:
-            raise NotImplementedError("gemm: sumsq_out supports bf16, non-SwiGLU outputs")
+        if out.dtype != torch.bfloat16 or act == ACT_SWIGLU or N % 32:
+            raise NotImplementedError("gemm: sumsq_out supports bf16, non-SwiGLU outputs with N % 32 == 0")
+        assert sumsq_out.is_cuda and sumsq_out.dtype == torch.float32 and sumsq_out.is_contiguous()
+        assert tuple(sumsq_out.shape) == (M, N // 32)
         args.sumsq_out = sumsq_out.data_ptr()
-    if sumsq_zero is not None:
-        args.sumsq_zero = sumsq_zero.data_ptr()
     if bcast_ptrs or mc_ptr:
         if out.dtype != torch.bfloat16 or act == ACT_SWIGLU:
             raise NotImplementedError("gemm: broadcast epilogue supports bf16, non-SwiGLU outputs")
@@ -192,7 +190,7 @@ def row_sumsq(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     _bf16(x)
     assert x.is_contiguous() and x.dim() == 2
-    out = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+    out = torch.empty((x.shape[0], 1), device=x.device, dtype=torch.float32)
     check(_lib.load().vl2_row_sumsq(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_sumsq")
     return out
 

@@ -114,7 +114,8 @@ class FusedFrameGather:
         return self.buf.view(self.F, self.S, self.C)[:, 1:].contiguous()
 
 
-def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev, iters: int = 5) -> dict:
+def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev, iters: int = 5,
+                         fused: bool = True) -> dict:
     """Device-timed (CUDA events, max over ranks) ViT(shard) + all-gather for one 16-frame video."""
     tower = model.get_vision_tower()
     F = px_dev.shape[0]
@@ -137,6 +138,10 @@ def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev
         times.append(t.tolist())
     times.sort(key=lambda x: x[0])
     tot, vit, gat = times[len(times) // 2]
+    if not fused:
+        return {"ranks": world, "frames_per_rank": shard_sizes(F, world), "vit_shard_plus_gather_ms": tot,
+                "vit_shard_ms": vit, "all_gather_ms": gat, "frames_per_s": F / (tot * 1e-3),
+                "gather_bytes": int(F * tower.num_patches * tower.hidden_size * 2)}
     fused = None
     try:
         import os
