@@ -231,7 +231,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const float* pp = p.rms_sumsq_in + (int64_t)row * p.rms_nparts;
         float q = 0.f;
         int i = 0;
-        for (; i + 4 <= p.rms_nparts; i += 4) {
+        const int nvec = (p.rms_nparts % 4 == 0) ? p.rms_nparts : 0;   // rows are 16-byte aligned only then
+        for (; i + 4 <= nvec; i += 4) {
           const float4 t4 = *reinterpret_cast<const float4*>(pp + i);
           q += (t4.x + t4.y) + (t4.z + t4.w);
         }
