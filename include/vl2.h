@@ -136,6 +136,14 @@ int vl2_debug_attn_trace(long long* host_out16);
  * out bf16 [Hq*D]. */
 int vl2_attention_decode(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv, int n_pos,
                          int Hq, int Hkv, int D, float scale, void* stream);
+/* CUDA-graph-replayable decode step: the current position is read from DEVICE memory (*pos_dev), so one captured graph
+ * serves every token.  vl2_decode_rope_append rotates q/k of the freshly projected fused row [q|k|v] at position *pos_dev
+ * and copies the row into cache[*pos_dev]; vl2_attention_decode_dyn attends to cache rows 0..*pos_dev (max_pos sizes the
+ * shared-memory score buffer). */
+int vl2_decode_rope_append(void* qkv_row, void* cache, int64_t cache_ld, const int32_t* pos_dev, int Hq, int Hkv, int D,
+                           const float* inv_freq, void* stream);
+int vl2_attention_decode_dyn(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv,
+                             const int32_t* pos_dev, int max_pos, int Hq, int Hkv, int D, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row-wise normalisations (HBM-bound, one pass).

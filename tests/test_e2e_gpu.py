@@ -146,6 +146,34 @@ def test_kv_cache_decode_matches_recompute(setup, cuda):
     assert rel(step, ref) < 1.5e-2
 
 
+def test_graph_replayed_decode_is_bit_exact(setup, cuda):
+    """The single-token step captured as ONE CUDA graph (token and position in device memory, K/V appended by the
+    RoPE kernel) must produce the same tokens and logits as the eager decode loop, across two generate() calls that
+    reuse the captured graph, and with a stopping criterion that ends the loop early."""
+    cfg, sd, px, ids, gold, model = setup
+    imgs = [(px.to(cuda), "video")]
+    dec = model.get_model().decoder
+    eager = model.generate(ids, images=imgs, max_new_tokens=7, do_sample=False, use_cache=True)
+    emb = gold["inputs_embeds"].to(torch.bfloat16).to(cuda)
+    l0, _ = dec.prefill(emb, all_logits=False, keep_cache=True, max_len=emb.shape[0] + 4)
+    t0 = int(l0[0].argmax())
+    eager_logits = dec.decode_step(model.get_model().embed_tokens(torch.tensor([t0]))).clone()
+    model.enable_cuda_graphs(True)
+    try:
+        for _ in range(2):
+            assert torch.equal(model.generate(ids, images=imgs, max_new_tokens=7, do_sample=False, use_cache=True), eager)
+        assert dec._decode_graph is not None
+        short = model.generate(ids, images=imgs, max_new_tokens=7, do_sample=False, use_cache=True,
+                               stopping_criteria=[lambda out_ids, _s: out_ids.shape[1] >= 3])
+        assert torch.equal(short, eager[:, :3])
+        dec.prefill(emb, all_logits=False, keep_cache=True, max_len=emb.shape[0] + 4)
+        dec.decode_graph_begin(t0)
+        dec.decode_graph_step()
+        assert torch.equal(dec.decode_graph_logits, eager_logits)
+    finally:
+        model.enable_cuda_graphs(False)
+
+
 def test_cuda_graph_replay_is_bit_exact(setup, cuda):
     """Graph-replayed stages (tower, connector, last-position prefill) must reproduce the eager launches bit for bit,
     also on the second replay and after a different input went through the same graph."""

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libvl2.so")
 SYMBOLS = [
     "vl2_version", "vl2_last_error", "vl2_launch_count",
     "vl2_gemm_bf16", "vl2_gemm_skinny", "vl2_attention", "vl2_attention_decode", "vl2_debug_attn_trace",
+    "vl2_decode_rope_append", "vl2_attention_decode_dyn",
     "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq",
     "vl2_patch_im2col", "vl2_clip_embed_finish",
     "vl2_dwconv3x3_ln_silu", "vl2_se_scale", "vl2_conv3d_im2col",
@@ -69,6 +70,8 @@ def load() -> C.CDLL:
         "vl2_gemm_bf16": [C.POINTER(GemmArgs), vp],
         "vl2_gemm_skinny": [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "vl2_debug_attn_trace": [vp],
+        "vl2_decode_rope_append": [vp, vp, i64, vp, i32, i32, i32, vp, vp],
+        "vl2_attention_decode_dyn": [vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, vp],
         "vl2_attention_decode": [vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, vp],
         "vl2_attention": [C.POINTER(AttnArgs), vp],
         "vl2_layernorm": [vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],

@@ -515,12 +515,14 @@ __global__ void conv3d_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // One CTA per token: cos/sin of the D/2 frequencies go through smem once, then each thread rotates 8 pairs of one
 // head with 16-byte accesses.
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off,
-                            int k_off, int pos0, const float* __restrict__ inv_freq) {
+                            int k_off, int pos0, const float* __restrict__ inv_freq, const int* __restrict__ pos_ptr,
+                            __nv_bfloat16* __restrict__ append_base, int64_t append_ld, int append_width) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float cs[];  // [D/2] cos, [D/2] sin
   const int half = D / 2;
   const int s = blockIdx.x;
+  if (pos_ptr != nullptr) pos0 = *pos_ptr;   // graph-replayed decode step: the position lives in device memory
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     float sn, c;
     sincosf((float)(pos0 + s) * inv_freq[i], &sn, &c);
@@ -545,6 +547,13 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, 
     }
     *reinterpret_cast<uint4*>(p) = pack8(oa);
     *reinterpret_cast<uint4*>(p + half) = pack8(ob);
+  }
+  if (append_base != nullptr) {
+    // decode: append the (rotated) fused row to the KV cache at row `pos0 + s`
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+    uint4* dst = reinterpret_cast<uint4*>(append_base + (int64_t)(pos0 + s) * append_ld);
+    for (int v = threadIdx.x; v < append_width / 8; v += blockDim.x) dst[v] = src[v];
   }
 }
 
@@ -683,11 +692,12 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
 __global__ void __launch_bounds__(256)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                    const __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out, int64_t ldkv, int n_pos,
-                   int group, int D, float scale) {
+                   int group, int D, float scale, const int* __restrict__ pos_ptr, int part_off) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sc[];  // [n_pos] scores, then [4][D] partial outputs
   __shared__ float red[64];
+  if (pos_ptr != nullptr) n_pos = *pos_ptr + 1;   // graph-replayed decode: attend to positions 0..pos
   const int h = blockIdx.x, kvh = h / group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int epl = D / 32;  // elements per lane (2 or 4)
@@ -731,7 +741,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
     o0 = fmaf(pv, bf16_lo(vv), o0);
     o1 = fmaf(pv, bf16_hi(vv), o1);
   }
-  float* part = sc + ((n_pos + 3) & ~3);
+  float* part = sc + (part_off > 0 ? part_off : ((n_pos + 3) & ~3));
   __syncthreads();
   part[grp * D + 2 * t] = o0;
   part[grp * D + 2 * t + 1] = o1;
@@ -882,7 +892,7 @@ extern "C" int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, i
   int threads = (Hq + Hkv) * (D / 16);
   threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
   launch_kernel(rope_kernel, dim3(S), dim3(threads), D * sizeof(float), (cudaStream_t)stream, 1, (bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
-                                                                      inv_freq);
+                inv_freq, (const int*)nullptr, (bf16*)nullptr, (int64_t)0, 0);
   VL2_CHECK_LAUNCH("rope_kernel");
   return VL2_OK;
 }
@@ -926,7 +936,40 @@ extern "C" int vl2_attention_decode(const void* q, const void* k_cache, const vo
     }
   }
   launch_kernel(attn_decode_kernel, dim3(Hq), dim3(256), smem, (cudaStream_t)stream, 1, (const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
-                                                             (bf16*)out, ldkv, n_pos, Hq / Hkv, D, scale);
+                (bf16*)out, ldkv, n_pos, Hq / Hkv, D, scale, (const int*)nullptr, 0);
+  VL2_CHECK_LAUNCH("attn_decode_kernel");
+  return VL2_OK;
+}
+
+// ---- graph-replayable decode step: the token position is read from device memory ------------------------------
+extern "C" int vl2_decode_rope_append(void* qkv_row, void* cache, int64_t cache_ld, const int32_t* pos_dev, int Hq, int Hkv,
+                                      int D, const float* inv_freq, void* stream) {
+  VL2_REQUIRE(qkv_row && cache && pos_dev && inv_freq && D % 16 == 0 && cache_ld % 8 == 0, VL2_E_BADSHAPE,
+              "vl2_decode_rope_append: bad arguments");
+  const int width = (Hq + 2 * Hkv) * D;
+  int threads = (Hq + Hkv) * (D / 16);
+  threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
+  launch_kernel(rope_kernel, dim3(1), dim3(threads), D * sizeof(float), (cudaStream_t)stream, 1, (bf16*)qkv_row, (int64_t)width, 1,
+                Hq, Hkv, D, 0, Hq * D, 0, inv_freq, (const int*)pos_dev, (bf16*)cache, cache_ld, width);
+  VL2_CHECK_LAUNCH("rope_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_attention_decode_dyn(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv,
+                                        const int32_t* pos_dev, int max_pos, int Hq, int Hkv, int D, float scale, void* stream) {
+  VL2_REQUIRE(pos_dev != nullptr && max_pos > 0 && max_pos <= 16384 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && (D == 64 || D == 128),
+              VL2_E_BADSHAPE, "vl2_attention_decode_dyn: bad shape (max_pos=%d Hq=%d Hkv=%d D=%d)", max_pos, Hq, Hkv, D);
+  const int part_off = (max_pos + 3) & ~3;
+  const size_t smem = (size_t)(part_off + (256 / (D / 2)) * D) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      attr = true;
+    }
+  }
+  launch_kernel(attn_decode_kernel, dim3(Hq), dim3(256), smem, (cudaStream_t)stream, 1, (const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache,
+                (bf16*)out, ldkv, 0, Hq / Hkv, D, scale, (const int*)pos_dev, part_off);
   VL2_CHECK_LAUNCH("attn_decode_kernel");
   return VL2_OK;
 }

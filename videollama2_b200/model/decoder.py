@@ -30,11 +30,15 @@ class DecoderEngine:
         self.kv: List[torch.Tensor] = []   # per layer [S_max, (Hq+2Hkv)*D] fused qkv rows (K,V columns = cache)
         self.kv_len = 0
         self._graphed = None
+        self._decode_graph = None   # (graph, tok_dev, pos_dev, logits) of the captured single-token step
+        self.graph_decode = False
 
     def enable_cuda_graphs(self, on: bool = True):
         """Graph the cache-less last-position prefill (the bench / first-token path)."""
         from ..graphs import GraphedStage
         self._graphed = GraphedStage(lambda e: self._prefill_last(e)) if on else None
+        self.graph_decode = on
+        self._decode_graph = None
         return self
 
     def _prefill_last(self, embeds: torch.Tensor) -> torch.Tensor:
@@ -104,9 +108,7 @@ class DecoderEngine:
         S = embeds.shape[0]
         x = embeds
         if keep_cache:
-            cap = max_len or S
-            width = (self.Hq + 2 * self.Hkv) * self.D
-            self.kv = [torch.empty((cap, width), device=x.device, dtype=torch.bfloat16) for _ in self.layers]
+            self._ensure_cache(max_len or S, x.device)
             self.kv_len = S
         ss_x = ops.row_sumsq(x)
         for i, L in enumerate(self.layers):
@@ -118,6 +120,15 @@ class DecoderEngine:
             hn = ops.rmsnorm(x[S - 1:].contiguous(), self.w["norm"], self.eps)
             logits = ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
         return logits, x
+
+    def _ensure_cache(self, cap: int, device) -> None:
+        """The per-layer fused-row cache is allocated once and reused (a captured decode graph holds its addresses)."""
+        if self.kv and self.kv[0].shape[0] >= cap and self.kv[0].device == torch.device(device):
+            return
+        cap = (cap + 255) // 256 * 256
+        width = (self.Hq + 2 * self.Hkv) * self.D
+        self.kv = [torch.empty((cap, width), device=device, dtype=torch.bfloat16) for _ in self.layers]
+        self._decode_graph = None
 
     # ---- KV-cache decode (one token) -----------------------------------------------------------------------
     def decode_step(self, x: torch.Tensor) -> torch.Tensor:
@@ -144,3 +155,67 @@ class DecoderEngine:
         self.kv_len = pos + 1
         hn = ops.rmsnorm(x, self.w["norm"], self.eps)
         return ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
+
+    # ---- the same step as ONE CUDA graph ---------------------------------------------------------------------
+    def _decode_body(self, tok_dev: torch.Tensor, pos_dev: torch.Tensor, stage: torch.Tensor) -> torch.Tensor:
+        """Single-token step whose position and token live in device memory: embeds *tok_dev, appends K/V at *pos_dev,
+        writes argmax(logits) back to tok_dev and increments pos_dev, so one captured graph serves every token."""
+        Hq, Hkv, D = self.Hq, self.Hkv, self.D
+        cap = self.kv[0].shape[0]
+        x = torch.index_select(self.w["embed"], 0, tok_dev)
+        o = torch.empty((1, Hq * D), device=x.device, dtype=torch.bfloat16)
+        for i, L in enumerate(self.layers):
+            cache = self.kv[i]
+            y = ops.rmsnorm(x, self.w["ones"], self.eps)
+            ops.gemm_skinny(y, L["wqkv"], bias=L.get("bqkv"), out=stage)
+            ops.decode_rope_append(stage, cache, pos_dev, Hq, Hkv, D, self.w["inv_freq"])
+            ops.attention_decode_dyn(stage[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
+                                     pos_dev, max_pos=cap, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, out=o)
+            x = ops.gemm_skinny(o, L["wo"], residual=x, out_dtype=torch.bfloat16)
+            y = ops.rmsnorm(x, self.w["ones"], self.eps)
+            h = ops.gemm_skinny(y, L["wgu"], act=ops.ACT_SWIGLU, out_dtype=torch.bfloat16)
+            x = ops.gemm_skinny(h, L["wd"], residual=x, out_dtype=torch.bfloat16)
+        hn = ops.rmsnorm(x, self.w["norm"], self.eps)
+        logits = ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
+        tok_dev.copy_(torch.argmax(logits, dim=1))
+        pos_dev.add_(1)
+        return logits
+
+    def decode_graph_begin(self, first_token: int) -> None:
+        """Arm the graph-replayed decode loop after prefill(keep_cache=True): token := first_token, pos := kv_len."""
+        if not self.kv:
+            raise RuntimeError("decode_graph_begin needs prefill(keep_cache=True) first")
+        dev = self.kv[0].device
+        if self._decode_graph is None:
+            tok_dev = torch.zeros((1,), device=dev, dtype=torch.int64)
+            pos_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
+            stage = torch.empty((1, (self.Hq + 2 * self.Hkv) * self.D), device=dev, dtype=torch.bfloat16)
+            scratch_pos = self.kv[0].shape[0] - 1     # warm-up writes land in the last cache row (rewritten when reached)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    pos_dev.fill_(scratch_pos)
+                    self._decode_body(tok_dev, pos_dev, stage)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                logits = self._decode_body(tok_dev, pos_dev, stage)
+            self._decode_graph = (graph, tok_dev, pos_dev, logits, stage)
+        _, tok_dev, pos_dev, _, _ = self._decode_graph
+        tok_dev.fill_(int(first_token))
+        pos_dev.fill_(self.kv_len)
+
+    def decode_graph_step(self) -> torch.Tensor:
+        """Replay one token; returns the device int64[1] holding the NEW token (argmax), logits stay in the graph's
+        static buffer (`decode_graph_logits`)."""
+        graph, tok_dev, _, _, _ = self._decode_graph
+        if self.kv_len >= self.kv[0].shape[0]:
+            raise RuntimeError(f"KV cache full ({self.kv_len} positions)")
+        graph.replay()
+        self.kv_len += 1
+        return tok_dev
+
+    @property
+    def decode_graph_logits(self) -> torch.Tensor:
+        return self._decode_graph[3]

@@ -145,12 +145,18 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         use_cache = kwargs.get("use_cache", True)
         S = x.shape[0]
         logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache and max_new > 1, max_len=S + max_new)
+        graphed = use_cache and max_new > 1 and dec.graph_decode
         for step in range(max_new):
-            tok = int(torch.argmax(logits[0]).item())
+            tok = int(torch.argmax(logits[0]).item()) if not (graphed and step > 0) else int(tok_dev.item())
             new_ids.append(tok)
             out_ids = torch.tensor([new_ids], dtype=torch.long)
             if tok in eos_ids or any(sc(out_ids, None) for sc in stopping) or step == max_new - 1:
                 break
+            if graphed:   # one graph launch per token: embed, 32 layers, lm_head, argmax all on the device
+                if step == 0:
+                    dec.decode_graph_begin(tok)
+                tok_dev = dec.decode_graph_step()
+                continue
             e = self.get_model().embed_tokens(torch.tensor([tok]))
             if use_cache:
                 logits = dec.decode_step(e)

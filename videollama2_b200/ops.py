@@ -12,7 +12,7 @@ from ._lib import (ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_SIGMOID, ACT_SILU
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "attention_decode", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
@@ -155,6 +155,28 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, S: i
                     ldk=k.stride(0), ldv=v.stride(0), ldo=out.stride(0), B=B, S=S, Hq=Hq, Hkv=Hkv, D=D,
                     causal=1 if causal else 0, scale=float(scale), reserved=0)
     check(_lib.load().vl2_attention(C.byref(args), _stream()), "vl2_attention")
+    return out
+
+
+def decode_rope_append(qkv_row: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tensor, Hq: int, Hkv: int, D: int,
+                       inv_freq: torch.Tensor) -> None:
+    """Graph-replayable: rotate q/k of the fused row at position *pos_dev and append the row to cache[*pos_dev]."""
+    _need_cuda(qkv_row, cache, pos_dev, inv_freq)
+    _bf16(qkv_row, cache)
+    assert qkv_row.is_contiguous() and qkv_row.numel() == (Hq + 2 * Hkv) * D and cache.stride(1) == 1
+    assert pos_dev.dtype == torch.int32 and pos_dev.numel() == 1
+    check(_lib.load().vl2_decode_rope_append(qkv_row.data_ptr(), cache.data_ptr(), cache.stride(0), pos_dev.data_ptr(),
+                                             Hq, Hkv, D, inv_freq.data_ptr(), _stream()), "vl2_decode_rope_append")
+
+
+def attention_decode_dyn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos_dev: torch.Tensor, *,
+                         max_pos: int, Hq: int, Hkv: int, D: int, scale: float, out: torch.Tensor) -> torch.Tensor:
+    _need_cuda(q, k_cache, v_cache, pos_dev, out)
+    _bf16(q, k_cache, v_cache, out)
+    assert k_cache.stride(0) == v_cache.stride(0) and pos_dev.dtype == torch.int32
+    check(_lib.load().vl2_attention_decode_dyn(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+                                               k_cache.stride(0), pos_dev.data_ptr(), max_pos, Hq, Hkv, D, float(scale),
+                                               _stream()), "vl2_attention_decode_dyn")
     return out
 
 
