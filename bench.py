@@ -163,7 +163,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vl2", choices=["vl2", "reference"])
-    ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b"])
+    ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b", "qwen2_7b_v21"],
+                    help="qwen2_7b_v21 = the released VideoLLaMA2.1 geometry: SigLIP-so400m@384 tower + stc_connector_v35")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     ap.add_argument("--decode-tokens", type=int, default=16, help="extra (untimed-region) KV-cache decode measurement; 0 = skip")
@@ -202,7 +203,11 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     llm = presets.MISTRAL_7B if args.model == "mistral7b" else presets.QWEN2_7B
-    cfg = presets.make_config(llm, FRAMES)
+    if args.model == "qwen2_7b_v21":
+        cfg = presets.make_config(llm, FRAMES, "stc_connector_v35", presets.SIGLIP_SO400M_384)
+    else:
+        cfg = presets.make_config(llm, FRAMES)
+    IMG = cfg.vision_config.image_size
     fl = presets.flops(cfg, FRAMES, PROMPT)
     S = fl["S"]
     sd = presets.random_state_dict(cfg, dev)
@@ -213,7 +218,7 @@ def main():
         model.enable_cuda_graphs(True)
 
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    px_host = torch.randn((FRAMES, 3, 336, 336), generator=g).to(torch.bfloat16).pin_memory()
+    px_host = torch.randn((FRAMES, 3, IMG, IMG), generator=g).to(torch.bfloat16).pin_memory()
     ids_host = torch.randint(3, cfg.vocab_size, (1, PROMPT), generator=torch.Generator().manual_seed(1235), dtype=torch.int64)
     ids_host[0, 4] = -201
     px_dev = px_host.to(dev)
@@ -389,7 +394,7 @@ def main():
             "metric": METRIC, "value": world * S / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"VideoLLaMA2-7B ({args.model}) 16 frames@336 + 256-token prompt -> S={S} prefill, last-position logits; "
+            "config": {"workload": f"VideoLLaMA2-7B ({args.model}) 16 frames@{IMG} + 256-token prompt -> S={S} prefill, last-position logits; "
                                    "one video per GPU", "frames": FRAMES, "prompt": PROMPT, "seq": S, "global_batch": world,
                        "parallelism": f"replicas x{world} (+ frame-sharded ViT reported separately)",
                        "cuda_graphs": not args.no_graphs,

@@ -42,13 +42,20 @@ enum {
   VL2_ACT_QUICK_GELU = 1, /* x*sigmoid(1.702x)          HF:clip/modeling_clip.py:339-351 (quick_gelu)      */
   VL2_ACT_SILU = 2,       /* x*sigmoid(x)               projector.py:173 (nn.SiLU), timm LayerNormAct2d     */
   VL2_ACT_GELU_ERF = 3,   /* 0.5x(1+erf(x/sqrt2))       projector.py:128 (nn.GELU)                          */
-  VL2_ACT_SWIGLU = 4      /* out[:,j] = silu(acc[:,2j])*acc[:,2j+1]  HF:mistral/modeling_mistral.py:46-48   */
+  VL2_ACT_SWIGLU = 4,     /* out[:,j] = silu(acc[:,2j])*acc[:,2j+1]  HF:mistral/modeling_mistral.py:46-48   */
+  VL2_ACT_GELU_TANH = 5   /* 0.5x(1+tanh(sqrt(2/pi)(x+0.044715x^3)))  HF SiglipMLP ("gelu_pytorch_tanh"), encoder.py:84-101 */
 };
 
 int vl2_version(void);
 const char* vl2_last_error(void);
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches counter). */
 int64_t vl2_launch_count(void);
+/* Programmatic dependent launch for every subsequent vl2_* launch of this process: 1 = on (each kernel is launched with
+ * the programmatic-stream-serialization attribute; kernels begin with griddepcontrol.launch_dependents and wait with
+ * griddepcontrol.wait before touching their inputs, so a kernel's prologue - for the GEMV: the first weight-stage
+ * prefetches - overlaps the tail of its predecessor), 0 = off, -1 = follow the VL2_PDL environment variable (default off).
+ * Used by the single-token decode graph, where ~230 small kernels run back to back. */
+int vl2_set_pdl(int mode);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense bf16 GEMM on tcgen05 tensor cores:  C[M,Nout] = epi( A[M,K] * W[N,K]^T ).
@@ -105,13 +112,21 @@ int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const float* bias, const void* residual /* bf16 [M,N] or NULL */,
                     void* C, int out_f32, int M, int N, int K, int act, void* stream);
 
+/* GEMV, the M = 1 case of the above as its own entry point (every nn.Linear of a single-token decode step):
+ * y[N] = act(s * W[N,K] x + bias) (+ residual); with rms_eps > 0, s = rsqrt(mean(x^2) + rms_eps): the RMSNorm in front of
+ * the projection (HF:mistral/modeling_mistral.py:35-48) with its gain folded into W's columns, at no extra pass over x.
+ * act as vl2_gemm_skinny.  HBM-bound: 2*N*K bytes. */
+int vl2_gemv_bf16(const void* x, const void* W, const float* bias, const void* residual /* bf16 [N] or NULL */, void* y,
+                  int out_f32, int N, int K, int act, float rms_eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Fused attention (FlashAttention-style, tcgen05 QK^T / PV with TMEM accumulators, TMA-staged K/V).
  *   q: bf16 [B*S, ldq] with head h at columns [q_off + h*D, +D)   (likewise k, v with kv head h / (Hq/Hkv))
  *   out: bf16 [B*S, ldo], head h at columns [h*D, +D).  softmax scale applied to logits in fp32.
  * causal = 0: HF:clip/modeling_clip.py:282-336 (CLIPAttention, 16 heads x 64).
  * causal = 1: HF:mistral/modeling_mistral.py:122-177 / qwen2/modeling_qwen2.py:187-246 (GQA, D=128).
- * D in {64, 128}.
+ * D: any multiple of 8 up to 128 (64 / 128 natively; other widths, e.g. SigLIP-so400m 72, run the next wider kernel with
+ * TMA zero fill beyond the head, heads packed at their true width in memory).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct vl2_attn_args {
   const void* q;
@@ -133,17 +148,19 @@ int vl2_debug_attn_trace(long long* host_out16);
 
 /* Single-token decode attention over a KV cache (HF:mistral/modeling_mistral.py:122-177 with a DynamicCache):
  * q bf16 [Hq*D]; k_cache / v_cache bf16 rows of ldkv elements (kv head h at columns [h*D, +D)), positions 0..n_pos-1;
- * out bf16 [Hq*D]. */
+ * out bf16 [Hq*D].  Split over the KV length (flash-decoding): `workspace` is a caller-owned device buffer of
+ * vl2_attention_decode_workspace(Hq, Hkv, D) bytes holding the per-split partial results.  Hq/Hkv <= 8. */
+size_t vl2_attention_decode_workspace(int Hq, int Hkv, int D);
 int vl2_attention_decode(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv, int n_pos,
-                         int Hq, int Hkv, int D, float scale, void* stream);
+                         int Hq, int Hkv, int D, float scale, void* workspace, void* stream);
 /* CUDA-graph-replayable decode step: the current position is read from DEVICE memory (*pos_dev), so one captured graph
  * serves every token.  vl2_decode_rope_append rotates q/k of the freshly projected fused row [q|k|v] at position *pos_dev
- * and copies the row into cache[*pos_dev]; vl2_attention_decode_dyn attends to cache rows 0..*pos_dev (max_pos sizes the
- * shared-memory score buffer). */
+ * and copies the row into cache[*pos_dev]; vl2_attention_decode_dyn attends to cache rows 0..*pos_dev and is
+ * bit-identical to vl2_attention_decode(n_pos = *pos_dev + 1). */
 int vl2_decode_rope_append(void* qkv_row, void* cache, int64_t cache_ld, const int32_t* pos_dev, int Hq, int Hkv, int D,
                            const float* inv_freq, void* stream);
 int vl2_attention_decode_dyn(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv,
-                             const int32_t* pos_dev, int max_pos, int Hq, int Hkv, int D, float scale, void* stream);
+                             const int32_t* pos_dev, int Hq, int Hkv, int D, float scale, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row-wise normalisations (HBM-bound, one pass).
@@ -161,7 +178,8 @@ int vl2_row_sumsq(const void* x, float* out, int64_t rows, int C, void* stream);
 /* ------------------------------------------------------------------------------------------------------------
  * CLIP patch embedding front/back ends (HF:clip/modeling_clip.py:202-218).
  * vl2_patch_im2col: pixels bf16 [F,3,H,W] (NCHW) -> A bf16 [F*(H/P)*(W/P), Kpad], column = c*P*P + i*P + j, zero
- *   padded to Kpad (Kpad % 64 == 0) so the patch conv becomes vl2_gemm_bf16 against weight[1024, Kpad].
+ *   padded to Kpad (Kpad % 64 == 0) so the patch conv becomes vl2_gemm_bf16 against weight[1024, Kpad].  H / P and
+ *   W / P round down like the strided conv does (SigLIP@384, P = 14: 27 x 27 patches, the last 6 pixels are unused).
  * vl2_clip_embed_finish: tok[f, 0] = cls + pos[0]; tok[f, 1+p] = patch[f*np+p] + pos[1+p]; then pre_layrnorm.
  * ---------------------------------------------------------------------------------------------------------- */
 int vl2_patch_im2col(const void* pixels, void* A, int F, int H, int W, int P, int Kpad, void* stream);

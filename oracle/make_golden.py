@@ -47,7 +47,9 @@ def main():
     fixtures = {"tokenizer": [(p, t, mm_utils.tokenizer_multimodal_token(p, tok, t)) for p, t in PROMPTS]}
     torch.save(fixtures, os.path.join(OUT, "tokenizer_multimodal_token.pt"))
 
-    for name in ("tiny", "tiny_qwen2", "tiny_v35"):
+    import sys
+    names = sys.argv[1:] or ("tiny", "tiny_qwen2", "tiny_v35", "tiny_siglip")
+    for name in names:
         cfg = synth.CONFIGS[name]
         sd = synth.state_dict(cfg)
         px, ids = synth.inputs(cfg)

@@ -63,6 +63,13 @@ def load():
             super().__init__(config, *a, **k)
 
     enc.CLIPVisionModel = _CpuCLIPVisionModel
+
+    class _CpuSiglipVisionModel(enc.SiglipVisionModel):     # encoder.py:96 forces flash_attention_2 the same way
+        def __init__(self, config=None, *a, **k):
+            config._attn_implementation = os.environ.get("VL2_ORACLE_ATTN", "sdpa")
+            super().__init__(config, *a, **k)
+
+    enc.SiglipVisionModel = _CpuSiglipVisionModel
     model = importlib.import_module("videollama2.model")
     _loaded = model
     return model
@@ -85,6 +92,22 @@ def clip_dir(vcfg) -> str:
     return d
 
 
+def siglip_dir(vcfg) -> str:
+    """A local directory whose path contains 'siglip' (encoder.py:159) holding the tower + processor configs."""
+    d = os.path.join(tempfile.gettempdir(), f"vl2_oracle_siglip_{vcfg.hidden}_{vcfg.layers}_{vcfg.image}")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "config.json"), "w") as fh:
+        json.dump({"model_type": "siglip_vision_model", "hidden_size": vcfg.hidden, "intermediate_size": vcfg.inter,
+                   "num_hidden_layers": vcfg.layers, "num_attention_heads": vcfg.heads, "image_size": vcfg.image,
+                   "patch_size": vcfg.patch, "hidden_act": "gelu_pytorch_tanh", "layer_norm_eps": vcfg.eps,
+                   "num_channels": 3}, fh)
+    with open(os.path.join(d, "preprocessor_config.json"), "w") as fh:
+        json.dump({"do_resize": True, "do_rescale": True, "do_normalize": True, "image_processor_type": "SiglipImageProcessor",
+                   "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5], "resample": 3, "rescale_factor": 1 / 255,
+                   "size": {"height": vcfg.image, "width": vcfg.image}}, fh)
+    return d
+
+
 def build_reference_model(cfg, dtype=torch.float32, state=None):
     """Instantiate the reference's Videollama2{Mistral,Qwen2}ForCausalLM for `cfg` (oracle.synth.ModelCfg) on CPU and
     load the synthetic HF-named weights.  dtype float32 -> "G32" golden (fp32 math on bf16-rounded weights);
@@ -102,7 +125,7 @@ def build_reference_model(cfg, dtype=torch.float32, state=None):
     else:
         hf_cfg = model_mod.Videollama2MistralConfig(**common, sliding_window=None)
         cls = model_mod.Videollama2MistralForCausalLM
-    hf_cfg.mm_vision_tower = clip_dir(cfg.vision)
+    hf_cfg.mm_vision_tower = siglip_dir(cfg.vision) if cfg.vision.kind == "siglip" else clip_dir(cfg.vision)
     hf_cfg.mm_projector_type = cfg.projector
     hf_cfg.mm_hidden_size = cfg.vision.hidden
     hf_cfg.mm_vision_select_layer = cfg.select_layer

@@ -24,6 +24,11 @@ class VisionCfg:
     image: int = 336
     patch: int = 14
     eps: float = 1e-5
+    kind: str = "clip"             # "clip" (CLS + pre-LN, quick_gelu) | "siglip" (no CLS, patch bias, gelu-tanh)
+
+    @property
+    def seq(self) -> int:
+        return self.num_patches + (1 if self.kind == "clip" else 0)
 
     @property
     def grid(self) -> int:
@@ -79,12 +84,16 @@ class ModelCfg:
 
 
 CLIP_L_336 = VisionCfg()
+# google/siglip-so400m-patch14-384 (README.md:125-126; dims from the upstream HF config)
+SIGLIP_SO400M_384 = VisionCfg(hidden=1152, inter=4304, layers=27, heads=16, image=384, patch=14, eps=1e-6, kind="siglip")
 MISTRAL_7B = LlmCfg()
 QWEN2_7B = LlmCfg(kind="qwen2", hidden=3584, inter=18944, layers=28, heads=28, kv_heads=4, vocab=152064, eps=1e-6)
 
 TINY_VIT = VisionCfg(hidden=128, inter=256, layers=4, heads=2, image=56, patch=14)
 TINY_LLM = LlmCfg(hidden=256, inter=512, layers=2, heads=4, kv_heads=2, vocab=512)
 TINY_QWEN = LlmCfg(kind="qwen2", hidden=256, inter=512, layers=2, heads=2, kv_heads=1, vocab=512, eps=1e-6)
+# head_dim 72, odd 5x5 grid, intermediate size that is a multiple of 8 but not of 64: the so400m tower's awkward shapes
+TINY_SIGLIP = VisionCfg(hidden=288, inter=304, layers=3, heads=4, image=70, patch=14, eps=1e-6, kind="siglip")
 # "mid": real head dims / tile-tail shapes at a size the CPU oracle finishes in seconds
 MID_VIT = VisionCfg(hidden=256, inter=512, layers=3, heads=4, image=112, patch=14)
 MID_LLM = LlmCfg(hidden=512, inter=1024, layers=2, heads=4, kv_heads=2, vocab=1024)
@@ -93,10 +102,12 @@ CONFIGS: Dict[str, ModelCfg] = {
     "tiny": ModelCfg("tiny", TINY_VIT, TINY_LLM, frames=4, prompt=12),
     "tiny_qwen2": ModelCfg("tiny_qwen2", TINY_VIT, TINY_QWEN, frames=4, prompt=12),
     "tiny_v35": ModelCfg("tiny_v35", TINY_VIT, TINY_LLM, frames=4, prompt=12, projector="stc_connector_v35"),
+    "tiny_siglip": ModelCfg("tiny_siglip", TINY_SIGLIP, TINY_QWEN, frames=4, prompt=12, projector="stc_connector_v35"),
     "mid": ModelCfg("mid", MID_VIT, MID_LLM, frames=6, prompt=40),
     "cfg1": ModelCfg("cfg1", CLIP_L_336, MISTRAL_7B, frames=8, prompt=32),
     "cfg2": ModelCfg("cfg2", CLIP_L_336, MISTRAL_7B, frames=16, prompt=256),
     "cfg3": ModelCfg("cfg3", CLIP_L_336, QWEN2_7B, frames=16, prompt=256),
+    "cfg3_v21": ModelCfg("cfg3_v21", SIGLIP_SO400M_384, QWEN2_7B, frames=16, prompt=256, projector="stc_connector_v35"),
 }
 
 
@@ -107,6 +118,8 @@ Spec = Tuple[str, Tuple[int, ...], str]
 
 
 def vision_specs(v: VisionCfg, prefix: str = "model.vision_tower.vision_tower.vision_model.") -> List[Spec]:
+    if v.kind == "siglip":
+        return siglip_specs(v, prefix)
     s: List[Spec] = [
         (prefix + "embeddings.class_embedding", (v.hidden,), "emb"),
         (prefix + "embeddings.patch_embedding.weight", (v.hidden, 3, v.patch, v.patch), "w"),
@@ -123,6 +136,39 @@ def vision_specs(v: VisionCfg, prefix: str = "model.vision_tower.vision_tower.vi
               (p + "mlp.fc2.weight", (v.hidden, v.inter), "w"), (p + "mlp.fc2.bias", (v.hidden,), "bias"),
               (p + "layer_norm2.weight", (v.hidden,), "gain"), (p + "layer_norm2.bias", (v.hidden,), "bias")]
     s += [(prefix + "post_layernorm.weight", (v.hidden,), "gain"), (prefix + "post_layernorm.bias", (v.hidden,), "bias")]
+    return s
+
+
+def _encoder_layer_specs(v: VisionCfg, p: str) -> List[Spec]:
+    s: List[Spec] = []
+    for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        s += [(p + f"self_attn.{nm}.weight", (v.hidden, v.hidden), "w"), (p + f"self_attn.{nm}.bias", (v.hidden,), "bias")]
+    s += [(p + "layer_norm1.weight", (v.hidden,), "gain"), (p + "layer_norm1.bias", (v.hidden,), "bias"),
+          (p + "mlp.fc1.weight", (v.inter, v.hidden), "w"), (p + "mlp.fc1.bias", (v.inter,), "bias"),
+          (p + "mlp.fc2.weight", (v.hidden, v.inter), "w"), (p + "mlp.fc2.bias", (v.hidden,), "bias"),
+          (p + "layer_norm2.weight", (v.hidden,), "gain"), (p + "layer_norm2.bias", (v.hidden,), "bias")]
+    return s
+
+
+def siglip_specs(v: VisionCfg, prefix: str) -> List[Spec]:
+    """HF SiglipVisionModel state-dict names (encoder.py:84-101 wraps it as `vision_tower`).  The attention-pooling
+    head and post_layernorm exist in real checkpoints but never feed hidden_states[-2]."""
+    s: List[Spec] = [
+        (prefix + "embeddings.patch_embedding.weight", (v.hidden, 3, v.patch, v.patch), "w"),
+        (prefix + "embeddings.patch_embedding.bias", (v.hidden,), "bias"),
+        (prefix + "embeddings.position_embedding.weight", (v.num_patches, v.hidden), "emb"),
+    ]
+    for i in range(v.layers):
+        s += _encoder_layer_specs(v, f"{prefix}encoder.layers.{i}.")
+    s += [(prefix + "post_layernorm.weight", (v.hidden,), "gain"), (prefix + "post_layernorm.bias", (v.hidden,), "bias"),
+          (prefix + "head.probe", (1, 1, v.hidden), "emb"),
+          (prefix + "head.attention.in_proj_weight", (3 * v.hidden, v.hidden), "w"),
+          (prefix + "head.attention.in_proj_bias", (3 * v.hidden,), "bias"),
+          (prefix + "head.attention.out_proj.weight", (v.hidden, v.hidden), "w"),
+          (prefix + "head.attention.out_proj.bias", (v.hidden,), "bias"),
+          (prefix + "head.layernorm.weight", (v.hidden,), "gain"), (prefix + "head.layernorm.bias", (v.hidden,), "bias"),
+          (prefix + "head.mlp.fc1.weight", (v.inter, v.hidden), "w"), (prefix + "head.mlp.fc1.bias", (v.inter,), "bias"),
+          (prefix + "head.mlp.fc2.weight", (v.hidden, v.inter), "w"), (prefix + "head.mlp.fc2.bias", (v.hidden,), "bias")]
     return s
 
 

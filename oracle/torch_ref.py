@@ -30,11 +30,18 @@ def vit_hidden_states(sd: SD, v, pixels: torch.Tensor, dtype=torch.float32, n_la
                       pfx: str = VPFX) -> List[torch.Tensor]:
     x = pixels.to(dtype)
     Fn = x.shape[0]
-    pe = F.conv2d(x, _w(sd, pfx + "embeddings.patch_embedding.weight", dtype), stride=v.patch)  # no bias
-    pe = pe.flatten(2).transpose(1, 2)                                                         # [F, np, C]
-    cls = _w(sd, pfx + "embeddings.class_embedding", dtype).expand(Fn, 1, -1)
-    h = torch.cat([cls, pe], dim=1) + _w(sd, pfx + "embeddings.position_embedding.weight", dtype)
-    h = F.layer_norm(h, (v.hidden,), _w(sd, pfx + "pre_layrnorm.weight", dtype), _w(sd, pfx + "pre_layrnorm.bias", dtype), v.eps)
+    siglip = getattr(v, "kind", "clip") == "siglip"
+    if siglip:
+        # HF SiglipVisionEmbeddings (HF:siglip/modeling_siglip.py): conv WITH bias, no class token, no pre-LN
+        pe = F.conv2d(x, _w(sd, pfx + "embeddings.patch_embedding.weight", dtype),
+                      _w(sd, pfx + "embeddings.patch_embedding.bias", dtype), stride=v.patch)
+        h = (pe.flatten(2).transpose(1, 2) + _w(sd, pfx + "embeddings.position_embedding.weight", dtype)).contiguous()
+    else:
+        pe = F.conv2d(x, _w(sd, pfx + "embeddings.patch_embedding.weight", dtype), stride=v.patch)  # no bias
+        pe = pe.flatten(2).transpose(1, 2)                                                         # [F, np, C]
+        cls = _w(sd, pfx + "embeddings.class_embedding", dtype).expand(Fn, 1, -1)
+        h = torch.cat([cls, pe], dim=1) + _w(sd, pfx + "embeddings.position_embedding.weight", dtype)
+        h = F.layer_norm(h, (v.hidden,), _w(sd, pfx + "pre_layrnorm.weight", dtype), _w(sd, pfx + "pre_layrnorm.bias", dtype), v.eps)
     hs = [h]
     d = v.hidden // v.heads
     for i in range(v.layers if n_layers is None else n_layers):
@@ -54,7 +61,7 @@ def vit_hidden_states(sd: SD, v, pixels: torch.Tensor, dtype=torch.float32, n_la
         r = h
         y = F.layer_norm(h, (v.hidden,), _w(sd, p + "layer_norm2.weight", dtype), _w(sd, p + "layer_norm2.bias", dtype), v.eps)
         y = F.linear(y, _w(sd, p + "mlp.fc1.weight", dtype), _w(sd, p + "mlp.fc1.bias", dtype))
-        y = y * torch.sigmoid(1.702 * y)
+        y = F.gelu(y, approximate="tanh") if siglip else y * torch.sigmoid(1.702 * y)
         h = r + F.linear(y, _w(sd, p + "mlp.fc2.weight", dtype), _w(sd, p + "mlp.fc2.bias", dtype))
         hs.append(h)
     return hs
@@ -65,7 +72,7 @@ def vit_features(sd: SD, v, pixels: torch.Tensor, select_layer: int = -2, dtype=
     Layers after the selected one are skipped (they do not influence the result)."""
     n = v.layers + 1 + select_layer if select_layer < 0 else select_layer
     hs = vit_hidden_states(sd, v, pixels, dtype, n_layers=n)
-    return hs[n][:, 1:]
+    return hs[n] if getattr(v, "kind", "clip") == "siglip" else hs[n][:, 1:]
 
 
 # ----------------------------------------------------------------------------------------------------------------

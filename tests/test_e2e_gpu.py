@@ -13,7 +13,7 @@ from helpers import build_engine, rel
 
 pytestmark = pytest.mark.gpu
 
-CFGS = ["tiny", "tiny_qwen2", "tiny_v35", "mid"]
+CFGS = ["tiny", "tiny_qwen2", "tiny_v35", "tiny_siglip", "mid"]
 
 
 @pytest.fixture(scope="module", params=CFGS)
@@ -195,6 +195,27 @@ def test_cuda_graph_replay_is_bit_exact(setup, cuda):
         assert torch.equal(model.encode_images_or_videos(imgs), eager_mm)
     finally:
         model.enable_cuda_graphs(False)
+
+
+def test_vision_feature_cache(setup, cuda):
+    """Second encode of the same frames (the eval runners' pattern) is served from the cache, bit-identical; changed
+    pixels miss."""
+    cfg, sd, px, ids, gold, model = setup
+    imgs = [(px.to(cuda), "video")]
+    ref = model.encode_images_or_videos(imgs).clone()
+    model.enable_vision_cache(2)
+    try:
+        a = model.encode_images_or_videos(imgs)
+        b = model.encode_images_or_videos([(px.to(cuda).clone(), "video")])       # a different tensor, same content
+        assert model.vision_cache_hits == 1 and torch.equal(a, ref) and torch.equal(b, ref)
+        other = model.encode_images_or_videos([((px * 0.5).to(cuda), "video")])
+        assert model.vision_cache_hits == 1 and not torch.equal(other, ref)
+        t0 = model.generate(ids, images=imgs, max_new_tokens=2, do_sample=False)
+        assert model.vision_cache_hits == 2
+        model.enable_vision_cache(0)
+        assert torch.equal(model.generate(ids, images=imgs, max_new_tokens=2, do_sample=False), t0)
+    finally:
+        model.enable_vision_cache(0)
 
 
 def test_no_cpu_fallback(setup):

@@ -83,3 +83,23 @@ def test_keywords_stopping_criteria():
     kw = tok("stop now").input_ids[1:]
     sc = KeywordsStoppingCriteria(["stop now"], tok, torch.zeros(1, 3, dtype=torch.long))
     assert sc(torch.tensor([[9, 9] + kw]), None) and not sc(torch.tensor([[9, 9, 9]]), None)
+
+
+def test_vision_cache_content_key():
+    """The vision-feature cache key is a content checksum: equal for a copy, different after a one-element change, a
+    different modality or a different shape (videollama2_arch.enable_vision_cache)."""
+    from videollama2_b200.model.videollama2_arch import Videollama2MetaForCausalLM as M
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((4, 3, 14, 14), generator=g).to(torch.bfloat16)
+    k0 = M._content_key([(x, "video")])
+    assert M._content_key([(x.clone(), "video")]) == k0
+    y = x.clone()
+    y[3, 2, 13, 13] = y[3, 2, 13, 13] + 0.5
+    assert M._content_key([(y, "video")]) != k0
+    assert M._content_key([(x, "image")]) != k0
+    assert M._content_key([(x.view(4, 3, 7, 28), "video")]) != k0
+    z = x.clone()
+    z[0], z[1] = x[1], x[0]                      # a permutation of frames keeps the plain sum, not the weighted one
+    assert M._content_key([(z, "video")]) != k0
+    odd = torch.arange(5, dtype=torch.uint8)      # byte count not a multiple of 8
+    assert M._content_key([(odd, "video")]) == M._content_key([(odd.clone(), "video")])

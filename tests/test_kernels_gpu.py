@@ -24,6 +24,7 @@ ACTS = {
     1: lambda x: x * torch.sigmoid(1.702 * x),
     2: torch.nn.functional.silu,
     3: lambda x: torch.nn.functional.gelu(x),
+    5: lambda x: torch.nn.functional.gelu(x, approximate="tanh"),
 }
 
 
@@ -83,7 +84,7 @@ def test_gemm_cta_pair_swiglu_and_f32(cuda):
     assert relerr(o32, a.float() @ gate.float().t()) < 2e-3
 
 
-@pytest.mark.parametrize("act", [0, 1, 2, 3])
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_gemm_epilogue(cuda, act, with_res):
     from videollama2_b200 import ops
@@ -126,6 +127,9 @@ def test_gemm_rejects_bad_args(cuda):
 @pytest.mark.parametrize("B,S,Hq,Hkv,D,causal", [
     (2, 577, 4, 4, 64, False), (1, 128, 2, 2, 64, False), (3, 45, 2, 2, 64, False),
     (1, 300, 4, 2, 128, True), (1, 1776, 8, 2, 128, True), (1, 128, 2, 1, 128, True), (2, 260, 2, 2, 64, True),
+    # head widths between the native 64 / 128 (SigLIP-so400m: 16 heads x 72): heads packed at their true width
+    (3, 729, 16, 16, 72, False), (2, 25, 2, 2, 72, False), (1, 200, 4, 2, 96, True), (2, 130, 3, 3, 40, False),
+    (1, 77, 2, 2, 8, False),
 ])
 def test_attention(cuda, B, S, Hq, Hkv, D, causal):
     from videollama2_b200 import ops
@@ -298,7 +302,43 @@ def test_skinny_gemm_residual_swiglu_out(cuda):
     assert relerr(buf[1], (x.float() @ w.float().t())[0]) < 4e-3 and buf[0].abs().max() == 0 and buf[2].abs().max() == 0
 
 
-@pytest.mark.parametrize("n_pos,Hq,Hkv,D", [(1, 4, 2, 128), (37, 4, 2, 128), (1777, 32, 8, 128), (300, 4, 4, 64), (5000, 2, 1, 128)])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (1000, 328), (28672, 4096), (4096, 14336), (37, 8), (152064, 3584)])
+@pytest.mark.parametrize("mode", ["plain", "rms_bias", "swiglu_rms", "residual", "f32out"])
+def test_gemv(cuda, N, K, mode):
+    """M = 1 weight-streaming GEMV with the fused RMSNorm scale / bias / SwiGLU / residual epilogues."""
+    from videollama2_b200 import ops
+    if mode == "swiglu_rms" and N % 2:
+        pytest.skip("SwiGLU needs even N")
+    x = rnd((1, K), cuda, 1.5, seed=91)
+    w = rnd((N, K), cuda, K ** -0.5, seed=92)
+    xf, wf = x.float(), w.float()
+    eps = 1e-5
+    s = torch.rsqrt((xf * xf).mean() + eps)
+    if mode == "plain":
+        out, ref = ops.gemv(x, w), xf @ wf.t()
+    elif mode == "rms_bias":
+        b = rnd((N,), cuda, 0.1, seed=93).float()
+        out, ref = ops.gemv(x, w, bias=b, rms_eps=eps), s * (xf @ wf.t()) + b
+    elif mode == "swiglu_rms":
+        out = ops.gemv(x, w, act=ops.ACT_SWIGLU, rms_eps=eps)
+        y = s * (xf @ wf.t())
+        ref = torch.nn.functional.silu(y[:, 0::2]) * y[:, 1::2]
+    elif mode == "residual":
+        r = rnd((1, N), cuda, 1.0, seed=94)
+        out, ref = ops.gemv(x, w, residual=r), xf @ wf.t() + r.float()
+    else:
+        out, ref = ops.gemv(x, w, out_dtype=torch.float32), xf @ wf.t()
+        assert out.dtype == torch.float32
+    assert out.shape == ref.shape
+    assert relerr(out, ref) < (2e-5 if mode == "f32out" else 4e-3)
+    # M = 1 through the skinny entry point takes the same kernel
+    if mode == "plain":
+        assert torch.equal(ops.gemm_skinny(x, w, out_dtype=torch.bfloat16), out)
+
+
+@pytest.mark.parametrize("n_pos,Hq,Hkv,D", [(1, 4, 2, 128), (37, 4, 2, 128), (1777, 32, 8, 128), (300, 4, 4, 64), (5000, 2, 1, 128),
+                                            (128, 8, 8, 128), (129, 28, 4, 128), (1607, 28, 4, 128), (9000, 16, 2, 64),
+                                            (40000, 8, 1, 128)])
 def test_attention_decode(cuda, n_pos, Hq, Hkv, D):
     from videollama2_b200 import ops
     width = (Hq + 2 * Hkv) * D
@@ -312,6 +352,26 @@ def test_attention_decode(cuda, n_pos, Hq, Hkv, D):
     vf = v[:n_pos].float().view(n_pos, Hkv, D).permute(1, 0, 2).repeat_interleave(Hq // Hkv, 0)
     ref = (torch.softmax(qf @ kf.transpose(1, 2) * D ** -0.5, -1) @ vf).reshape(1, Hq * D)
     assert relerr(out, ref) < 6e-3
+    # graph-replayable variant (position read from device memory) is bit-identical
+    pos_dev = torch.tensor([n_pos - 1], device=cuda, dtype=torch.int32)
+    out2 = torch.empty_like(out)
+    ops.attention_decode_dyn(q, k, v, pos_dev, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, out=out2)
+    assert torch.equal(out, out2)
+
+
+def test_decode_rope_append_matches_eager(cuda):
+    from videollama2_b200 import ops
+    Hq, Hkv, D, pos = 8, 2, 128, 77
+    width = (Hq + 2 * Hkv) * D
+    row = rnd((1, width), cuda, seed=61)
+    inv = (1.0 / (1e6 ** (torch.arange(0, D, 2).float() / D))).to(cuda)
+    eager = row.clone()
+    ops.rope_inplace(eager, 1, Hq, Hkv, D, 0, Hq * D, pos, inv)
+    cache = torch.zeros((100, width), device=cuda, dtype=torch.bfloat16)
+    stage = row.clone()
+    ops.decode_rope_append(stage, cache, torch.tensor([pos], device=cuda, dtype=torch.int32), Hq, Hkv, D, inv)
+    assert torch.equal(stage, eager) and torch.equal(cache[pos:pos + 1], eager)
+    assert int(cache[:pos].abs().sum()) == 0 and int(cache[pos + 1:].abs().sum()) == 0
 
 
 @pytest.mark.parametrize("bn", [0, 1256, 224])

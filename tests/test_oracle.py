@@ -9,7 +9,7 @@ import torch
 from helpers import rel
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["tiny", "tiny_qwen2", "tiny_v35"]
+NAMES = ["tiny", "tiny_qwen2", "tiny_v35", "tiny_siglip"]
 
 
 @pytest.mark.parametrize("name", NAMES)

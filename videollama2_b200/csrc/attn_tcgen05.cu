@@ -51,6 +51,7 @@ struct AttnParams {
   void* out;
   int64_t ldo;
   int S, Hq, group;  // group = Hq / Hkv
+  int d_true;        // real head width (<= D); columns beyond it are TMA zero fill
   int causal;
   float scale_log2;  // softmax scale * log2(e)
 };
@@ -121,14 +122,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
       for (int a = 0; a < Cfg::kAtoms; ++a)
-        tma_load_3d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, head * D + a * 64, q0, b);
+        tma_load_4d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, a * 64, head, q0, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
-          tma_load_3d(sK + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[st], kvh * D + a * 64, j * BKV, b);
+          tma_load_4d(sK + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[st], a * 64, kvh, j * BKV, b);
       }
     } else if (lane == 1) {
       for (int j = 0; j < n_kv; ++j) {
@@ -137,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
-          tma_load_3d(sV + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[st], kvh * D + a * 64, j * BKV, b);
+          tma_load_4d(sV + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[st], a * 64, kvh, j * BKV, b);
       }
     }
   } else if (warp == 9) {
@@ -301,7 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float inv = 1.f / (sl[r] + sl[128 + r]);
     mbar_wait(&o_full[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after_sync();
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * D + hf * (D / 2);
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * p.S + qi) * p.ldo + head * p.d_true + hf * (D / 2);
 #pragma unroll
     for (int c = 0; c < D / 64; ++c) {
       uint32_t ov[32];
@@ -310,6 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (qi < p.S) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (hf * (D / 2) + c * 32 + g * 8 >= p.d_true) break;   // head_dim < D: the zero-padded columns are not stored
           *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(
               pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv),
               pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv),
@@ -332,28 +334,31 @@ template <int D>
 static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
   CUtensorMap tq, tk, tv;
-  const uint32_t box[3] = {64, 128, 1};
+  // 4-D maps (d, head, row, batch): a head narrower than the kernel's D (e.g. SigLIP's 72) is zero-filled by the TMA
+  // unit beyond its true width, so QK^T and PV simply see zero columns.
+  const uint32_t box[4] = {64, 1, 128, 1};
+  const uint64_t dt = (uint64_t)a->D;
   {
-    uint64_t dims[3] = {(uint64_t)a->Hq * D, (uint64_t)a->S, (uint64_t)a->B};
-    uint64_t str[2] = {(uint64_t)a->ldq * 2, (uint64_t)a->ldq * 2 * a->S};
-    int rc = make_tmap_bf16(&tq, a->q, 3, dims, str, box);
+    uint64_t dims[4] = {dt, (uint64_t)a->Hq, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[3] = {dt * 2, (uint64_t)a->ldq * 2, (uint64_t)a->ldq * 2 * a->S};
+    int rc = make_tmap_bf16(&tq, a->q, 4, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)a->Hkv * D, (uint64_t)a->S, (uint64_t)a->B};
-    uint64_t str[2] = {(uint64_t)a->ldk * 2, (uint64_t)a->ldk * 2 * a->S};
-    int rc = make_tmap_bf16(&tk, a->k, 3, dims, str, box);
+    uint64_t dims[4] = {dt, (uint64_t)a->Hkv, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[3] = {dt * 2, (uint64_t)a->ldk * 2, (uint64_t)a->ldk * 2 * a->S};
+    int rc = make_tmap_bf16(&tk, a->k, 4, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)a->Hkv * D, (uint64_t)a->S, (uint64_t)a->B};
-    uint64_t str[2] = {(uint64_t)a->ldv * 2, (uint64_t)a->ldv * 2 * a->S};
-    int rc = make_tmap_bf16(&tv, a->v, 3, dims, str, box);
+    uint64_t dims[4] = {dt, (uint64_t)a->Hkv, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[3] = {dt * 2, (uint64_t)a->ldv * 2, (uint64_t)a->ldv * 2 * a->S};
+    int rc = make_tmap_bf16(&tv, a->v, 4, dims, str, box);
     if (rc) return rc;
   }
   AttnParams p;
   p.trace = (a->reserved == 777) ? 1 : 0;
-  p.out = a->out; p.ldo = a->ldo; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
+  p.out = a->out; p.ldo = a->ldo; p.d_true = a->D; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
@@ -373,13 +378,14 @@ extern "C" int vl2_attention(const vl2_attn_args* a, void* stream) {
   VL2_REQUIRE(a != nullptr, VL2_E_BADSHAPE, "vl2_attention: null args");
   VL2_REQUIRE(a->B > 0 && a->S > 0 && a->Hq > 0 && a->Hkv > 0 && a->Hq % a->Hkv == 0, VL2_E_BADSHAPE,
               "vl2_attention: bad B/S/heads (%d,%d,%d,%d)", a->B, a->S, a->Hq, a->Hkv);
-  VL2_REQUIRE(a->D == 64 || a->D == 128, VL2_E_UNSUPPORTED, "vl2_attention: head_dim %d unsupported (64 or 128)", a->D);
+  VL2_REQUIRE(a->D >= 8 && a->D <= 128 && a->D % 8 == 0, VL2_E_UNSUPPORTED,
+              "vl2_attention: head_dim %d unsupported (multiple of 8, <= 128)", a->D);
   VL2_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, VL2_E_BADALIGN,
               "vl2_attention: row strides must be multiples of 8 elements");
   VL2_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->out), VL2_E_BADALIGN,
               "vl2_attention: pointers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->D == 64) return launch_attn<64>(a, st);
+  if (a->D <= 64) return launch_attn<64>(a, st);
   return launch_attn<128>(a, st);
 }
 

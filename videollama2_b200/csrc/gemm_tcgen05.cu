@@ -76,11 +76,17 @@ __device__ __forceinline__ float fast_sigmoid_mul(float x, float k_log2e) {
   // x * sigmoid(k x) = x / (1 + 2^(-k*log2e*x)); approximate reciprocal on the MUFU pipe
   return __fdividef(x, 1.f + fast_exp2(-k_log2e * x));
 }
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // 0.5 x (1 + tanh(u)) = x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)      (HF "gelu_pytorch_tanh", SigLIP MLP)
+  const float u2 = x * fmaf(0.0356774081f * x, x, 0.7978845608f) * 2.885390082f;   // 2 u log2(e)
+  return __fdividef(x, 1.f + fast_exp2(-u2));
+}
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
     case VL2_ACT_QUICK_GELU: return fast_sigmoid_mul(x, 1.702f * 1.4426950408889634f);
     case VL2_ACT_SILU: return fast_sigmoid_mul(x, 1.4426950408889634f);
     case VL2_ACT_GELU_ERF: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case VL2_ACT_GELU_TANH: return gelu_tanh(x);
     default: return x;
   }
 }
@@ -306,6 +312,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           } else if (p.act == VL2_ACT_GELU_ERF) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752f));
+          } else if (p.act == VL2_ACT_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
           }
           if (res != nullptr) {
 #pragma unroll
@@ -491,7 +500,7 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
   VL2_REQUIRE(a->lda >= a->K && a->ldw >= a->K, VL2_E_BADSHAPE, "vl2_gemm_bf16: lda/ldw smaller than K");
   VL2_REQUIRE(aligned16(a->A) && aligned16(a->W) && aligned16(a->C) && aligned16(a->residual) && aligned16(a->bias),
               VL2_E_BADALIGN, "vl2_gemm_bf16: pointers must be 16-byte aligned");
-  VL2_REQUIRE(a->act >= VL2_ACT_NONE && a->act <= VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: unknown act %d",
+  VL2_REQUIRE(a->act >= VL2_ACT_NONE && a->act <= VL2_ACT_GELU_TANH, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: unknown act %d",
               a->act);
   VL2_REQUIRE(a->sumsq_out == nullptr || (!a->out_f32 && a->act != VL2_ACT_SWIGLU && a->N % 32 == 0), VL2_E_UNSUPPORTED,
               "vl2_gemm_bf16: sumsq_out supports bf16, non-SwiGLU outputs with N %% 32 == 0 only");

@@ -21,7 +21,12 @@ int set_error(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_pdl_override{-1};
+void set_pdl_override(int v) { g_pdl_override.store(v); }
+
 bool pdl_enabled() {
+  const int ov = g_pdl_override.load(std::memory_order_relaxed);
+  if (ov >= 0) return ov == 1;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VL2_PDL");
@@ -87,4 +92,9 @@ extern "C" {
 int vl2_version(void) { return VL2_VERSION; }
 const char* vl2_last_error(void) { return vl2::g_err; }
 int64_t vl2_launch_count(void) { return vl2::g_launches.load(); }
+int vl2_set_pdl(int mode) {
+  if (mode < -1 || mode > 1) return vl2::set_error(VL2_E_BADSHAPE, "vl2_set_pdl: mode must be -1, 0 or 1");
+  vl2::set_pdl_override(mode);
+  return VL2_OK;
+}
 }

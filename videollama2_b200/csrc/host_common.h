@@ -42,6 +42,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+void set_pdl_override(int v);  // -1: follow VL2_PDL, 0: off, 1: on (vl2_set_pdl)
 bool pdl_enabled();  // VL2_PDL=1 enables programmatic dependent launch (default off: profiles/r01_bench_v10_*.json)
 
 // One launch path for every kernel: optional thread-block cluster, programmatic dependent launch attribute.

@@ -7,7 +7,7 @@ import os
 import torch
 
 from .config import Videollama2Config, VisionConfig
-from .encoder import CLIPVisionTower, build_vision_tower
+from .encoder import CLIPVisionTower, SiglipVisionTower, build_vision_tower
 from .projector import STCConnector, STCConnectorV35, build_vision_projector, load_mm_projector
 from .videollama2_mistral import Videollama2MistralConfig, Videollama2MistralForCausalLM
 from .videollama2_qwen2 import Videollama2Qwen2Config, Videollama2Qwen2ForCausalLM

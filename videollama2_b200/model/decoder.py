@@ -8,6 +8,7 @@ RMSNorm gains multiplied into the weight columns: the per-layer norms cost no ke
 the residual GEMM epilogues, the 1/rms factor is applied in the consuming GEMM's epilogue)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -32,6 +33,7 @@ class DecoderEngine:
         self._graphed = None
         self._decode_graph = None   # (graph, tok_dev, pos_dev, logits) of the captured single-token step
         self.graph_decode = False
+        self.decode_pdl = os.environ.get("VL2_DECODE_PDL", "1") != "0"   # PDL edges inside the decode graph
 
     def enable_cuda_graphs(self, on: bool = True):
         """Graph the cache-less last-position prefill (the bench / first-token path)."""
@@ -70,7 +72,10 @@ class DecoderEngine:
                 L["bqkv"] = f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in names], 0))
             self.layers.append(L)
         self.w = {"embed": bf(sd["model.embed_tokens.weight"]), "norm": bf(sd["model.norm.weight"]),
-                  "lm_head": bf(sd["lm_head.weight"]),
+                  # final-norm gain folded into the lm_head columns (the GEMV / GEMM epilogue applies 1/rms itself)
+                  "lm_head": (sd["lm_head.weight"].to(device=dev, dtype=torch.float32)
+                                * sd["model.norm.weight"].to(device=dev, dtype=torch.float32)[None, :]
+                                ).to(torch.bfloat16).contiguous(),
                   "ones": torch.ones((self.H,), device=dev, dtype=torch.bfloat16)}
         inv = 1.0 / (self.config.rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))
         self.w["inv_freq"] = inv.to(dev)
@@ -114,11 +119,9 @@ class DecoderEngine:
         for i, L in enumerate(self.layers):
             x, ss_x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None, ss_x)
         if all_logits:
-            hn = ops.rmsnorm(x, self.w["norm"], self.eps)
-            logits = ops.gemm(hn, self.w["lm_head"], out_dtype=torch.float32)
+            logits = ops.gemm(x, self.w["lm_head"], out_dtype=torch.float32, rms_in=ss_x, rms_eps=self.eps)
         else:
-            hn = ops.rmsnorm(x[S - 1:].contiguous(), self.w["norm"], self.eps)
-            logits = ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
+            logits = ops.gemv(x[S - 1:].contiguous(), self.w["lm_head"], rms_eps=self.eps, out_dtype=torch.float32)
         return logits, x
 
     def _ensure_cache(self, cap: int, device) -> None:
@@ -133,7 +136,8 @@ class DecoderEngine:
     # ---- KV-cache decode (one token) -----------------------------------------------------------------------
     def decode_step(self, x: torch.Tensor) -> torch.Tensor:
         """x [1,H] bf16 (embedding of the newest token) -> logits fp32 [1,V]; appends K/V at position kv_len.
-        Every linear layer is a weight-streaming GEMV (vl2_gemm_skinny), attention is vl2_attention_decode."""
+        Every linear layer is a weight-streaming GEMV with the RMSNorm in front of it fused (vl2_gemv_bf16), attention
+        is the split-KV vl2_attention_decode."""
         if not self.kv:
             raise RuntimeError("decode_step needs prefill(keep_cache=True) first")
         pos = self.kv_len
@@ -142,41 +146,34 @@ class DecoderEngine:
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
         for i, L in enumerate(self.layers):
             cache = self.kv[i]
-            y = ops.rmsnorm(x, self.w["ones"], self.eps)       # gamma lives in the weight columns
             row = cache[pos:pos + 1]
-            ops.gemm_skinny(y, L["wqkv"], bias=L.get("bqkv"), out=row)
+            ops.gemv(x, L["wqkv"], bias=L.get("bqkv"), out=row, rms_eps=self.eps)
             ops.rope_inplace(row, 1, Hq, Hkv, D, 0, Hq * D, pos, self.w["inv_freq"])
             o = ops.attention_decode(row[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
                                      n_pos=pos + 1, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5)
-            x = ops.gemm_skinny(o, L["wo"], residual=x, out_dtype=torch.bfloat16)
-            y = ops.rmsnorm(x, self.w["ones"], self.eps)
-            h = ops.gemm_skinny(y, L["wgu"], act=ops.ACT_SWIGLU, out_dtype=torch.bfloat16)
-            x = ops.gemm_skinny(h, L["wd"], residual=x, out_dtype=torch.bfloat16)
+            x = ops.gemv(o, L["wo"], residual=x)
+            h = ops.gemv(x, L["wgu"], act=ops.ACT_SWIGLU, rms_eps=self.eps)
+            x = ops.gemv(h, L["wd"], residual=x)
         self.kv_len = pos + 1
-        hn = ops.rmsnorm(x, self.w["norm"], self.eps)
-        return ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
+        return ops.gemv(x, self.w["lm_head"], rms_eps=self.eps, out_dtype=torch.float32)
 
     # ---- the same step as ONE CUDA graph ---------------------------------------------------------------------
     def _decode_body(self, tok_dev: torch.Tensor, pos_dev: torch.Tensor, stage: torch.Tensor) -> torch.Tensor:
         """Single-token step whose position and token live in device memory: embeds *tok_dev, appends K/V at *pos_dev,
         writes argmax(logits) back to tok_dev and increments pos_dev, so one captured graph serves every token."""
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
-        cap = self.kv[0].shape[0]
         x = torch.index_select(self.w["embed"], 0, tok_dev)
         o = torch.empty((1, Hq * D), device=x.device, dtype=torch.bfloat16)
         for i, L in enumerate(self.layers):
             cache = self.kv[i]
-            y = ops.rmsnorm(x, self.w["ones"], self.eps)
-            ops.gemm_skinny(y, L["wqkv"], bias=L.get("bqkv"), out=stage)
+            ops.gemv(x, L["wqkv"], bias=L.get("bqkv"), out=stage, rms_eps=self.eps)
             ops.decode_rope_append(stage, cache, pos_dev, Hq, Hkv, D, self.w["inv_freq"])
             ops.attention_decode_dyn(stage[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
-                                     pos_dev, max_pos=cap, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, out=o)
-            x = ops.gemm_skinny(o, L["wo"], residual=x, out_dtype=torch.bfloat16)
-            y = ops.rmsnorm(x, self.w["ones"], self.eps)
-            h = ops.gemm_skinny(y, L["wgu"], act=ops.ACT_SWIGLU, out_dtype=torch.bfloat16)
-            x = ops.gemm_skinny(h, L["wd"], residual=x, out_dtype=torch.bfloat16)
-        hn = ops.rmsnorm(x, self.w["norm"], self.eps)
-        logits = ops.gemm_skinny(hn, self.w["lm_head"], out_dtype=torch.float32)
+                                     pos_dev, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, out=o)
+            x = ops.gemv(o, L["wo"], residual=x)
+            h = ops.gemv(x, L["wgu"], act=ops.ACT_SWIGLU, rms_eps=self.eps)
+            x = ops.gemv(h, L["wd"], residual=x)
+        logits = ops.gemv(x, self.w["lm_head"], rms_eps=self.eps, out_dtype=torch.float32)
         tok_dev.copy_(torch.argmax(logits, dim=1))
         pos_dev.add_(1)
         return logits
@@ -196,10 +193,11 @@ class DecoderEngine:
             with torch.cuda.stream(side):
                 for _ in range(2):
                     pos_dev.fill_(scratch_pos)
-                    self._decode_body(tok_dev, pos_dev, stage)
+                    with ops.pdl(self.decode_pdl):
+                        self._decode_body(tok_dev, pos_dev, stage)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph), ops.pdl(self.decode_pdl):
                 logits = self._decode_body(tok_dev, pos_dev, stage)
             self._decode_graph = (graph, tok_dev, pos_dev, logits, stage)
         _, tok_dev, pos_dev, _, _ = self._decode_graph

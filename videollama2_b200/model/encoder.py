@@ -1,5 +1,6 @@
-"""CLIP ViT tower on libvl2 kernels — same class surface as the reference's CLIPVisionTower
-(videollama2/model/encoder.py:12-81), arithmetic of HF CLIPVisionModel (HF:clip/modeling_clip.py:202-218,282-385,647-696).
+"""CLIP / SigLIP ViT towers on libvl2 kernels — same class surface as the reference's CLIPVisionTower and
+SiglipVisionTower (videollama2/model/encoder.py:12-81, 84-151), arithmetic of HF CLIPVisionModel
+(HF:clip/modeling_clip.py:202-218,282-385,647-696) and HF SiglipVisionModel (HF:siglip/modeling_siglip.py).
 
 Only the layers that feed `hidden_states[select_layer]` are executed (select_layer = -2 -> 23 of 24; the reference runs
 the 24th layer and post_layernorm and throws the result away)."""
@@ -73,18 +74,7 @@ class CLIPVisionTower:
             "pos": bf(sd[prefix + "embeddings.position_embedding.weight"]),
             "pre_g": bf(sd[prefix + "pre_layrnorm.weight"]), "pre_b": bf(sd[prefix + "pre_layrnorm.bias"]),
         }
-        self.layers = []
-        for i in range(self.n_used_layers):
-            p = f"{prefix}encoder.layers.{i}."
-            self.layers.append({
-                "ln1_g": bf(sd[p + "layer_norm1.weight"]), "ln1_b": bf(sd[p + "layer_norm1.bias"]),
-                "ln2_g": bf(sd[p + "layer_norm2.weight"]), "ln2_b": bf(sd[p + "layer_norm2.bias"]),
-                "wqkv": bf(torch.cat([sd[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
-                "bqkv": f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
-                "wo": bf(sd[p + "self_attn.out_proj.weight"]), "bo": f32(sd[p + "self_attn.out_proj.bias"]),
-                "w1": bf(sd[p + "mlp.fc1.weight"]), "b1": f32(sd[p + "mlp.fc1.bias"]),
-                "w2": bf(sd[p + "mlp.fc2.weight"]), "b2": f32(sd[p + "mlp.fc2.bias"]),
-            })
+        self._load_layers(sd, prefix, dev)
         self._device = dev
         self.is_loaded = True
         return self
@@ -106,6 +96,18 @@ class CLIPVisionTower:
         patch = ops.gemm(A, self.w["patch"])
         x = ops.clip_embed_finish(patch, self.w["cls"], self.w["pos"], self.w["pre_g"], self.w["pre_b"], Fn,
                                   c.layer_norm_eps)
+        x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr)
+        return x.view(Fn, S, C)
+
+    _ACT = ops.ACT_QUICK_GELU
+
+    def _encoder(self, x: torch.Tensor, Fn: int, S: int, last_out=None, bcast_ptrs=None, mc_ptr: int = 0) -> torch.Tensor:
+        """Pre-LN transformer layers shared by both towers: LN -> fused QKV GEMM -> attention -> out_proj(+residual)
+        -> LN -> fc1(+activation) -> fc2(+residual)."""
+        c = self._config
+        C = c.hidden_size
+        H = c.num_attention_heads
+        D = C // H
         for li, L in enumerate(self.layers):
             last = li == len(self.layers) - 1
             y = ops.layernorm(x, L["ln1_g"], L["ln1_b"], c.layer_norm_eps)
@@ -114,12 +116,28 @@ class CLIPVisionTower:
                               scale=D ** -0.5)
             x = ops.gemm(o, L["wo"], bias=L["bo"], residual=x)
             y = ops.layernorm(x, L["ln2_g"], L["ln2_b"], c.layer_norm_eps)
-            h = ops.gemm(y, L["w1"], bias=L["b1"], act=ops.ACT_QUICK_GELU)
+            h = ops.gemm(y, L["w1"], bias=L["b1"], act=self._ACT)
             if last and (last_out is not None or bcast_ptrs or mc_ptr):
                 x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x, out=last_out, bcast_ptrs=bcast_ptrs, mc_ptr=mc_ptr)
             else:
                 x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x)
-        return x.view(Fn, S, C)
+        return x
+
+    def _load_layers(self, sd, prefix, dev):
+        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+        self.layers = []
+        for i in range(self.n_used_layers):
+            p = f"{prefix}encoder.layers.{i}."
+            self.layers.append({
+                "ln1_g": bf(sd[p + "layer_norm1.weight"]), "ln1_b": bf(sd[p + "layer_norm1.bias"]),
+                "ln2_g": bf(sd[p + "layer_norm2.weight"]), "ln2_b": bf(sd[p + "layer_norm2.bias"]),
+                "wqkv": bf(torch.cat([sd[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
+                "bqkv": f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
+                "wo": bf(sd[p + "self_attn.out_proj.weight"]), "bo": f32(sd[p + "self_attn.out_proj.bias"]),
+                "w1": bf(sd[p + "mlp.fc1.weight"]), "b1": f32(sd[p + "mlp.fc1.bias"]),
+                "w2": bf(sd[p + "mlp.fc2.weight"]), "b2": f32(sd[p + "mlp.fc2.bias"]),
+            })
 
     def feature_select(self, hidden: torch.Tensor) -> torch.Tensor:
         if self.select_feature == "patch":
@@ -166,6 +184,11 @@ class CLIPVisionTower:
         return (self._config.image_size // self._config.patch_size) ** 2
 
     @property
+    def seq_len(self):
+        """Rows per frame of the residual stream (class token + patches)."""
+        return self.num_patches + 1
+
+    @property
     def num_patches_per_side(self):
         return self._config.image_size // self._config.patch_size
 
@@ -174,13 +197,84 @@ class CLIPVisionTower:
         return self._config.image_size
 
 
+class _SiglipProcessorInfo:
+    """Fields of SiglipImageProcessor the callers read (mm_utils.py:132-202 / __init__.py:60-96)."""
+
+    def __init__(self, size: int):
+        self.size = {"height": size, "width": size}
+        self.crop_size = {"height": size, "width": size}
+        self.image_mean = [0.5, 0.5, 0.5]
+        self.image_std = [0.5, 0.5, 0.5]
+
+
+class SiglipVisionTower(CLIPVisionTower):
+    """SigLIP ViT (so400m/14@384 in VideoLLaMA2.1): no class token, no pre-LN, patch conv WITH bias, learned position
+    table over the patches, gelu-tanh MLP, LayerNorm eps 1e-6, head_dim 72 (encoder.py:84-151).  `feature_select` keeps
+    every token (encoder.py:103-109); post_layernorm and the attention-pooling head never feed hidden_states[-2]."""
+
+    _ACT = ops.ACT_GELU_TANH
+
+    def __init__(self, vision_tower: str, args, vision_config: Optional[VisionConfig] = None, load_pretrained=False):
+        super().__init__(vision_tower, args, vision_config=vision_config, load_pretrained=load_pretrained)
+        if self.select_feature != "patch":
+            raise ValueError(f"Unexpected select feature: {self.select_feature}")
+        self.image_processor = _SiglipProcessorInfo(self._config.image_size)
+        self._pos_rows: Dict[int, torch.Tensor] = {}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], device, prefix: str = _PFX) -> "SiglipVisionTower":
+        c = self._config
+        dev = torch.device(device)
+        K = 3 * c.patch_size * c.patch_size
+        self.kpad = (K + 63) // 64 * 64
+        wp = torch.zeros((c.hidden_size, self.kpad), dtype=torch.bfloat16, device=dev)
+        wp[:, :K] = sd[prefix + "embeddings.patch_embedding.weight"].to(device=dev, dtype=torch.bfloat16).reshape(c.hidden_size, K)
+        self.w = {
+            "patch": wp,
+            "patch_b": sd[prefix + "embeddings.patch_embedding.bias"].to(device=dev, dtype=torch.float32).contiguous(),
+            "pos": sd[prefix + "embeddings.position_embedding.weight"].to(device=dev, dtype=torch.bfloat16).contiguous(),
+        }
+        self._pos_rows = {}
+        self._load_layers(sd, prefix, dev)
+        self._device = dev
+        self.is_loaded = True
+        return self
+
+    def hidden_states(self, images: torch.Tensor, last_out: Optional[torch.Tensor] = None, bcast_ptrs=None,
+                      mc_ptr: int = 0) -> torch.Tensor:
+        """[F,3,H,W] bf16 -> residual stream after the selected layer, [F, np, C].  The embedding is ONE GEMM: im2col
+        patches x conv weight, + bias and + position rows in its epilogue (the position table repeated per frame is the
+        GEMM's residual operand)."""
+        c = self._config
+        Fn = images.shape[0]
+        S = self.num_patches
+        pos = self._pos_rows.get(Fn)
+        if pos is None:
+            pos = self.w["pos"].repeat(Fn, 1).contiguous()
+            self._pos_rows[Fn] = pos
+        A = ops.patch_im2col(images.contiguous(), c.patch_size, self.kpad)
+        x = ops.gemm(A, self.w["patch"], bias=self.w["patch_b"], residual=pos)
+        x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr)
+        return x.view(Fn, S, c.hidden_size)
+
+    def feature_select(self, hidden: torch.Tensor) -> torch.Tensor:
+        return hidden
+
+    @property
+    def seq_len(self):
+        return self.num_patches
+
+
 def build_vision_tower(vision_tower_cfg, **kwargs):
-    """encoder.py:154-164: only CLIP towers are implemented on this path (SigLIP is a later row)."""
+    """encoder.py:154-164: 'clip' / 'siglip' in the tower name pick the class; an in-memory vision_config decides by its
+    model_type."""
     vision_tower = getattr(vision_tower_cfg, "mm_vision_tower", getattr(vision_tower_cfg, "vision_tower", None))
     if vision_tower is None:
         raise ValueError("Unknown vision tower: None")
-    if "clip" in vision_tower.lower() or getattr(vision_tower_cfg, "vision_config", None) is not None:
+    vc = getattr(vision_tower_cfg, "vision_config", None)
+    if vc is not None and "siglip" in getattr(vc, "model_type", ""):
+        return SiglipVisionTower(vision_tower, args=vision_tower_cfg, **kwargs)
+    if "clip" in vision_tower.lower() or vc is not None:
         return CLIPVisionTower(vision_tower, args=vision_tower_cfg, **kwargs)
     if "siglip" in vision_tower.lower():
-        raise NotImplementedError("SiglipVisionTower is not implemented in the B200 engine yet")
+        return SiglipVisionTower(vision_tower, args=vision_tower_cfg, **kwargs)
     raise ValueError(f"Unknown vision tower: {vision_tower}")

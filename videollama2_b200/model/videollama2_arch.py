@@ -2,6 +2,8 @@
 (videollama2/model/videollama2_arch.py:28-263), running on libvl2 kernels."""
 from __future__ import annotations
 
+import collections
+
 from typing import Dict, List, Optional
 
 import torch
@@ -53,8 +55,50 @@ class Videollama2MetaForCausalLM:
     def get_vision_tower(self):
         return self.get_model().get_vision_tower()
 
-    # arch.py:114-134
+    # ---- vision-feature cache -----------------------------------------------------------
+    def enable_vision_cache(self, entries: int = 2):
+        """The reference's eval runners call mm_infer twice per video (eval/inference_video_mcqa_videomme.py:275,279,
+        inference_video_oqa_vcgpt_consistency.py:106,115) and re-encode the same frames each time.  With the cache on,
+        `encode_images_or_videos` keys its result on a 128-bit content checksum of the frame tensor (computed on the
+        device, one pass over the pixels) plus shape / modality, and returns the stored visual tokens on a hit.
+        Off by default: identical semantics to the reference either way, the cache only skips recomputation."""
+        self._vision_cache = collections.OrderedDict() if entries > 0 else None
+        self._vision_cache_entries = entries
+        self.vision_cache_hits = 0
+        return self
+
+    @staticmethod
+    def _content_key(images):
+        keys = []
+        for data, modal in images:
+            w = data.contiguous().view(torch.uint8).view(-1)
+            pad = (-w.numel()) % 8
+            if pad:
+                w = torch.cat([w, w.new_zeros(pad)])
+            w = w.view(torch.int64)
+            idx = torch.arange(1, w.numel() + 1, device=w.device, dtype=torch.int64)
+            h = torch.stack([w.sum(), (w * (2 * idx + 1)).sum()])        # wrap-around int64 arithmetic: two checksums
+            keys.append((modal, tuple(data.shape), str(data.dtype), tuple(int(v) for v in h.tolist())))
+        return tuple(keys)
+
     def encode_images_or_videos(self, images):
+        cache = getattr(self, "_vision_cache", None)
+        if cache is not None:
+            key = self._content_key(images)
+            hit = cache.get(key)
+            if hit is not None:
+                cache.move_to_end(key)
+                self.vision_cache_hits += 1
+                return hit
+            out = self._encode_images_or_videos(images).clone()   # the stages' graph buffers are reused: keep a copy
+            cache[key] = out
+            while len(cache) > self._vision_cache_entries:
+                cache.popitem(last=False)
+            return out
+        return self._encode_images_or_videos(images)
+
+    # arch.py:114-134
+    def _encode_images_or_videos(self, images):
         num_frames = getattr(self.config, "num_frames", NUM_FRAMES)
         data_batch = []
         for data, modal in images:

@@ -8,13 +8,13 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_SIGMOID, ACT_SILU, ACT_SWIGLU, AttnArgs, GemmArgs,
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SIGMOID, ACT_SILU, ACT_SWIGLU, AttnArgs, GemmArgs,
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
-    "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_SWIGLU", "ACT_SIGMOID",
+    "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
 
 
@@ -128,16 +128,69 @@ def gemm_skinny(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor
     return out
 
 
+class pdl:
+    """Context manager: programmatic dependent launch for the vl2 launches inside (vl2_set_pdl)."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        check(_lib.load().vl2_set_pdl(1 if self.on else 0), "vl2_set_pdl")
+        return self
+
+    def __exit__(self, *exc):
+        check(_lib.load().vl2_set_pdl(-1), "vl2_set_pdl")
+        return False
+
+
+_decode_ws = {}
+
+
+def decode_workspace(device, Hq: int, Hkv: int, D: int) -> torch.Tensor:
+    """Per-(device, stream) scratch for the split-KV decode attention (vl2_attention_decode_workspace bytes)."""
+    key = (torch.device(device).index, _stream(), Hq, Hkv, D)
+    ws = _decode_ws.get(key)
+    if ws is None:
+        nbytes = int(_lib.load().vl2_attention_decode_workspace(Hq, Hkv, D))
+        ws = torch.empty((nbytes // 4,), device=device, dtype=torch.float32)
+        _decode_ws[key] = ws
+    return ws
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, rms_eps: float = 0.0,
+         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """y[1,Nout] = act(s * w[N,K] x + bias) (+ residual); rms_eps > 0 fuses the RMSNorm in front (gain folded into w)."""
+    _need_cuda(x, w, bias, residual, out)
+    _bf16(x, w, residual)
+    assert x.is_contiguous() and w.is_contiguous() and w.dim() == 2 and x.numel() == w.shape[1]
+    N, K = w.shape
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    n_out = N // 2 if act == ACT_SWIGLU else N
+    if out is None:
+        out = torch.empty((1, n_out), device=x.device, dtype=out_dtype)
+    assert out.is_contiguous() and out.numel() == n_out and out.dtype in (torch.float32, torch.bfloat16)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.numel() == n_out
+    check(_lib.load().vl2_gemv_bf16(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
+                                    1 if out.dtype == torch.float32 else 0, N, K, act, float(rms_eps), _stream()),
+          "vl2_gemv_bf16")
+    return out
+
+
 def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, *, n_pos: int, Hq: int, Hkv: int,
-                     D: int, scale: float) -> torch.Tensor:
+                     D: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [Hq*D]; k_cache / v_cache: row-strided views [>=n_pos, Hkv*D] of the per-layer cache."""
     _need_cuda(q, k_cache, v_cache)
     _bf16(q, k_cache, v_cache)
     assert q.is_contiguous() and q.numel() == Hq * D and k_cache.stride(1) == 1 and v_cache.stride(1) == 1
     assert k_cache.stride(0) == v_cache.stride(0) and k_cache.shape[0] >= n_pos
-    out = torch.empty((1, Hq * D), device=q.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((1, Hq * D), device=q.device, dtype=torch.bfloat16)
+    ws = decode_workspace(q.device, Hq, Hkv, D)
     check(_lib.load().vl2_attention_decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
-                                           k_cache.stride(0), n_pos, Hq, Hkv, D, float(scale), _stream()),
+                                           k_cache.stride(0), n_pos, Hq, Hkv, D, float(scale), ws.data_ptr(), _stream()),
           "vl2_attention_decode")
     return out
 
@@ -170,13 +223,15 @@ def decode_rope_append(qkv_row: torch.Tensor, cache: torch.Tensor, pos_dev: torc
 
 
 def attention_decode_dyn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos_dev: torch.Tensor, *,
-                         max_pos: int, Hq: int, Hkv: int, D: int, scale: float, out: torch.Tensor) -> torch.Tensor:
+                         Hq: int, Hkv: int, D: int, scale: float, out: torch.Tensor,
+                         workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(q, k_cache, v_cache, pos_dev, out)
     _bf16(q, k_cache, v_cache, out)
     assert k_cache.stride(0) == v_cache.stride(0) and pos_dev.dtype == torch.int32
+    ws = workspace if workspace is not None else decode_workspace(q.device, Hq, Hkv, D)
     check(_lib.load().vl2_attention_decode_dyn(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
-                                               k_cache.stride(0), pos_dev.data_ptr(), max_pos, Hq, Hkv, D, float(scale),
-                                               _stream()), "vl2_attention_decode_dyn")
+                                               k_cache.stride(0), pos_dev.data_ptr(), Hq, Hkv, D, float(scale),
+                                               ws.data_ptr(), _stream()), "vl2_attention_decode_dyn")
     return out
 
 

@@ -80,7 +80,7 @@ class FusedFrameGather:
         self.rank = dist.get_rank(self.group)
         self.world = dist.get_world_size(self.group)
         self.F = num_frames
-        self.S = tower.num_patches + 1
+        self.S = tower.seq_len              # tokens per frame in the residual stream (CLIP: patches + CLS)
         self.C = tower.hidden_size
         dev = tower.device
         self.buf = symm_mem.empty((num_frames * self.S, self.C), dtype=torch.bfloat16, device=dev)
@@ -111,7 +111,7 @@ class FusedFrameGather:
                 peers = [ptr + off for r, ptr in enumerate(self.ptrs) if r != self.rank]
                 self.tower.hidden_states(frames[a:b].to(torch.bfloat16).contiguous(), last_out=local, bcast_ptrs=peers)
         self.hdl.barrier(channel=1)              # all ranks' tiles have landed everywhere
-        return self.buf.view(self.F, self.S, self.C)[:, 1:].contiguous()
+        return self.tower.feature_select(self.buf.view(self.F, self.S, self.C)).contiguous()
 
 
 def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev, iters: int = 5,

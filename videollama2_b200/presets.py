@@ -8,6 +8,11 @@ from .model.config import Videollama2Config, VisionConfig
 CLIP_L_336 = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
                   image_size=336, patch_size=14, layer_norm_eps=1e-5)
 
+# google/siglip-so400m-patch14-384: the tower of the released VideoLLaMA2.1 checkpoints (README.md:125-126)
+SIGLIP_SO400M_384 = dict(hidden_size=1152, intermediate_size=4304, num_hidden_layers=27, num_attention_heads=16,
+                         image_size=384, patch_size=14, layer_norm_eps=1e-6, hidden_act="gelu_pytorch_tanh",
+                         model_type="siglip_vision_model")
+
 MISTRAL_7B = dict(model_type="videollama2_mistral", hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
                   num_attention_heads=32, num_key_value_heads=8, vocab_size=32000, rms_norm_eps=1e-5, rope_theta=1e6)
 QWEN2_7B = dict(model_type="videollama2_qwen2", hidden_size=3584, intermediate_size=18944, num_hidden_layers=28,
@@ -17,7 +22,9 @@ QWEN2_7B = dict(model_type="videollama2_qwen2", hidden_size=3584, intermediate_s
 
 def make_config(llm: dict, frames: int, projector: str = "stc_connector", vision: dict = CLIP_L_336) -> Videollama2Config:
     vc = VisionConfig(**vision)
-    return Videollama2Config(**llm, mm_vision_tower="synthetic-clip-vit-large-patch14-336", mm_projector_type=projector,
+    siglip = "siglip" in vc.model_type
+    return Videollama2Config(**llm, mm_vision_tower="synthetic-siglip-so400m-patch14-384" if siglip
+                             else "synthetic-clip-vit-large-patch14-336", mm_projector_type=projector,
                              mm_hidden_size=vc.hidden_size, mm_vision_select_layer=-2, num_frames=frames,
                              vision_config=vc)
 
@@ -42,10 +49,16 @@ def state_dict_specs(cfg: Videollama2Config):
     vp = "model.vision_tower.vision_tower.vision_model."
     C, Iv = v.hidden_size, v.intermediate_size
     npatch = (v.image_size // v.patch_size) ** 2
-    s += [(vp + "embeddings.class_embedding", (C,), "emb"),
-          (vp + "embeddings.patch_embedding.weight", (C, 3, v.patch_size, v.patch_size), "w"),
-          (vp + "embeddings.position_embedding.weight", (npatch + 1, C), "emb"),
-          (vp + "pre_layrnorm.weight", (C,), "gain"), (vp + "pre_layrnorm.bias", (C,), "bias")]
+    siglip = "siglip" in v.model_type
+    if siglip:   # HF SiglipVisionModel naming; the pooling head (never on the path) is omitted from random init
+        s += [(vp + "embeddings.patch_embedding.weight", (C, 3, v.patch_size, v.patch_size), "w"),
+              (vp + "embeddings.patch_embedding.bias", (C,), "bias"),
+              (vp + "embeddings.position_embedding.weight", (npatch, C), "emb")]
+    else:
+        s += [(vp + "embeddings.class_embedding", (C,), "emb"),
+              (vp + "embeddings.patch_embedding.weight", (C, 3, v.patch_size, v.patch_size), "w"),
+              (vp + "embeddings.position_embedding.weight", (npatch + 1, C), "emb"),
+              (vp + "pre_layrnorm.weight", (C,), "gain"), (vp + "pre_layrnorm.bias", (C,), "bias")]
     for i in range(v.num_hidden_layers):
         p = f"{vp}encoder.layers.{i}."
         for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
@@ -105,10 +118,11 @@ def flops(cfg: Videollama2Config, frames: int, prompt: int, all_logits: bool = F
     g = v.image_size // v.patch_size
     npatch = g * g
     nl = v.num_hidden_layers + 1 + cfg.mm_vision_select_layer if cfg.mm_vision_select_layer < 0 else cfg.mm_vision_select_layer
-    Mv = frames * (npatch + 1)
+    seq = npatch + (0 if "siglip" in v.model_type else 1)
+    Mv = frames * seq
     vit_patch = 2 * frames * npatch * C * 3 * v.patch_size ** 2
     vit_gemm = nl * 2 * Mv * (4 * C * C + 2 * C * Iv)
-    vit_attn = nl * frames * v.num_attention_heads * 4 * (npatch + 1) ** 2 * (C // v.num_attention_heads)
+    vit_attn = nl * frames * v.num_attention_heads * 4 * seq ** 2 * (C // v.num_attention_heads)
     H = cfg.hidden_size
     pad = 0 if cfg.mm_projector_type.endswith("v35") else 1
     to, go = (frames + 2 * pad - 2) // 2 + 1, (g + 2 * pad - 2) // 2 + 1
