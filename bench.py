@@ -300,6 +300,29 @@ def main():
                       "note": "greedy, batch 1, weight-streaming GEMV + single-token attention kernels; "
                               "one CUDA-graph replay per token (position and token live in device memory)"}
 
+    # frame preprocessing on the device: 16 decoded 1080p uint8 frames -> pixel_values
+    prep = None
+    if rank == 0 and world == 1 and not args.profile_one_step:
+        from videollama2_b200 import mm_utils as vl2_mm
+        proc = model.get_vision_tower().image_processor
+        gp = torch.Generator(device="cpu").manual_seed(77)
+        raw = torch.randint(0, 256, (FRAMES, 1080, 1920, 3), generator=gp, dtype=torch.uint8).pin_memory()
+        raw_dev = raw.to(dev)
+        for _ in range(2):
+            vl2_mm.process_video(raw_dev, proc, num_frames=FRAMES, device=dev)
+        ms_prep_dev, _, _ = timed(lambda: vl2_mm.process_video(raw_dev, proc, num_frames=FRAMES, device=dev), 5)
+        ms_prep_e2e, _, _ = timed(lambda: vl2_mm.process_video(raw.to(dev, non_blocking=True), proc, num_frames=FRAMES,
+                                                              device=dev), 5)
+        in_bytes = raw.numel()
+        tmp_bytes = FRAMES * 1920 * IMG * 3
+        algo = in_bytes + 2 * tmp_bytes + FRAMES * 3 * IMG * IMG * 2
+        prep = {"input": f"{FRAMES} x 1080x1920x3 uint8 (pad to square, Pillow-exact bicubic to {IMG}, normalise, bf16)",
+                "ms_resident": ms_prep_dev, "ms_from_pinned_host": ms_prep_e2e, "frames_per_s": FRAMES / (ms_prep_dev * 1e-3),
+                "algorithmic_bytes": int(algo), "achieved_gbps": algo / ms_prep_dev / 1e6,
+                "frac_of_hbm": algo / ms_prep_dev / 1e6 / float(peaks().get("hbm_gbs") or 6500.0),
+                "h2d_bytes": int(in_bytes)}
+        del raw_dev
+
     # dominant-kernel roofline: every tcgen05 GEMM launch of one step bracketed by CUDA events on the launch stream
     roof = None
     model.enable_cuda_graphs(False)      # per-kernel event timing needs eager launches
@@ -406,7 +429,7 @@ def main():
             "e2e": {"value": world * S / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": px_host.numel() * 2 + ids_host.numel() * 8, "d2h_bytes_per_step": 8,
                     "api": "Videollama2MistralForCausalLM.generate(ids, images=[(frames,'video')], max_new_tokens=1)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "decode": decode,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "decode": decode, "preprocess": prep,
         }
         if fp is not None:
             line["frame_parallel"] = fp

@@ -213,6 +213,36 @@ int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q
 int vl2_embed_splice(const int64_t* ids, const int32_t* dst_row, int n, const void* table, int64_t vocab, void* out,
                      int H, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Frame preprocessing on the device (the step in front of the tower: videollama2/mm_utils.py:27-38 expand2square,
+ * :91-103 process_image, :132-202 process_video -> transformers 4.40 CLIPImageProcessor / SiglipImageProcessor ->
+ * Pillow Image.resize(BICUBIC)).  uint8 RGB frames [T,H,W,3] are placed (virtually) on a canvas_h x canvas_w canvas filled
+ * with pad_rgb at offset (off_y, off_x), resized to out_h x out_w with Pillow's two-pass fixed-point antialiased bicubic
+ * resampler (bit-exact: the 22-bit coefficient tables bounds_* [n,2] = (first tap, taps), kk_* [n, ksize_*] are computed by
+ * the caller exactly as Resample.c does), cropped to crop x crop at (crop_top, crop_left), mapped through lut [3,256]
+ * (= (u8 * (1/255) - mean) / std in float32) and stored as bf16 [T,3,crop,crop]; out_u8 (optional) receives the resized
+ * uint8 window [T,crop,crop,3].  tmp: vl2_preprocess_workspace() bytes.  HBM-bound byte work.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vl2_preprocess_args {
+  const uint8_t* frames;
+  int32_t T, H, W;
+  int32_t canvas_h, canvas_w, off_y, off_x;
+  uint8_t pad_rgb[4];
+  int32_t out_h, out_w;
+  int32_t crop_top, crop_left, crop;
+  const int32_t* bounds_h;
+  const int32_t* kk_h;
+  const int32_t* bounds_v;
+  const int32_t* kk_v;
+  int32_t ksize_h, ksize_v;
+  const float* lut;
+  uint8_t* tmp;
+  void* out_bf16;
+  uint8_t* out_u8;
+} vl2_preprocess_args;
+size_t vl2_preprocess_workspace(const vl2_preprocess_args* args);
+int vl2_preprocess_frames(const vl2_preprocess_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

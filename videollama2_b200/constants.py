@@ -10,6 +10,7 @@ DEFAULT_AUDIO_TOKEN = "<audio>"
 
 NUM_FRAMES = 8
 MAX_FRAMES = 32
+NUM_FRAMES_PER_SECOND = 1
 
 MODAL_INDEX_MAP = {
     "<image>": -200,

@@ -690,18 +690,21 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
 // (cp.async.bulk + mbarrier): the bytes in flight are set by the ring depth, not by how many loads the compiler keeps
 // in registers, so even N = 4096 (one row per warp, 28 warps per SM) keeps > 100 KB per SM outstanding.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kGemvStages = 4;
 constexpr int kGemvChunk = 2048;                      // bytes of one row per stage (1024 bf16)
 constexpr int kGemvWarps = 4;
+// Ring depth: R = 1 (N < 8192: o_proj / down_proj / q,k,v) uses 3 stages = 24 KB per CTA so that 7+ CTAs fit on an SM and
+// the 1024-CTA grids of the 4096-row projections run as ONE wave (ncu: with 4 stages 6 CTAs fit -> 1.15 waves, the
+// second one nearly empty); R = 2 uses 4 stages.
+template <int R> struct GemvCfg { static constexpr int kStages = R == 1 ? 3 : 4; };
 
-template <int R>
+template <int R, bool RMS>
 __global__ void __launch_bounds__(kGemvWarps * 32)
 gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W, const float* __restrict__ bias,
             const __nv_bfloat16* __restrict__ residual, void* __restrict__ y, int out_f32, int N, int K, int act,
             float rms_eps) {
+  constexpr int kGemvStages = GemvCfg<R>::kStages;
   extern __shared__ __align__(128) uint8_t gemv_smem[];
-  __shared__ uint64_t bars[kGemvWarps][kGemvStages];
-  pdl_launch_dependents();
+  __shared__ uint64_t bars[kGemvWarps][GemvCfg<R>::kStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kGemvWarps + warp) * R;
   if (n0 >= N) return;                                  // whole warp leaves: no block-wide barrier below
@@ -756,8 +759,10 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
         for (int j = 0; j < 4; ++j) {
           xf[2 * j] = bf16_lo(xa[j]);
           xf[2 * j + 1] = bf16_hi(xa[j]);
-          ss = fmaf(xf[2 * j], xf[2 * j], ss);
-          ss = fmaf(xf[2 * j + 1], xf[2 * j + 1], ss);
+          if (RMS) {
+            ss = fmaf(xf[2 * j], xf[2 * j], ss);
+            ss = fmaf(xf[2 * j + 1], xf[2 * j + 1], ss);
+          }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -773,11 +778,14 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
     }
     __syncwarp();
   }
+  // late PDL trigger: the dependent grid is launched while this one drains (its CTAs only prefetch weights until
+  // griddepcontrol.wait releases them), never while this grid still has CTAs waiting for an SM slot
+  pdl_launch_dependents();
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
-  ss = warp_sum(ss);
+  if (RMS) ss = warp_sum(ss);
   if (lane != 0) return;
-  const float s = rms_eps > 0.f ? rsqrtf(ss / (float)K + rms_eps) : 1.f;
+  const float s = RMS ? rsqrtf(ss / (float)K + rms_eps) : 1.f;
   float v[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -820,7 +828,6 @@ __global__ void __launch_bounds__(128)
 attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                          const __nv_bfloat16* __restrict__ vc, float* __restrict__ ws, int64_t ldkv, int n_pos, int group,
                          float scale, const int* __restrict__ pos_ptr) {
-  pdl_launch_dependents();
   pdl_wait();
   constexpr int NG = D / 8;              // 16-byte column groups per row
   constexpr int NSUB = kDecTile / NG;    // position subgroups in the P.V phase
@@ -937,6 +944,7 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
     }
     __syncthreads();   // ps / red are rewritten by the next tile
   }
+  pdl_launch_dependents();
   // combine the position subgroups (fixed order) and publish (m, l, o) of every query head of this kv head
   for (int g = 0; g < G; ++g) {
     if (g >= group) break;
@@ -1025,6 +1033,7 @@ extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta,
   if (nv <= 1) VL2_LN_WARP(1);
   else if (nv <= 2) VL2_LN_WARP(2);
   else if (nv <= 4) VL2_LN_WARP(4);
+  else if (nv <= 6) VL2_LN_WARP(6);     // C <= 1536: SigLIP-so400m rows (1152) stay in registers
   else
     launch_kernel(layernorm_stream_kernel, dim3(wgrid), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (const bf16*)gamma, (const bf16*)beta,
                                                                    (const bf16*)residual, (bf16*)y, rows, C, eps, act);
@@ -1175,20 +1184,25 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
 static int launch_gemv(const void* x, const void* W, const float* bias, const void* residual, void* y, int out_f32, int N,
                        int K, int act, float rms_eps, cudaStream_t stream) {
   const bool two = act == VL2_ACT_SWIGLU || N >= 8192;
+  const bool rms = rms_eps > 0.f;
   const int rows_per_cta = kGemvWarps * (two ? 2 : 1);
   const int blocks = (N + rows_per_cta - 1) / rows_per_cta;
-  const size_t smem = (size_t)kGemvWarps * kGemvStages * (two ? 2 : 1) * kGemvChunk;
+  const size_t smem = two ? (size_t)kGemvWarps * GemvCfg<2>::kStages * 2 * kGemvChunk
+                          : (size_t)kGemvWarps * GemvCfg<1>::kStages * kGemvChunk;
   static bool attr = false;
   if (!attr) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
-  if (two)
-    launch_kernel(gemv_kernel<2>, dim3(blocks), dim3(kGemvWarps * 32), smem, stream, 1, (const bf16*)x, (const bf16*)W, bias,
-                  (const bf16*)residual, y, out_f32, N, K, act, rms_eps);
-  else
-    launch_kernel(gemv_kernel<1>, dim3(blocks), dim3(kGemvWarps * 32), smem, stream, 1, (const bf16*)x, (const bf16*)W, bias,
-                  (const bf16*)residual, y, out_f32, N, K, act, rms_eps);
+#define VL2_GEMV(RR, RMS_)                                                                                                  \
+  launch_kernel(gemv_kernel<RR, RMS_>, dim3(blocks), dim3(kGemvWarps * 32), smem, stream, 1, (const bf16*)x, (const bf16*)W, \
+                bias, (const bf16*)residual, y, out_f32, N, K, act, rms_eps)
+  if (two && rms) VL2_GEMV(2, true);
+  else if (two) VL2_GEMV(2, false);
+  else if (rms) VL2_GEMV(1, true);
+  else VL2_GEMV(1, false);
+#undef VL2_GEMV
   VL2_CHECK_LAUNCH("gemv_kernel");
   return VL2_OK;
 }

@@ -3,15 +3,20 @@
 tokenizer_multimodal_token  <- videollama2/mm_utils.py:277-302
 splice_plan / build_splice  <- the index logic of prepare_inputs_labels_for_multimodal, videollama2/model/videollama2_arch.py:177-261
 KeywordsStoppingCriteria    <- videollama2/mm_utils.py:314-345 (token-id tail match only)
-Video decoding / resizing (process_video, mm_utils.py:132-202) is CPU I/O outside the accelerated path.
+frame_sample                <- videollama2/mm_utils.py:106-129 (frame index arithmetic, exact)
+process_video / process_image <- videollama2/mm_utils.py:91-103,132-202 for frames that are already decoded (arrays, PIL
+                               images, uint8 tensors): pad-to-square, Pillow-exact resize, crop, normalise on the GPU
+                               (videollama2_b200/preprocess.py).  Container decoding (decord / imageio) stays CPU I/O.
 """
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple
 
+import numpy as np
 import torch
 
-from .constants import DEFAULT_IMAGE_TOKEN, IGNORE_INDEX, MODAL_INDEX_MAP
+from .constants import (DEFAULT_IMAGE_TOKEN, IGNORE_INDEX, MAX_FRAMES, MODAL_INDEX_MAP, NUM_FRAMES,
+                        NUM_FRAMES_PER_SECOND)
 
 _MODAL_IDS = tuple(MODAL_INDEX_MAP.values())
 
@@ -133,3 +138,82 @@ class KeywordsStoppingCriteria:
             if output_ids.shape[1] >= n and torch.equal(output_ids[0, -n:].cpu(), kid):
                 return True
         return False
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# frame sampling + preprocessing of decoded frames
+# ----------------------------------------------------------------------------------------------------------------
+def frame_sample(duration, mode="uniform", num_frames=None, fps=None):
+    """Indices of the frames to keep out of `duration` decoded frames (mm_utils.py:106-129).
+    uniform: the midpoint of each of `num_frames` equal segments of [0, duration-1], rounded half-up via +1e-6;
+    fps: one frame per `fps // NUM_FRAMES_PER_SECOND` source frames, starting half a segment in."""
+    if mode == "uniform":
+        assert num_frames is not None, "Number of frames must be provided for uniform sampling."
+        seg = float(duration - 1) / num_frames
+        mids = [(seg * i + seg * (i + 1)) / 2 for i in range(num_frames)]
+        return np.round(np.array(mids) + 1e-6).astype(int)
+    if mode == "fps":
+        assert fps is not None, "FPS must be provided for FPS sampling."
+        step = min(fps // NUM_FRAMES_PER_SECOND, duration)
+        return np.arange(step // 2, duration, step, dtype=int)
+    raise ImportError(f"Unsupported frame sampling mode: {mode}")
+
+
+def _processor_kind(processor) -> Tuple[str, int]:
+    size = processor.size
+    if "shortest_edge" in size:
+        return "clip", int(processor.crop_size["height"])
+    return "siglip", int(size["height"])
+
+
+def _as_uint8_frames(video) -> List[np.ndarray]:
+    if isinstance(video, torch.Tensor):
+        return [video]                                   # handled as one [T,H,W,3] block by the caller
+    if isinstance(video, np.ndarray):
+        return [f for f in video] if video.ndim == 4 else [video]
+    if isinstance(video, (list, tuple)) and len(video) and isinstance(video[0], str):
+        raise NotImplementedError("decode the files first (PIL / decord are CPU I/O); pass frames as arrays or images")
+    if isinstance(video, (list, tuple)):
+        return [np.asarray(f.convert("RGB")) if hasattr(f, "convert") else np.asarray(f) for f in video]
+    raise ValueError(f"Unsupported video path type: {type(video)}")
+
+
+def process_video(video_path, processor, s=None, e=None, aspect_ratio="pad", num_frames=NUM_FRAMES, device="cuda"):
+    """Decoded frames -> bf16 pixel_values [T,3,S,S] on `device` (mm_utils.py:132-202 from step 4 on):
+    missing frames are appended as black frames (with the reference's swapped width/height, mm_utils.py:190-191),
+    at most MAX_FRAMES are kept, then every frame goes through expand2square + processor.preprocess on the GPU."""
+    from . import preprocess
+    if isinstance(video_path, str):
+        raise NotImplementedError("container decoding (decord / imageio, mm_utils.py:143-176) is CPU I/O outside the "
+                                  "accelerated path: decode the sampled frames (frame_sample) and pass them in")
+    kind, size = _processor_kind(processor)
+    kw = dict(kind=kind, aspect_ratio=aspect_ratio)
+    if isinstance(video_path, torch.Tensor) and video_path.dim() == 4 and \
+            (num_frames is None or video_path.shape[0] >= num_frames):
+        frames = video_path[:MAX_FRAMES].to(device)
+        return preprocess.preprocess_frames(frames, size, processor.image_mean, processor.image_std, **kw)
+    frames = _as_uint8_frames(video_path.cpu().numpy() if isinstance(video_path, torch.Tensor) else video_path)
+    while num_frames is not None and len(frames) < num_frames:
+        h, w = frames[-1].shape[:2]
+        frames.append(np.zeros((w, h, 3), dtype=np.uint8))          # (*PIL.size, 3) = (width, height, 3) in the reference
+    frames = frames[:MAX_FRAMES]
+    out: List[torch.Tensor] = []
+    i = 0
+    while i < len(frames):                                          # consecutive frames of one shape share a launch
+        j = i
+        while j < len(frames) and frames[j].shape == frames[i].shape:
+            j += 1
+        block = torch.from_numpy(np.ascontiguousarray(np.stack(frames[i:j]))).to(device)
+        out.append(preprocess.preprocess_frames(block, size, processor.image_mean, processor.image_std, **kw))
+        i = j
+    return torch.cat(out, 0) if len(out) > 1 else out[0]
+
+
+def process_image(image, processor, aspect_ratio="pad", device="cuda"):
+    """One decoded image (array / PIL image / uint8 tensor [H,W,3]) -> bf16 [1,3,S,S] (mm_utils.py:91-103)."""
+    if isinstance(image, str):
+        raise NotImplementedError("decode the file first (PIL is CPU I/O); pass the image as an array or a PIL image")
+    if isinstance(image, torch.Tensor):
+        image = image.cpu().numpy()
+    arr = np.asarray(image.convert("RGB")) if hasattr(image, "convert") else np.asarray(image)
+    return process_video([arr], processor, aspect_ratio=aspect_ratio, num_frames=None, device=device)

@@ -33,7 +33,7 @@ class DecoderEngine:
         self._graphed = None
         self._decode_graph = None   # (graph, tok_dev, pos_dev, logits) of the captured single-token step
         self.graph_decode = False
-        self.decode_pdl = os.environ.get("VL2_DECODE_PDL", "1") != "0"   # PDL edges inside the decode graph
+        self.decode_pdl = os.environ.get("VL2_DECODE_PDL", "0") == "1"   # PDL edges inside the decode graph
 
     def enable_cuda_graphs(self, on: bool = True):
         """Graph the cache-less last-position prefill (the bench / first-token path)."""
