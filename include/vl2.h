@@ -103,6 +103,10 @@ typedef struct vl2_gemm_args {
   float rms_eps;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
+/* Debug aid: with args->reserved2 == 777 CTA 0 records clock64() at its tile boundaries: out[0] = tiles traced (<= 7), and
+ * for tile t at out[8t+1..8t+6]: MMA role waits for the accumulator stage / starts issuing / issued its last commit;
+ * epilogue warp starts the tile / sees the accumulator complete / stored its last span.  Synchronises the device. */
+int vl2_debug_gemm_trace(long long* host_out64);
 
 /* Skinny GEMM (M <= 32 rows, HBM-bound weight streaming): C[M,N] = act(A[M,K] W[N,K]^T + bias).
  * Used for the SE excitation MLP of the RegStage blocks (timm SEModule, projector.py:153-161) and the last-position
@@ -145,6 +149,10 @@ int vl2_attention(const vl2_attn_args* args, void* stream);
  * ([0] wait S, [1] TMEM load, [2] mask+max+exchange, [3] wait PV / rescale, [4] exp2+pack+st.shared, [5] fence+arrive,
  *  [6] number of key tiles). */
 int vl2_debug_attn_trace(long long* host_out16);
+
+/* Hint: pull [ptr, ptr + bytes) into L2 (cp.async.bulk.prefetch.L2 in 16 KB pieces; returns immediately).  The decode graph
+ * forks this next to the latency-bound attention phase so the o_proj / gate-up GEMVs start from L2-resident weights. */
+int vl2_l2_prefetch(const void* ptr, size_t bytes, void* stream);
 
 /* Single-token decode attention over a KV cache (HF:mistral/modeling_mistral.py:122-177 with a DynamicCache):
  * q bf16 [Hq*D]; k_cache / v_cache bf16 rows of ldkv elements (kv head h at columns [h*D, +D)), positions 0..n_pos-1;

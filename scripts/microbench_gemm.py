@@ -54,4 +54,15 @@ for name, M, N, K, has_bias, has_res, act in SHAPES:
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
     res[name] = {"M": M, "N": N, "K": K, "us": round(us, 1), "TFs": round(2 * M * N * K / us / 1e6, 1)}
+    if "--trace" in sys.argv:
+        ops.gemm(A[0], W[0], bias=b, act=act, residual=R[0] if R else None, out=out, bn=bn, trace=True)
+        t = ops.gemm_trace()
+        n_t = int(t[0])
+        base = t[1]
+        rows = []
+        for i in range(n_t):
+            v = t[8 * i + 1: 8 * i + 7]
+            rows.append({"mma_wait_acc": v[1] - v[0], "mma_issue": v[2] - v[1], "epi_wait_acc": v[4] - v[3],
+                         "epi_work": v[5] - v[4], "mma_start_at": v[0] - base, "epi_start_at": v[3] - base})
+        res[name]["trace_cycles"] = rows
 print(json.dumps(res))

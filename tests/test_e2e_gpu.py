@@ -174,6 +174,24 @@ def test_graph_replayed_decode_is_bit_exact(setup, cuda):
         model.enable_cuda_graphs(False)
 
 
+def test_graph_decode_with_l2_prefetch_fork(setup, cuda):
+    """The decode graph with the forked weight-prefetch branch (vl2_l2_prefetch next to the attention phase) produces
+    the same tokens: the fork only moves bytes into L2."""
+    cfg, sd, px, ids, gold, model = setup
+    imgs = [(px.to(cuda), "video")]
+    dec = model.get_model().decoder
+    eager = model.generate(ids, images=imgs, max_new_tokens=6, do_sample=False, use_cache=True)
+    old = dec.decode_prefetch_mb
+    dec.decode_prefetch_mb = 0.05
+    model.enable_cuda_graphs(True)
+    try:
+        for _ in range(2):
+            assert torch.equal(model.generate(ids, images=imgs, max_new_tokens=6, do_sample=False, use_cache=True), eager)
+    finally:
+        model.enable_cuda_graphs(False)
+        dec.decode_prefetch_mb = old
+
+
 def test_cuda_graph_replay_is_bit_exact(setup, cuda):
     """Graph-replayed stages (tower, connector, last-position prefill) must reproduce the eager launches bit for bit,
     also on the second replay and after a different input went through the same graph."""

@@ -30,6 +30,30 @@ def test_clip_layer_real_dims(cuda):
     assert rel(emb, hs[0][:, 1:]) < 5e-3               # patch conv + cls/pos + pre-LN only
 
 
+def test_siglip_layer_real_dims(cuda):
+    """SigLIP-so400m/14@384 at its real dimensions (1152 wide, 16 heads x 72, MLP 4304, 27x27 patches out of 384 pixels
+    with 6 unused ones, patch bias, gelu-tanh): embedding and one encoder layer against the fp32 oracle."""
+    from oracle import synth, torch_ref
+    from videollama2_b200.model.config import VisionConfig
+    from videollama2_b200.model.encoder import SiglipVisionTower
+    v = synth.VisionCfg(hidden=1152, inter=4304, layers=1, heads=16, image=384, patch=14, eps=1e-6, kind="siglip")
+    pfx = "model.vision_tower.vision_tower.vision_model."
+    sd = dict(synth.iter_state(synth.vision_specs(v)))
+    px = torch.randn((2, 3, 384, 384), generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    hs = torch_ref.vit_hidden_states(sd, v, px, torch.float32)
+    vc = VisionConfig(hidden_size=1152, intermediate_size=4304, num_hidden_layers=1, num_attention_heads=16,
+                      image_size=384, patch_size=14, layer_norm_eps=1e-6, hidden_act="gelu_pytorch_tanh",
+                      model_type="siglip_vision_model")
+    args = type("A", (), {"mm_vision_select_layer": 1, "mm_vision_select_feature": "patch"})()
+    tower = SiglipVisionTower("synthetic-siglip", args, vision_config=vc).load_state_dict(sd, cuda, prefix=pfx)
+    out = tower(px.to(cuda))
+    assert out.shape == (2, 729, 1152) and tower.num_patches == 729
+    assert rel(out, hs[1]) < 1e-2
+    args0 = type("A", (), {"mm_vision_select_layer": 0, "mm_vision_select_feature": "patch"})()
+    emb = SiglipVisionTower("synthetic-siglip", args0, vision_config=vc).load_state_dict(sd, cuda, prefix=pfx)(px.to(cuda))
+    assert rel(emb, hs[0]) < 5e-3                      # patch conv + bias + position rows (one GEMM)
+
+
 def test_mistral_layer_real_dims(cuda):
     from oracle import synth, torch_ref
     from videollama2_b200.model.decoder import DecoderEngine

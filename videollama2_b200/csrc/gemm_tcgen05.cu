@@ -63,7 +63,13 @@ struct GemmParams {
   float* sumsq_out;
   int rms_nparts;
   float rms_inv_dim, rms_eps;
+  int l2_ahead;   // k-blocks of L2 prefetch distance in the producer (0 = off)
+  int trace;   // debug: CTA 0 records clock64() at tile boundaries of its MMA and epilogue roles (vl2_debug_gemm_trace)
 };
+
+// [0] tiles traced; per tile t (<= 7), at 8*t + 1: MMA waits for the accumulator stage, MMA starts issuing, MMA issued
+// the last commit, epilogue warp 4 starts the tile, its accumulator is complete, its last span is stored.
+__device__ long long g_gemm_trace[64];
 
 // one 16-byte store replicated by the NVSwitch to every GPU of the multicast group
 __device__ __forceinline__ void multimem_st128(void* mc_addr, const uint4& v) {
@@ -149,12 +155,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
+      // A second cursor runs p.l2_ahead k-blocks ahead of the loads and only hints the boxes into L2
+      // (cp.async.bulk.prefetch.tensor): with 6 smem stages the stage round trip (TMA issue -> data -> MMA -> commit)
+      // bounds a k-block at latency / 6; taking the HBM miss out of that round trip leaves the L2-hit latency.
       int stage = 0;
       uint32_t phase = 0;
+      int pf_tile = tile0, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile >= num_tiles) return;
+        const int pm0 = (pf_tile % p.num_m_tiles) * kTileM + (int)rank * BM;
+        const int pn0 = (pf_tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
+        tma_prefetch_l2_2d(&tmap_a, pf_kb * BK, pm0);
+        tma_prefetch_l2_2d(&tmap_b, pf_kb * BK, pn0);
+        if (++pf_kb == num_k_blocks) { pf_kb = 0; pf_tile += tile_stride; }
+      };
+      for (int i = 0; i < p.l2_ahead; ++i) prefetch_next();
       for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
         const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
         const int n0 = (tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
+          if (p.l2_ahead > 0) prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR) {
             // both CTAs' bytes land on the leader's full barrier
@@ -180,8 +200,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const bool tr = p.trace && blockIdx.x == 0 && it < 7;
+        if (tr) g_gemm_trace[8 * it + 1] = clock64();
         mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue drained this accumulator stage
         tc_fence_after_sync();
+        if (tr) g_gemm_trace[8 * it + 2] = clock64();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -201,6 +224,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         // accumulator complete -> epilogue (of both CTAs)
         if (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+        if (tr) { g_gemm_trace[8 * it + 3] = clock64(); g_gemm_trace[0] = it + 1; }
       }
     }
   } else if (warp >= 4) {
@@ -223,6 +247,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const bool etr = p.trace && blockIdx.x == 0 && it < 7 && etid == 0;
+      if (etr) g_gemm_trace[8 * it + 4] = clock64();
       const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
       const int n0 = (tile / p.num_m_tiles) * BN;
       const int row = m0 + row_in_tile;
@@ -248,6 +274,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
+      if (etr) g_gemm_trace[8 * it + 5] = clock64();
       const uint32_t taddr = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
       const int rbase = m0 + ew * 32;  // first row of this warp's 32-row block
 
@@ -379,6 +406,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           __syncwarp();  // the buffer is reused by the next span
         }
       }
+      if (etr) g_gemm_trace[8 * it + 6] = clock64();
       // all tcgen05.ld of this thread have completed (wait::ld above) -> hand the accumulator stage back
       tmem_ld_wait();
       tc_fence_before_sync();
@@ -393,6 +421,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
+
+static int l2_ahead_kblocks();
 
 template <int BN, bool PAIR>
 static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
@@ -417,6 +447,8 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
   p.rms_sumsq_in = a->rms_sumsq_in; p.sumsq_out = a->sumsq_out; p.rms_nparts = a->rms_nparts;
   p.rms_inv_dim = a->rms_inv_dim; p.rms_eps = a->rms_eps;
+  p.trace = (a->reserved2 == 777) ? 1 : 0;
+  p.l2_ahead = l2_ahead_kblocks();
   p.n_bcast = a->n_bcast;
   p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
   for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
@@ -477,6 +509,20 @@ static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair) {
   return best;
 }
 
+// VL2_GEMM_L2_AHEAD: L2 prefetch distance of the TMA producer in k-blocks.  Default 0 = off: measured 20-30 % SLOWER at
+// 6 / 12 / 24 k-blocks on every ViT and decoder shape (profiles/experiments/gemm_l2_prefetch.txt) - the kernel is bound by
+// the L2 -> SM request rate (~58 B/clk/SM), not by latency, and the hints double the requests.
+static int l2_ahead_kblocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VL2_GEMM_L2_AHEAD");
+    v = e != nullptr ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    if (v > 64) v = 64;
+  }
+  return v;
+}
+
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -487,6 +533,14 @@ static bool pair_enabled() {
 }
 
 }  // namespace vl2
+
+// Debug: copy the tile-boundary cycle trace of the last traced launch (args->reserved2 == 777) to host memory.
+extern "C" int vl2_debug_gemm_trace(long long* host_out64) {
+  VL2_REQUIRE(host_out64 != nullptr, VL2_E_BADSHAPE, "vl2_debug_gemm_trace: null output");
+  VL2_CHECK_CUDA(cudaDeviceSynchronize());
+  VL2_CHECK_CUDA(cudaMemcpyFromSymbol(host_out64, vl2::g_gemm_trace, 64 * sizeof(long long)));
+  return VL2_OK;
+}
 
 extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
   using namespace vl2;

@@ -811,6 +811,20 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// L2 prefetch of a weight range (cp.async.bulk.prefetch.L2): launched on a forked branch of the decode graph while the
+// latency-bound attention phase leaves HBM idle, so that the following GEMVs find (part of) their weights in the 126 MB L2.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+l2_prefetch_kernel(const uint8_t* __restrict__ base, size_t bytes, unsigned chunk) {
+  const size_t n_chunks = (bytes + chunk - 1) / chunk;
+  for (size_t c = (size_t)blockIdx.x * 32 + threadIdx.x; c < n_chunks; c += (size_t)gridDim.x * 32) {
+    const size_t off = c * chunk;
+    const unsigned n = (unsigned)(bytes - off < chunk ? bytes - off : chunk) & ~15u;
+    if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Single-token (decode) attention over a KV cache held as rows of the fused QKV buffer, split over the KV length
 // (flash-decoding): grid (kv head, split); a CTA takes the 128-position tiles `split, split + nsplit, ...` of its kv
 // head and serves all `group` query heads that share it, so K and V are read from HBM exactly once.
@@ -1216,6 +1230,14 @@ extern "C" int vl2_gemv_bf16(const void* x, const void* W, const float* bias, co
   VL2_REQUIRE(act != VL2_ACT_SWIGLU || (N % 2 == 0 && residual == nullptr), VL2_E_UNSUPPORTED,
               "vl2_gemv_bf16: SWIGLU needs even N and no residual");
   return launch_gemv(x, W, bias, residual, y, out_f32, N, K, act, rms_eps, (cudaStream_t)stream);
+}
+
+extern "C" int vl2_l2_prefetch(const void* ptr, size_t bytes, void* stream) {
+  VL2_REQUIRE(ptr != nullptr && aligned16(ptr), VL2_E_BADALIGN, "vl2_l2_prefetch: pointer must be 16-byte aligned");
+  if (bytes < 16) return VL2_OK;
+  launch_kernel(l2_prefetch_kernel, dim3(32), dim3(32), 0, (cudaStream_t)stream, 1, (const uint8_t*)ptr, bytes, 16384u);
+  VL2_CHECK_LAUNCH("l2_prefetch_kernel");
+  return VL2_OK;
 }
 
 extern "C" size_t vl2_attention_decode_workspace(int Hq, int Hkv, int D) {

@@ -34,6 +34,10 @@ class DecoderEngine:
         self._decode_graph = None   # (graph, tok_dev, pos_dev, logits) of the captured single-token step
         self.graph_decode = False
         self.decode_pdl = os.environ.get("VL2_DECODE_PDL", "0") == "1"   # PDL edges inside the decode graph
+        # MB of o_proj + gate/up weights pulled into L2 on a forked graph branch while the attention phase runs
+        # (HBM is idle there); 0 disables the fork
+        self.decode_prefetch_mb = float(os.environ.get("VL2_DECODE_PREFETCH_MB", "0"))
+        self._side_stream = None
 
     def enable_cuda_graphs(self, on: bool = True):
         """Graph the cache-less last-position prefill (the bench / first-token path)."""
@@ -167,9 +171,27 @@ class DecoderEngine:
         for i, L in enumerate(self.layers):
             cache = self.kv[i]
             ops.gemv(x, L["wqkv"], bias=L.get("bqkv"), out=stage, rms_eps=self.eps)
+            joined = None
+            if self.decode_prefetch_mb > 0:       # fork: weight prefetch into L2 next to the attention phase
+                main = torch.cuda.current_stream()
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=x.device)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                self._side_stream.wait_event(fork)
+                with torch.cuda.stream(self._side_stream):
+                    budget = int(self.decode_prefetch_mb * 1e6)
+                    n_wo = L["wo"].numel() * 2
+                    ops.l2_prefetch(L["wo"], min(budget, n_wo))
+                    if budget > n_wo:
+                        ops.l2_prefetch(L["wgu"], budget - n_wo)
+                    joined = torch.cuda.Event()
+                    joined.record(self._side_stream)
             ops.decode_rope_append(stage, cache, pos_dev, Hq, Hkv, D, self.w["inv_freq"])
             ops.attention_decode_dyn(stage[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
                                      pos_dev, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, out=o)
+            if joined is not None:
+                torch.cuda.current_stream().wait_event(joined)
             x = ops.gemv(o, L["wo"], residual=x)
             h = ops.gemv(x, L["wgu"], act=ops.ACT_SWIGLU, rms_eps=self.eps)
             x = ops.gemv(h, L["wd"], residual=x)

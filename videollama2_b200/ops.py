@@ -12,7 +12,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SI
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "l2_prefetch", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
@@ -46,7 +46,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
          bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
-         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None, trace: bool = False) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
     `bn` forces the tile width (tests); 0 = library heuristic.
     `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
@@ -99,8 +99,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
             args.bcast_out[i] = ptr
         args.n_bcast = len(ptrs)
         args.mc_out = mc_ptr or None
+    if trace:
+        args.reserved2 = 777
     check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
     return out
+
+
+def gemm_trace() -> list:
+    """Tile-boundary cycle trace of the last gemm(..., trace=True) launch (vl2_debug_gemm_trace)."""
+    buf = (C.c_longlong * 64)()
+    check(_lib.load().vl2_debug_gemm_trace(buf), "vl2_debug_gemm_trace")
+    return list(buf)
 
 
 def gemm_skinny(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
@@ -141,6 +150,14 @@ class pdl:
     def __exit__(self, *exc):
         check(_lib.load().vl2_set_pdl(-1), "vl2_set_pdl")
         return False
+
+
+def l2_prefetch(t: torch.Tensor, nbytes: Optional[int] = None) -> None:
+    """Hint the first `nbytes` of a contiguous device tensor into L2 (vl2_l2_prefetch) on the current stream."""
+    _need_cuda(t)
+    total = t.numel() * t.element_size()
+    n = total if nbytes is None else min(int(nbytes), total)
+    check(_lib.load().vl2_l2_prefetch(t.data_ptr(), n, _stream()), "vl2_l2_prefetch")
 
 
 _decode_ws = {}
