@@ -98,9 +98,16 @@ typedef struct vl2_gemm_args {
   const float* rms_sumsq_in;
   float* sumsq_out;
   int32_t rms_nparts;
-  int32_t reserved3;
+  int32_t reserved3;       /* test hook: 2..4 forces that many K-slices for the tiles of the last round (needs splitk_ws) */
   float rms_inv_dim;
   float rms_eps;
+  /* optional split-K workspace (device memory, 16-byte aligned, ZERO-FILLED once by the caller, reusable by every later
+   * launch on the same stream): when the tile count leaves the last round of the persistent grid mostly idle, the
+   * remaining tiles are cut into K-slices whose fp32 partial accumulators go through this buffer (deterministic order).
+   * 64 KB of counters + up to ~40 MB of partials; NULL / too small = no split.  Opt-in (environment VL2_GEMM_SPLITK=1): on
+   * the 7B shapes it pays only for K = 14336 and it makes rounding depend on M; see DESIGN.md. */
+  void* splitk_ws;
+  int64_t splitk_ws_bytes;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 /* Debug aid: with args->reserved2 == 777 CTA 0 records clock64() at its tile boundaries: out[0] = tiles traced (<= 7), and

@@ -103,6 +103,56 @@ def test_gemm_epilogue(cuda, act, with_res):
     assert out32.dtype == torch.float32 and relerr(out32, ref) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K,bn,kind", [
+    (1776, 4096, 4096, 0, "res_sumsq"),      # decoder o_proj: 112 pair tiles on 74 pairs -> 38 tiles split in 2
+    (1776, 6144, 4096, 0, "bias"),           # decoder QKV: 168 pair tiles -> 20 tiles split in 3
+    (1776, 4096, 1024, 1256, "plain"),       # short K: 16 k-blocks -> 2 slices of 8
+    (1200, 4096, 2048, 256, "res_sumsq"),    # single-CTA tiles: 160 tiles on 148 SMs -> 12 tiles split in 4
+    (1776, 28672, 512, 0, "swiglu"),         # SwiGLU epilogue on an owner tile
+    (300, 520, 256, 0, "bias"),              # one round, short K: nothing to split
+    (1154, 1024, 4096, 0, "res_sumsq"),      # ViT fc2 of a 2-frame shard: 20 pair tiles for 74 pairs -> 3 slices each
+    (1776, 4096, 14336, 0, "res_sumsq"),     # decoder down_proj
+])
+@pytest.mark.parametrize("slices", [2, 3, 4])
+def test_gemm_splitk_tail(cuda, M, N, K, bn, kind, slices):
+    """The last, partial round of the persistent grid is cut into K-slices (fp32 partials through the workspace, owner
+    CTA adds them in a fixed order; `slices` = 2..4 K-slices per remaining tile, forced through the test hook; off by default in production): same result as the unsplit kernel up to fp32 summation order, bit-identical from
+    launch to launch (the arrival counters re-arm themselves), and equal to the fp32 reference."""
+    from videollama2_b200 import ops
+    a = rnd((M, K), cuda, seed=11)
+    w = rnd((N, K), cuda, K ** -0.5, seed=12)
+    kw = {}
+    n_out = N
+    if kind == "bias":
+        kw["bias"] = torch.randn(N, device=cuda)
+    elif kind == "res_sumsq":
+        kw["residual"] = rnd((M, N), cuda, seed=13)
+        kw["sumsq_out"] = torch.empty((M, N // 32), device=cuda, dtype=torch.float32)
+    elif kind == "swiglu":
+        kw["act"] = ops.ACT_SWIGLU
+        n_out = N // 2
+    ref = a.float() @ w.float().t()
+    if kind == "bias":
+        ref = ref + kw["bias"]
+    elif kind == "res_sumsq":
+        ref = ref + kw["residual"].float()
+    elif kind == "swiglu":
+        ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
+    outs = []
+    for _ in range(3):
+        outs.append(ops.gemm(a, w, bn=bn, splitk=slices, **kw).clone())
+        if kind == "res_sumsq":
+            ss = kw["sumsq_out"].sum(1)
+            assert relerr(ss, outs[-1].float().pow(2).sum(1)) < 1e-3
+    assert outs[0].shape == (M, n_out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert relerr(outs[0], ref) < 6e-3
+    if kind == "res_sumsq":
+        kw["sumsq_out"] = torch.empty((M, N // 32), device=cuda, dtype=torch.float32)
+    unsplit = ops.gemm(a, w, bn=bn, splitk=False, **kw)
+    assert relerr(outs[0], unsplit.float()) < 2e-3
+
+
 def test_gemm_swiglu_and_strided(cuda):
     from videollama2_b200 import ops
     M, I, K = 260, 384, 128

@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("bcast_out", C.c_void_p * 8), ("mc_out", C.c_void_p), ("n_bcast", C.c_int32), ("reserved2", C.c_int32),
         ("rms_sumsq_in", C.c_void_p), ("sumsq_out", C.c_void_p), ("rms_nparts", C.c_int32), ("reserved3", C.c_int32),
         ("rms_inv_dim", C.c_float), ("rms_eps", C.c_float),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
     ]
 
 

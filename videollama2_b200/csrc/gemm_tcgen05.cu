@@ -63,7 +63,10 @@ struct GemmParams {
   float* sumsq_out;
   int rms_nparts;
   float rms_inv_dim, rms_eps;
-  int l2_ahead;   // k-blocks of L2 prefetch distance in the producer (0 = off)
+  // split-K of the last, partial round (see launch_gemm): items >= split_first are K-slices of the remaining tiles
+  int split_first, split_s, num_items;
+  float* ws_partial;      // [tiles past split_first][split_s - 1][tile rows][BN] fp32 partial accumulators
+  unsigned* ws_flags;     // [tiles past split_first][2] arrival counters (self-resetting)
   int trace;   // debug: CTA 0 records clock64() at tile boundaries of its MMA and epilogue roles (vl2_debug_gemm_trace)
 };
 
@@ -95,6 +98,32 @@ __device__ __forceinline__ float act_apply(float x, int act) {
     case VL2_ACT_GELU_TANH: return gelu_tanh(x);
     default: return x;
   }
+}
+
+// One unit of the persistent loop: a whole output tile (part = -1), or - for the tiles of the last, partial round - one
+// K-slice of a tile: part 0 owns the tile (adds the other slices' partials and runs the epilogue), parts > 0 dump their
+// fp32 accumulators to the workspace.  Every role (producer, MMA, epilogue) decodes the same sequence.
+constexpr size_t kSplitFlagBytes = 65536;  // arrival counters at the head of the split-K workspace, one 128-byte line each
+constexpr int kSplitFlagStride = 32;       // (zero at first use, self-resetting)
+constexpr double kSplitOverheadCycles = 16000.0;   // dump + fence + flag + owner's partial reads (trace: llm_qkv, 3 slices)
+struct WorkItem { int tile, kb0, kb1, part; };
+__device__ __forceinline__ WorkItem decode_item(int item, const GemmParams& p, int nkb) {
+  WorkItem w;
+  if (item < p.split_first) {
+    w.tile = item; w.kb0 = 0; w.kb1 = nkb; w.part = -1;
+  } else {
+    const int j = item - p.split_first;
+    w.tile = p.split_first + j / p.split_s;
+    w.part = j % p.split_s;
+    w.kb0 = (int)((long long)w.part * nkb / p.split_s);
+    w.kb1 = (int)((long long)(w.part + 1) * nkb / p.split_s);
+  }
+  return w;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 template <int BN, bool PAIR>
@@ -155,26 +184,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      // A second cursor runs p.l2_ahead k-blocks ahead of the loads and only hints the boxes into L2
-      // (cp.async.bulk.prefetch.tensor): with 6 smem stages the stage round trip (TMA issue -> data -> MMA -> commit)
-      // bounds a k-block at latency / 6; taking the HBM miss out of that round trip leaves the L2-hit latency.
       int stage = 0;
       uint32_t phase = 0;
-      int pf_tile = tile0, pf_kb = 0;
-      auto prefetch_next = [&]() {
-        if (pf_tile >= num_tiles) return;
-        const int pm0 = (pf_tile % p.num_m_tiles) * kTileM + (int)rank * BM;
-        const int pn0 = (pf_tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
-        tma_prefetch_l2_2d(&tmap_a, pf_kb * BK, pm0);
-        tma_prefetch_l2_2d(&tmap_b, pf_kb * BK, pn0);
-        if (++pf_kb == num_k_blocks) { pf_kb = 0; pf_tile += tile_stride; }
-      };
-      for (int i = 0; i < p.l2_ahead; ++i) prefetch_next();
-      for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-        const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
-        const int n0 = (tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          if (p.l2_ahead > 0) prefetch_next();
+      for (int item = tile0; item < p.num_items; item += tile_stride) {
+        const WorkItem w = decode_item(item, p, num_k_blocks);
+        const int m0 = (w.tile % p.num_m_tiles) * kTileM + (int)rank * BM;
+        const int n0 = (w.tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR) {
             // both CTAs' bytes land on the leader's full barrier
@@ -197,7 +213,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
+      for (int item = tile0; item < p.num_items; item += tile_stride, ++it) {
+        const WorkItem w = decode_item(item, p, num_k_blocks);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         const bool tr = p.trace && blockIdx.x == 0 && it < 7;
@@ -206,7 +223,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tc_fence_after_sync();
         if (tr) g_gemm_trace[8 * it + 2] = clock64();
         const uint32_t d_tmem = tmem_base + as * Cfg::kAccStride;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kStageBytesA);
@@ -215,8 +232,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            if (PAIR) umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0);
-            else umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+            if (PAIR) umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0) || (k != 0));
+            else umma_bf16_ss(d_tmem, da, db, idesc, (kb != w.kb0) || (k != 0));
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -244,13 +261,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int sw = lane & 7;                              // its swizzle key
     const int t_row = lane >> 3, t_chunk = lane & 7;      // transposed role: 8 lanes per row, 4 rows per instruction
     int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
+    for (int item = tile0; item < p.num_items; item += tile_stride, ++it) {
+      const WorkItem w = decode_item(item, p, num_k_blocks);
+      const int tile = w.tile;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const bool etr = p.trace && blockIdx.x == 0 && it < 7 && etid == 0;
       if (etr) g_gemm_trace[8 * it + 4] = clock64();
       const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
       const int n0 = (tile / p.num_m_tiles) * BN;
+      if (w.part > 0) {
+        // ---- K-slice of a split tile: dump the fp32 accumulators (thread = row, 128-byte pieces), then signal the owner
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after_sync();
+        const uint32_t taddr_p = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
+        // layout: [tile slot][slice][CTA half][epilogue warp quarter][32-column chunk][8 groups][lane][4 floats]: every
+        // warp-level store / load below is one contiguous 512-byte piece (thread = row would touch 32 lines per instruction)
+        float* dst = p.ws_partial +
+                     ((size_t)(tile - p.split_first) * (p.split_s - 1) + (w.part - 1)) * ((size_t)kTileM * BN) +
+                     (size_t)((int)rank * 4 + ew) * (32 * BN) + lane * 4;
+#pragma unroll 1
+        for (int c = grp * 32; c < BN; c += 64) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr_p + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            __stcg(reinterpret_cast<float4*>(dst + (c / 32) * 1024 + g * 128),
+                   make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                               __uint_as_float(v[4 * g + 3])));
+        }
+        __threadfence();
+        tc_fence_before_sync();
+        if (PAIR) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // every thread's partials are fenced
+        if (etid == 0) atomicAdd(p.ws_flags + ((tile - p.split_first) * 2 + (int)rank) * kSplitFlagStride, 1u);
+        continue;
+      }
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
       const uint32_t sb = smem_u32(sbias + as * 256);
@@ -274,6 +321,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after_sync();
+      const float* part_src = nullptr;
+      if (w.part == 0) {
+        // owner of a split tile: the other K-slices run concurrently on other CTAs of this (last) round
+        // ONE thread polls (a line of its own per counter): hundreds of pollers on one L2 line starve the arriving atomics
+        if (etid == 0) {
+          const unsigned* flag = p.ws_flags + ((tile - p.split_first) * 2 + (int)rank) * kSplitFlagStride;
+          unsigned spins = 0;
+          while (ld_acquire_gpu(flag) < (unsigned)(p.split_s - 1)) {
+            if (++spins > (1u << 24)) { asm volatile("trap;"); }
+            __nanosleep(200);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        part_src = p.ws_partial + (size_t)(tile - p.split_first) * (p.split_s - 1) * ((size_t)kTileM * BN) +
+                   (size_t)((int)rank * 4 + ew) * (32 * BN) + lane * 4;
+      }
       if (etr) g_gemm_trace[8 * it + 5] = clock64();
       const uint32_t taddr = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
       const int rbase = m0 + ew * 32;  // first row of this warp's 32-row block
@@ -305,8 +368,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tmem_ld_wait();
           float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) * rs;
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
           if (hf == 0 && span > 32) tmem_ld_32x32(taddr + c0 + 32, v);   // prefetch the second half
+          if (part_src != nullptr) {     // split tile: add the other K-slices in a fixed order (deterministic)
+            for (int pp = 0; pp < p.split_s - 1; ++pp) {
+              const float* src = part_src + (size_t)pp * ((size_t)kTileM * BN) + ((c0 + hf * 32) / 32) * 1024;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + g * 128));
+                x[4 * g] += t4.x; x[4 * g + 1] += t4.y; x[4 * g + 2] += t4.z; x[4 * g + 3] += t4.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] *= rs;
           if (p.bias != nullptr) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -407,6 +482,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
       if (etr) g_gemm_trace[8 * it + 6] = clock64();
+      if (w.part == 0) {   // every thread has consumed the partials: re-arm the counter for the next launch
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (etid == 0) p.ws_flags[((tile - p.split_first) * 2 + (int)rank) * kSplitFlagStride] = 0u;
+      }
       // all tcgen05.ld of this thread have completed (wait::ld above) -> hand the accumulator stage back
       tmem_ld_wait();
       tc_fence_before_sync();
@@ -422,7 +501,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
-static int l2_ahead_kblocks();
+static bool splitk_enabled();
 
 template <int BN, bool PAIR>
 static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
@@ -448,7 +527,6 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   p.rms_sumsq_in = a->rms_sumsq_in; p.sumsq_out = a->sumsq_out; p.rms_nparts = a->rms_nparts;
   p.rms_inv_dim = a->rms_inv_dim; p.rms_eps = a->rms_eps;
   p.trace = (a->reserved2 == 777) ? 1 : 0;
-  p.l2_ahead = l2_ahead_kblocks();
   p.n_bcast = a->n_bcast;
   p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
   for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
@@ -463,7 +541,45 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
-  const int units = tiles < slots ? tiles : slots;
+  // Split-K of the last, partial round (wave quantisation): the `rem` tiles left for `slots` CTAs (pairs) are cut into s
+  // K-slices each, so the round costs a fraction of a tile time.  Slice 0 owns the tile: it adds the other slices' fp32
+  // partials (workspace, fixed order -> deterministic) and runs the epilogue.  Needs the caller's workspace (splitk_ws).
+  p.split_first = tiles;
+  p.split_s = 1;
+  p.ws_flags = nullptr;
+  p.ws_partial = nullptr;
+  {
+    const int num_kb = (a->K + BK - 1) / BK;
+    const int rem = tiles % slots;
+    // s slices per remaining tile; the rem * s items may need more than one sub-round: pick the s with the shortest tail
+    // ceil(rem * s / slots) / s (in tile times; 1.0 = unsplit).  Items are dealt out in index order, an owner only waits for
+    // higher-numbered items and an item is only queued behind a lower-numbered one, so the waits cannot form a cycle.
+    int s = 1;
+    if (rem > 0) {
+      // cost of the tail round in cycles: ~550 per k-block (profiles/r01_gemm_tile_trace.txt) + the measured cost of the
+      // partials' round trip through L2, the owner's wait and its longer epilogue; a split must beat the unsplit round by 10 %
+      const double tile_cycles = 550.0 * num_kb;
+      double best = 0.9 * tile_cycles;
+      for (int c = 2; c <= 4; ++c) {
+        if (num_kb / c < 8) break;
+        const double tail = (double)((rem * c + slots - 1) / slots) / c;
+        const double cost = tail * tile_cycles + kSplitOverheadCycles;
+        if (cost < best) { best = cost; s = c; }
+      }
+    }
+    const bool forced = rem > 0 && a->reserved3 >= 2 && a->reserved3 <= 4 && num_kb >= a->reserved3;   // test hook
+    if (forced) s = a->reserved3;
+    const size_t need = kSplitFlagBytes + (size_t)rem * (s > 1 ? s - 1 : 0) * tile_m * BN * sizeof(float);
+    if (s > 1 && (splitk_enabled() || forced) && a->splitk_ws != nullptr && (size_t)a->splitk_ws_bytes >= need && (size_t)2 * rem * kSplitFlagStride * 4 <= kSplitFlagBytes &&
+        aligned16(a->splitk_ws)) {
+      p.split_first = tiles - rem;
+      p.split_s = s;
+      p.ws_flags = reinterpret_cast<unsigned*>(a->splitk_ws);
+      p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->splitk_ws) + kSplitFlagBytes);
+    }
+  }
+  p.num_items = p.split_first + (tiles - p.split_first) * p.split_s;
+  const int units = p.num_items < slots ? p.num_items : slots;
   VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
                                Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, p));
   VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
@@ -478,7 +594,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
 //   * a launch costs waves x tile time + one un-overlapped epilogue.
 struct TileChoice { int bn; bool pair; };
 
-static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair) {
+static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair, bool allow_split) {
   const int kb = (K + BK - 1) / BK;
   const double L = 3000.0;
   const int extra = 8 * 4096 + 2048 + 256;
@@ -493,7 +609,7 @@ static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair) {
       const int tile_m = pair ? 256 : 128;
       const long tiles = (long)((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
       const long slots = pair ? sms / 2 : sms;
-      const long waves = (tiles + slots - 1) / slots;
+      const long full = tiles / slots, rem = tiles % slots;
       const double stage_bytes = 16384.0 + (pair ? bn / 2 : bn) * 128.0;
       int stages = (int)((227 * 1024 - extra) / stage_bytes);
       if (stages > 8) stages = 8;
@@ -502,25 +618,34 @@ static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair) {
       const double lat = L / stages;
       double per_kb = mma > smem ? mma : smem;
       if (lat > per_kb) per_kb = lat;
-      const double cost = waves * (kb * per_kb + 600.0) + 2000.0 + bn * 16.0;
+      // the last, partial round costs a whole tile time, or a fraction of it when launch_gemm can split it along K
+      double tail = rem > 0 ? 1.0 : 0.0;
+      if (allow_split && rem > 0) {
+        for (int c = 2; c <= 4 && kb / c >= 8; ++c) {
+          const double t = (double)((rem * c + slots - 1) / slots) / c + kSplitOverheadCycles / (550.0 * kb);
+          if (t < tail * 0.9) tail = t;
+        }
+      }
+      const double cost = ((double)full + tail) * (kb * per_kb + 600.0) + 2000.0 + bn * 16.0;
       if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best.bn = bn; best.pair = pair != 0; }
     }
   }
   return best;
 }
 
-// VL2_GEMM_L2_AHEAD: L2 prefetch distance of the TMA producer in k-blocks.  Default 0 = off: measured 20-30 % SLOWER at
-// 6 / 12 / 24 k-blocks on every ViT and decoder shape (profiles/experiments/gemm_l2_prefetch.txt) - the kernel is bound by
-// the L2 -> SM request rate (~58 B/clk/SM), not by latency, and the hints double the requests.
-static int l2_ahead_kblocks() {
+// VL2_GEMM_SPLITK=1 enables the split-K tail round (needs the caller's workspace).  Default OFF: measured on the 7B shapes
+// it only pays for K = 14336 (down_proj 162 -> 157 us; the partials' round trip costs ~16 k cycles, half a K = 4096 tile),
+// i.e. 0.4 % of a step, and it makes a GEMM's rounding depend on M (how many tiles land in the last round), which would
+// end the bit-exact frame-sharding / frame-independence properties of the vision tower (tests/test_fullsize_gpu.py).
+// (An L2 prefetch cursor in the TMA producer - cp.async.bulk.prefetch.tensor 6/12/24 k-blocks ahead - was measured 20-30 %
+// slower on every shape and removed: profiles/experiments/gemm_l2_prefetch.txt.)
+static bool splitk_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("VL2_GEMM_L2_AHEAD");
-    v = e != nullptr ? atoi(e) : 0;
-    if (v < 0) v = 0;
-    if (v > 64) v = 64;
+    const char* e = getenv("VL2_GEMM_SPLITK");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  return v;
+  return v == 1;
 }
 
 static bool pair_enabled() {
@@ -572,7 +697,7 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
                 "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  TileChoice t = choose_tile(a->M, a->N, a->K, sm_count(), pair_enabled());
+  TileChoice t = choose_tile(a->M, a->N, a->K, sm_count(), pair_enabled(), splitk_enabled() && a->splitk_ws != nullptr);
   // test hook: reserved = BN forces a single-CTA tile width, 1000 + BN forces the cta_group::2 pair kernel
   if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) { t.bn = a->reserved; t.pair = false; }
   if (a->reserved >= 1128 && a->reserved <= 1256 && (a->reserved - 1000) % 32 == 0) { t.bn = a->reserved - 1000; t.pair = true; }

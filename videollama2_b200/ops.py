@@ -46,7 +46,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
          bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
-         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None, trace: bool = False) -> torch.Tensor:
+         rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None, trace: bool = False,
+         splitk=True) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
     `bn` forces the tile width (tests); 0 = library heuristic.
     `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
@@ -101,8 +102,28 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         args.mc_out = mc_ptr or None
     if trace:
         args.reserved2 = 777
+    if splitk:
+        if splitk is not True and int(splitk) > 1:
+            args.reserved3 = int(splitk)            # test hook: force the number of K-slices
+        ws = _splitk_workspace(a.device)
+        args.splitk_ws = ws.data_ptr()
+        args.splitk_ws_bytes = ws.numel()
     check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
     return out
+
+
+_SPLITK_WS_BYTES = 48 << 20
+_splitk_ws = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    """Per-(device, stream) split-K scratch of vl2_gemm_bf16 (zero-filled once: its counters re-arm themselves)."""
+    key = (torch.device(device).index, _stream())
+    ws = _splitk_ws.get(key)
+    if ws is None:
+        ws = torch.zeros((_SPLITK_WS_BYTES,), device=device, dtype=torch.uint8)
+        _splitk_ws[key] = ws
+    return ws
 
 
 def gemm_trace() -> list:
