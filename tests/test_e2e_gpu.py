@@ -236,6 +236,33 @@ def test_vision_feature_cache(setup, cuda):
         model.enable_vision_cache(0)
 
 
+def test_raw_frames_to_tokens(setup, cuda):
+    """The whole mm_infer-shaped path from decoded uint8 frames: device preprocessing (pad, Pillow-exact resize,
+    normalise) -> tower -> connector -> splice -> prefill -> greedy tokens, against the oracle fed the oracle's own
+    preprocessing of the same frames."""
+    import numpy as np
+    from oracle import preprocess_ref, torch_ref
+    from videollama2_b200 import mm_utils
+    cfg, sd, px, ids, gold, model = setup
+    proc = model.get_vision_tower().image_processor
+    size = cfg.vision.image
+    kind = "siglip" if cfg.vision.kind == "siglip" else "clip"
+    rng = np.random.default_rng(11)
+    small = rng.integers(0, 256, (cfg.frames, 12, 20, 3), dtype=np.uint8)
+    frames = np.repeat(np.repeat(small, 9, axis=1), 9, axis=2)                      # 108 x 180 blocky frames
+    pix = mm_utils.process_video(frames, proc, num_frames=cfg.frames, device=cuda)
+    _, ref_px = preprocess_ref.preprocess_frames(list(frames), size, kind, "pad", mean=tuple(proc.image_mean),
+                                                 std=tuple(proc.image_std))
+    assert pix.shape == (cfg.frames, 3, size, size)
+    assert torch.equal(pix.cpu(), torch.from_numpy(ref_px).to(torch.bfloat16))    # pixel_values: bit-exact
+    ref = torch_ref.full_forward(sd, cfg, pix.cpu(), ids, torch.float32)
+    out = model(input_ids=ids, attention_mask=torch.ones_like(ids), images=[(pix, "video")])
+    noise = torch_ref.full_forward(sd, cfg, pix.cpu(), ids, torch.bfloat16)
+    assert rel(out.logits[0], ref["logits"]) < _tol(rel(noise["logits"], ref["logits"]))
+    new = model.generate(ids, images=[(pix, "video")], max_new_tokens=2, do_sample=False)
+    assert int(new[0, 0]) == int(out.logits[0, -1].argmax())
+
+
 def test_no_cpu_fallback(setup):
     from videollama2_b200._lib import Vl2Error
     cfg, sd, px, ids, gold, model = setup

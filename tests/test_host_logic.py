@@ -103,3 +103,62 @@ def test_vision_cache_content_key():
     assert M._content_key([(z, "video")]) != k0
     odd = torch.arange(5, dtype=torch.uint8)      # byte count not a multiple of 8
     assert M._content_key([(odd, "video")]) == M._content_key([(odd.clone(), "video")])
+
+
+def test_checkpoint_reader_handles_shards_and_bin(tmp_path):
+    """`load_pretrained_model`'s checkpoint reader (model/__init__.py, reference: videollama2/model/__init__.py:165-193)
+    merges sharded safetensors through the index file, reads a single safetensors file or a pytorch_model.bin, and fails
+    loudly on an empty directory."""
+    import json
+    from safetensors.torch import save_file
+    from videollama2_b200.model import _read_checkpoint
+    a = {"model.layers.0.w": torch.arange(6, dtype=torch.float32).reshape(2, 3), "lm_head.weight": torch.ones(4, 2)}
+    b = {"model.mm_projector.readout.0.bias": torch.full((5,), 0.5)}
+    d = tmp_path / "sharded"
+    d.mkdir()
+    save_file(a, str(d / "model-00001-of-00002.safetensors"))
+    save_file(b, str(d / "model-00002-of-00002.safetensors"))
+    index = {"weight_map": {**{k: "model-00001-of-00002.safetensors" for k in a},
+                            **{k: "model-00002-of-00002.safetensors" for k in b}}}
+    (d / "model.safetensors.index.json").write_text(json.dumps(index))
+    sd = _read_checkpoint(str(d))
+    assert set(sd) == set(a) | set(b) and all(torch.equal(sd[k], {**a, **b}[k]) for k in sd)
+    one = tmp_path / "single"
+    one.mkdir()
+    save_file(a, str(one / "model.safetensors"))
+    assert set(_read_checkpoint(str(one))) == set(a)
+    binp = tmp_path / "bin"
+    binp.mkdir()
+    torch.save(b, str(binp / "pytorch_model.bin"))
+    assert torch.equal(_read_checkpoint(str(binp))["model.mm_projector.readout.0.bias"], b["model.mm_projector.readout.0.bias"])
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        _read_checkpoint(str(empty))
+
+
+def test_loader_rejects_unsupported_branches(tmp_path):
+    from videollama2_b200.model import load_pretrained_model
+    with pytest.raises(NotImplementedError):
+        load_pretrained_model(str(tmp_path), load_4bit=True)
+    with pytest.raises(NotImplementedError):
+        load_pretrained_model(str(tmp_path), model_base="base")
+    (tmp_path / "config.json").write_text('{"model_type": "videollama2_mixtral"}')
+    with pytest.raises(ValueError):
+        load_pretrained_model(str(tmp_path))
+
+
+def test_presets_flops_match_baseline():
+    """The FLOP model behind every roofline fraction reproduces BASELINE.md's totals for the three 7B configs."""
+    from videollama2_b200 import presets
+    m = presets.make_config(presets.MISTRAL_7B, 16)
+    q = presets.make_config(presets.QWEN2_7B, 16)
+    assert abs(presets.flops(m, 16, 256)["total"] / 1e12 - 34.715) < 0.01
+    assert abs(presets.flops(q, 16, 256)["total"] / 1e12 - 32.17) < 0.02
+    assert abs(presets.flops(presets.make_config(presets.MISTRAL_7B, 8), 8, 32)["total"] / 1e12 - 17.03) < 0.02
+    v21 = presets.make_config(presets.QWEN2_7B, 16, "stc_connector_v35", presets.SIGLIP_SO400M_384)
+    f = presets.flops(v21, 16, 256)
+    assert f["vis_tokens"] == 8 * 13 * 13 and f["S"] == 255 + 1352
+    names = {n for n, _, _ in presets.state_dict_specs(v21)}
+    assert "model.vision_tower.vision_tower.vision_model.embeddings.patch_embedding.bias" in names
+    assert not any("class_embedding" in n for n in names)
