@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvl2.so")
+LIB_PATH = os.environ.get("VL2_LIBVL2") or os.path.join(_HERE, "libvl2.so")   # override: A/B runs of two builds
 
 # Every symbol include/vl2.h declares (tests/test_abi.py checks the header against this list and the .so).
 SYMBOLS = [

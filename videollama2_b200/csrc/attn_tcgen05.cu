@@ -82,8 +82,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // heavy (late) causal tiles first
-  const int qt = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int head = blockIdx.y;
+  // Non-causal: x = query tile, y = head (consecutive CTAs share a head's K/V in L2).  Causal: x = head, y = query-tile
+  // rank, heaviest (latest) tile first: the hardware hands CTAs out in x-fastest order, so every head's 14-tile CTA is
+  // scheduled before any 13-tile one - longest-processing-time-first list scheduling over the SMs instead of one head
+  // after the other (and the 4 query heads of a GQA group, adjacent in x, read the same K/V tiles at the same time).
+  const int qt = p.causal ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.x;
+  const int head = p.causal ? (int)blockIdx.x : (int)blockIdx.y;
   const int b = blockIdx.z;
   const int kvh = head / p.group;
   const int q0 = qt * BQ;
@@ -365,7 +369,8 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((a->S + BQ - 1) / BQ, a->Hq, a->B);
+  const int n_qt = (a->S + BQ - 1) / BQ;
+  dim3 grid(a->causal ? a->Hq : n_qt, a->causal ? n_qt : a->Hq, a->B);
   VL2_CHECK_CUDA(launch_kernel(attn_fwd_kernel<D>, grid, dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, p));
   VL2_CHECK_LAUNCH("attn_fwd_kernel");
   return VL2_OK;
