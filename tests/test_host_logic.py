@@ -162,3 +162,42 @@ def test_presets_flops_match_baseline():
     names = {n for n, _, _ in presets.state_dict_specs(v21)}
     assert "model.vision_tower.vision_tower.vision_model.embeddings.patch_embedding.bias" in names
     assert not any("class_embedding" in n for n in names)
+
+
+def _my_mm_infer_call(case):
+    import videollama2_b200
+    from oracle.mm_infer_ref import RecordingModel, ToyChatTokenizer, summarise
+    model, tok = RecordingModel(case["model_type"]), ToyChatTokenizer()
+    frames = None if case["modal"] == "text" else torch.zeros((2, 3, 4, 4))
+    text = videollama2_b200.mm_infer(frames, case["instruct"], model, tok, modal=case["modal"], **case["kwargs"])
+    return text, summarise(model.calls[0]), model.calls[0]
+
+
+def test_mm_infer_matches_reference_goldens():
+    """videollama2_b200.mm_infer builds the same prompt ids / mask and hands generate() the same arguments as the
+    reference's mm_infer run with the same toy tokenizer (tests/golden/mm_infer.pt, oracle/mm_infer_ref.py)."""
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mm_infer.pt"))
+    for case in gold:
+        text, mine, raw = _my_mm_infer_call(case)
+        want = case["call"]
+        assert text == case["text"]
+        assert torch.equal(mine["input_ids"], want["input_ids"]) and torch.equal(mine["attention_mask"], want["attention_mask"])
+        for k in ("images_modal", "n_stopping", "do_sample", "temperature", "max_new_tokens", "top_p", "use_cache", "pad_token_id"):
+            assert mine[k] == want[k], (k, mine[k], want[k])
+        if raw["images"] is not None:
+            assert raw["images"][0][0].dtype == torch.bfloat16          # the engine's dtype (reference: .half())
+
+
+def test_mm_infer_matches_live_reference():
+    from oracle import mm_infer_ref, ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present: the committed goldens cover this")
+    instruct, modal, mtype, kw = mm_infer_ref.CASES[0]
+    text, call = mm_infer_ref.run_reference(instruct, modal, mtype, torch.zeros((2, 3, 4, 4)), **kw)
+    case = {"instruct": instruct, "modal": modal, "model_type": mtype, "kwargs": kw}
+    my_text, mine, _ = _my_mm_infer_call(case)
+    assert my_text == text and torch.equal(mine["input_ids"], mm_infer_ref.summarise(call)["input_ids"])
+    import videollama2_b200
+    with pytest.raises(ValueError):
+        videollama2_b200.mm_infer(None, "x", mm_infer_ref.RecordingModel("videollama2"), mm_infer_ref.ToyChatTokenizer(), modal="audio")
+    assert videollama2_b200.get_model_name_from_path("/ckpt/run1/checkpoint-500/") == "run1_checkpoint-500"
