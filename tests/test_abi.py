@@ -60,3 +60,54 @@ def test_ops_refuse_cpu_tensors():
         ops.gemm(x, x)
     with pytest.raises(Vl2Error):
         ops.layernorm(x, x[0], x[0], 1e-5)
+
+
+C_CONSUMER = r"""
+#include <stdio.h>
+#include <string.h>
+#include "vl2.h"
+/* A plain C99 consumer of the C-ABI: no torch, no C++.  Prints the struct sizes the Python binding must agree with and
+ * checks that argument validation happens before any CUDA call (so it also runs on a box without a GPU). */
+int main(void) {
+  vl2_gemm_args g;
+  vl2_attn_args a;
+  vl2_preprocess_args pp;
+  memset(&g, 0, sizeof g); memset(&a, 0, sizeof a); memset(&pp, 0, sizeof pp);
+  printf("%d %zu %zu %zu\n", vl2_version(), sizeof g, sizeof a, sizeof pp);
+  g.M = 4; g.N = 8; g.K = 12;                       /* K %% 8 != 0 */
+  int rc = vl2_gemm_bf16(&g, NULL);
+  printf("%d %s\n", rc, vl2_last_error());
+  rc = vl2_attention(NULL, NULL);
+  printf("%d\n", rc);
+  rc = vl2_preprocess_frames(&pp, NULL);
+  printf("%d\n", rc);
+  printf("%zu %zu\n", vl2_attention_decode_workspace(32, 8, 128), vl2_preprocess_workspace(&pp));
+  return 0;
+}
+"""
+
+
+def test_plain_c_consumer_links_and_validates(lib, tmp_path):
+    """include/vl2.h is valid C99, a C program links against libvl2.so with nothing but the header, the struct sizes
+    match the ctypes mirrors, and bad arguments are rejected with VL2_E_* codes before any device work."""
+    import shutil
+    import subprocess
+    from videollama2_b200 import _lib, preprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "consumer.c"
+    src.write_text(C_CONSUMER)
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-l:libvl2.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    ver, sz_gemm, sz_attn, sz_pp = out[0].split()
+    assert int(ver) == 100
+    assert int(sz_gemm) == ctypes.sizeof(_lib.GemmArgs) and int(sz_attn) == ctypes.sizeof(_lib.AttnArgs)
+    assert int(sz_pp) == ctypes.sizeof(preprocess.PreprocessArgs)
+    assert out[1].startswith("-") and "multiples of 8" in out[1]          # VL2_E_BADSHAPE + message
+    assert int(out[2]) < 0 and int(out[3]) < 0
+    ws_attn, ws_pp = out[4].split()
+    assert int(ws_attn) == 32 * (296 // 8) * 130 * 4 and int(ws_pp) == 0
