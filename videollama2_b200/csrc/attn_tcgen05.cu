@@ -13,6 +13,8 @@
 // Online softmax state (m, l) lives in registers of the row's thread; O accumulates in TMEM over all key tiles and is
 // rescaled in place only when a row maximum grows by more than 2^8 (lazy rescale).  S is read from TMEM once per tile.
 // QK^T of tile j+1 is issued before the softmax of tile j finishes, so tensor-core and MUFU work overlap.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -52,6 +54,7 @@ struct AttnParams {
   int64_t ldo;
   int S, Hq, group;  // group = Hq / Hkv
   int d_true;        // real head width (<= D); columns beyond it are TMA zero fill
+  int n_batch;       // B (persistent variant: the grid no longer carries it)
   int causal;
   float scale_log2;  // softmax scale * log2(e)
 };
@@ -334,6 +337,342 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant (the default; VL2_ATTN_PERSISTENT=0 selects the one-CTA-per-item kernel above): one CTA per SM loops
+// over work items, so barrier / TMEM set-up happens once per CTA, the K / V rings keep streaming across items and causal
+// items are balanced by a closed-form schedule.  Extra barriers: q_empty (the Q tile may be reloaded), o_free (O has been
+// read out of TMEM); every ring stage / phase is driven by a tile counter that runs across the items.
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
+  uint8_t* sQ = smem + Cfg::kOffQ;
+  uint8_t* sK = smem + Cfg::kOffK;
+  uint8_t* sV = smem + Cfg::kOffV;
+  uint8_t* sP = smem + Cfg::kOffP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* p_full = bars + 11;   // [2]
+  uint64_t* o_full = bars + 13;   // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_empty = bars + 16;  // MMA -> Q loader: the previous item's Q K^T MMAs have read Q
+  uint64_t* o_free = bars + 17;   // softmax -> MMA: the previous item's O has been read out of TMEM
+  float* smax = reinterpret_cast<float*>(smem + Cfg::kOffMax);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // heavy (late) causal tiles first
+  // Persistent CTA: work items = (query tile, head, batch), sorted heaviest first (causal: latest query tile first) and
+  // dealt to the CTAs boustrophedon-wise (round 0: cta, round 1: G-1-cta, ...): a closed-form schedule within a few
+  // per cent of longest-processing-time-first, identical in every role of the CTA.
+  const int n_qt = (p.S + BQ - 1) / BQ;
+  const int hb_count = p.Hq * p.n_batch;
+  const int n_items = n_qt * hb_count;
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  struct Item { int head, b, kvh, q0, n_kv; };
+  auto item_of = [&](int it, Item& w) -> bool {
+    const int idx = it * G + ((it & 1) ? (G - 1 - cta) : cta);
+    if (idx >= n_items) return false;
+    const int r = idx / hb_count, hb = idx - r * hb_count;
+    const int qt = p.causal ? (n_qt - 1 - r) : r;
+    w.head = hb % p.Hq;
+    w.b = hb / p.Hq;
+    w.kvh = w.head / p.group;
+    w.q0 = qt * BQ;
+    w.n_kv = p.causal ? (qt + 1) : (p.S + BKV - 1) / BKV;
+    return true;
+  };
+
+  pdl_launch_dependents();
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, kSoftmaxThreads);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], kSoftmaxThreads);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  pdl_wait();
+  if (warp == 9) {
+    tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 8) {
+    // ===================== TMA producers: lane 0 = Q + K ring, lane 1 = V ring (independent, never block each other)
+    Item w;
+    if (lane == 0) {
+      int gk = 0;   // K tiles loaded so far (ring stage / phase)
+      for (int it = 0; item_of(it, w); ++it) {
+        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
+        mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < Cfg::kAtoms; ++a)
+          tma_load_4d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, a * 64, w.head, w.q0, w.b);
+        for (int j = 0; j < w.n_kv; ++j, ++gk) {
+          const int st = gk & 1;
+          mbar_wait(&k_empty[st], ((gk >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
+#pragma unroll
+          for (int a = 0; a < Cfg::kAtoms; ++a)
+            tma_load_4d(sK + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_k, &k_full[st], a * 64, w.kvh, j * BKV, w.b);
+        }
+      }
+    } else if (lane == 1) {
+      int gv = 0;
+      for (int it = 0; item_of(it, w); ++it) {
+        for (int j = 0; j < w.n_kv; ++j, ++gv) {
+          const int st = gv & 1;
+          mbar_wait(&v_empty[st], ((gv >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
+#pragma unroll
+          for (int a = 0; a < Cfg::kAtoms; ++a)
+            tma_load_4d(sV + st * Cfg::kTileBytes + a * Cfg::kAtomBytes, &tmap_v, &v_full[st], a * 64, w.kvh, j * BKV, w.b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      int gq = 0, gp = 0;   // S tiles issued / P V tiles issued so far (ring stages and phases run across items)
+      auto issue_qk = [&]() {
+        const int st = gq & 1;
+        mbar_wait(&k_full[st], (gq >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
+        const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32;
+          umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + off, 16, 1024), umma_desc_sw128(k_addr + off, 16, 1024),
+                       idesc_qk, kk != 0);
+        }
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
+        ++gq;
+      };
+      Item w;
+      for (int it = 0; item_of(it, w); ++it) {
+        mbar_wait(q_full, it & 1);
+        issue_qk();
+        if (w.n_kv == 1) umma_commit(q_empty);
+        for (int j = 0; j < w.n_kv; ++j, ++gp) {
+          const int st = gp & 1;
+          if (j + 1 < w.n_kv) {
+            issue_qk();
+            if (j + 2 == w.n_kv) umma_commit(q_empty);   // last Q K^T of the item issued: Q may be overwritten once they ran
+          }
+          mbar_wait(&p_full[st], (gp >> 1) & 1);
+          mbar_wait(&v_full[st], (gp >> 1) & 1);
+          if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);   // the previous item's O has left TMEM
+          tc_fence_after_sync();
+          const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
+          const uint32_t p_addr = smem_u32(sP + st * Cfg::kPBytes);
+#pragma unroll
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
+            // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
+            const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
+            umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(&o_full[st]);
+          umma_commit(&v_empty[st]);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / output warps (two threads per query row) =====================
+    // One TMEM pass over S per tile; O accumulates in TMEM across tiles (tcgen05.mma accumulate) and is rescaled
+    // in place only when a row maximum grows by more than 2^8 (lazy rescale: probabilities stay <= 256, exact after
+    // the final division by l).  Thread (r, hf) owns columns [64 hf, 64 hf + 64) of row r's scores and columns
+    // [hf D/2, (hf+1) D/2) of its output; both threads of a row make identical rescale decisions from the exchanged
+    // row maximum, so their partial sums l share one scale and are added once at the end.
+    const int hf = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO + hf * (D / 2);
+    constexpr float kRescaleThreshold = 8.f;
+    int gt = 0;   // key tiles processed so far by this CTA: TMEM / smem stage and barrier phases run across items
+
+    const bool tr0 = p.trace && blockIdx.x == 0 && threadIdx.x == 0;
+    long long t0 = 0, acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VL2_TR(i) do { if (tr) { const long long t1 = clock64(); acc_t[i] += t1 - t0; t0 = t1; } } while (0)
+    Item w;
+    for (int it = 0; item_of(it, w); ++it) {
+    const bool tr = tr0 && it == 0;
+    const int n_kv = w.n_kv, q0 = w.q0;
+    const int qi = q0 + r;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j, ++gt) {
+      if (tr) t0 = clock64();
+      const int st = gt & 1;
+      const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
+      const int kv0 = j * BKV + hf * 64;
+      const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
+      mbar_wait(&s_full[st], (gt >> 1) & 1);
+      tc_fence_after_sync();
+      VL2_TR(0);   // waiting for S_j
+      uint32_t sv[2][32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
+      tmem_ld_wait();
+      VL2_TR(1);   // TMEM load
+      if (need_mask) {  // warp-uniform; predicated selects, no per-element branches
+        const int lim = p.causal ? min(p.S - 1, qi) : (p.S - 1);   // last visible key index for this row
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            sv[c][i] = (kv0 + c * 32 + i <= lim) ? sv[c][i] : 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+      }
+      // exchange the half-row maxima (double-buffered by tile parity: one named barrier per tile)
+      float* sm = smax + st * 256;
+      sm[hf * 128 + r] = fmaxf(mx0, mx1);
+      asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+      VL2_TR(2);   // mask + max + exchange barrier
+      const float m_tile = fmaxf(sm[r], sm[128 + r]) * p.scale_log2;
+      // reference maximum for this tile: keep the old one unless it is too stale
+      float m_use = m, alpha = 1.f;
+      const bool grow = (m_tile > m + kRescaleThreshold) || (m == -INFINITY);
+      if (grow) {
+        m_use = (m_tile == -INFINITY) ? 0.f : m_tile;   // fully masked rows stay finite
+        alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
+      }
+      // P is double buffered: buffer (j & 1) was last read by P V(j-2); O (TMEM) may only be rescaled once P V(j-1)
+      // is complete
+      if (gt > 1) mbar_wait(&o_full[st], ((gt >> 1) & 1) ^ 1);
+      if (j > 0) {
+        if (__any_sync(0xffffffffu, grow)) {
+          mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int c = 0; c < D / 64; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(o_taddr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32(o_taddr + c * 32, ov);
+          }
+          tmem_st_wait();
+        }
+      }
+      VL2_TR(3);   // waiting for P V(j-2) / rescale
+      // probabilities -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { rs0 += pr[i]; rs1 += pr[i + 1]; rs2 += pr[i + 2]; rs3 += pr[i + 3]; }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = c * 4 + g;
+          uint8_t* dst = sP + st * Cfg::kPBytes + hf * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
+                         pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
+        }
+      }
+      l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
+      m = m_use;
+      VL2_TR(4);   // exp2 + pack + st.shared
+      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&p_full[st]);
+      VL2_TR(5);   // proxy fence + arrive
+    }
+    if (tr) {
+      for (int i = 0; i < 6; ++i) g_attn_trace[i] = acc_t[i];
+      g_attn_trace[6] = n_kv;
+    }
+    // combine the two half-row sums, then each thread normalises and stores its half of the output columns.  The
+    // exchange reuses the max buffer of the item's LAST tile: the barrier below orders it after every read of that
+    // tile's maxima, the next item's first tile uses the other buffer, and the buffer is only rewritten two tiles later.
+    float* sl = smax + ((gt - 1) & 1) * 256;
+    asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+    sl[hf * 128 + r] = l;
+    asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+    const float inv = 1.f / (sl[r] + sl[128 + r]);
+    mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
+    tc_fence_after_sync();
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)w.b * p.S + qi) * p.ldo + w.head * p.d_true + hf * (D / 2);
+#pragma unroll
+    for (int c = 0; c < D / 64; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32(o_taddr + c * 32, ov);
+      tmem_ld_wait();
+      if (qi < p.S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (hf * (D / 2) + c * 32 + g * 8 >= p.d_true) break;   // head_dim < D: the zero-padded columns are not stored
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(
+              pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv),
+              pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv),
+              pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv),
+              pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv));
+        }
+      }
+    }
+    // O has left TMEM (tcgen05.wait::ld above): the MMA warp may start the next item's first P V (accumulate = 0)
+    tc_fence_before_sync();
+    mbar_arrive(o_free);
+    }   // items
+#undef VL2_TR
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+static bool attn_persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VL2_ATTN_PERSISTENT");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;   // default on: -15..-19 % on the towers, -6 % on the decoder (profiles/)
+  }
+  return v == 1;
+}
+
 template <int D>
 static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
   using Cfg = AttnCfg<D>;
@@ -362,7 +701,7 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
   }
   AttnParams p;
   p.trace = (a->reserved == 777) ? 1 : 0;
-  p.out = a->out; p.ldo = a->ldo; p.d_true = a->D; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
+  p.out = a->out; p.ldo = a->ldo; p.d_true = a->D; p.n_batch = a->B; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
@@ -370,6 +709,18 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     attr_set = true;
   }
   const int n_qt = (a->S + BQ - 1) / BQ;
+  if (attn_persistent_enabled()) {
+    static bool attr_p = false;
+    if (!attr_p) {
+      VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persistent_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      attr_p = true;
+    }
+    const int n_items = n_qt * a->Hq * a->B;
+    const int ctas = n_items < sm_count() ? n_items : sm_count();
+    VL2_CHECK_CUDA(launch_kernel(attn_fwd_persistent_kernel<D>, dim3(ctas), dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, p));
+    VL2_CHECK_LAUNCH("attn_fwd_persistent_kernel");
+    return VL2_OK;
+  }
   dim3 grid(a->causal ? a->Hq : n_qt, a->causal ? n_qt : a->Hq, a->B);
   VL2_CHECK_CUDA(launch_kernel(attn_fwd_kernel<D>, grid, dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, p));
   VL2_CHECK_LAUNCH("attn_fwd_kernel");
