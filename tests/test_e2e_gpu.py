@@ -263,6 +263,26 @@ def test_raw_frames_to_tokens(setup, cuda):
     assert int(new[0, 0]) == int(out.logits[0, -1].argmax())
 
 
+def test_sampling_generate(setup, cuda):
+    """do_sample=True: top_k = 1 reduces to greedy; a fixed generator gives the same tokens from the eager decode loop
+    and from the graph-replayed one (the sampled token is written back into the graph's token buffer)."""
+    cfg, sd, px, ids, gold, model = setup
+    imgs = [(px.to(cuda), "video")]
+    greedy = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=False)
+    k1 = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=True, temperature=0.7, top_p=0.9, top_k=1)
+    assert torch.equal(k1, greedy)
+    kw = dict(max_new_tokens=6, do_sample=True, temperature=1.5, top_p=0.95)
+    a = model.generate(ids, images=imgs, generator=torch.Generator(device=cuda).manual_seed(9), **kw)
+    b = model.generate(ids, images=imgs, generator=torch.Generator(device=cuda).manual_seed(9), **kw)
+    assert a.shape == (1, 6) and torch.equal(a, b)
+    model.enable_cuda_graphs(True)
+    try:
+        c = model.generate(ids, images=imgs, generator=torch.Generator(device=cuda).manual_seed(9), **kw)
+    finally:
+        model.enable_cuda_graphs(False)
+    assert torch.equal(c, a)
+
+
 def test_no_cpu_fallback(setup):
     from videollama2_b200._lib import Vl2Error
     cfg, sd, px, ids, gold, model = setup

@@ -201,3 +201,29 @@ def test_mm_infer_matches_live_reference():
     with pytest.raises(ValueError):
         videollama2_b200.mm_infer(None, "x", mm_infer_ref.RecordingModel("videollama2"), mm_infer_ref.ToyChatTokenizer(), modal="audio")
     assert videollama2_b200.get_model_name_from_path("/ckpt/run1/checkpoint-500/") == "run1_checkpoint-500"
+
+
+def test_sampling_warpers_match_hf():
+    """generate(do_sample=True) filters the logits exactly like HF's temperature / top-k / top-p warpers (the arguments
+    the reference's mm_infer passes, with GenerationConfig's default top_k = 50)."""
+    lp = pytest.importorskip("transformers.generation.logits_process")
+    from videollama2_b200.sampling import sample_token, warp_logits
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn((4, 300), generator=g) * 3
+    ids = torch.zeros((4, 1), dtype=torch.long)
+    for temp, k, p in [(0.2, 50, 0.9), (1.0, 50, 0.5), (0.7, 0, 0.95), (1.3, 10, 1.0), (0.2, 50, 0.01)]:
+        ref = lp.TemperatureLogitsWarper(temp)(ids, logits.clone()) if temp != 1.0 else logits.clone()
+        if k > 0:
+            ref = lp.TopKLogitsWarper(top_k=k)(ids, ref)
+        if p < 1.0:
+            ref = lp.TopPLogitsWarper(top_p=p)(ids, ref)
+        mine = warp_logits(logits, temp, k, p)
+        assert torch.equal(torch.isinf(mine), torch.isinf(ref)), (temp, k, p)
+        keep = ~torch.isinf(ref)
+        assert torch.allclose(mine[keep], ref[keep], rtol=1e-6, atol=1e-6)
+    assert sample_token(logits[0], 0.2, 0.9, top_k=1) == int(logits[0].argmax())          # top_k = 1 is greedy
+    a = sample_token(logits[1], 1.0, 0.9, generator=torch.Generator().manual_seed(5))
+    b = sample_token(logits[1], 1.0, 0.9, generator=torch.Generator().manual_seed(5))
+    assert a == b
+    with pytest.raises(ValueError):
+        warp_logits(logits, temperature=-1.0)

@@ -118,13 +118,16 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
     # ---- generate (videollama2_mistral.py:110-144) -----------------------------------------------------------------
     @torch.no_grad()
     def generate(self, inputs=None, images=None, **kwargs):
-        """Greedy decoding; returns only the NEW token ids (as HF generate does with inputs_embeds)."""
+        """Greedy decoding, or sampling with HF's temperature / top-k(50) / top-p warpers when do_sample=True (optional
+        `generator=` for reproducibility); returns only the NEW token ids (as HF generate does with inputs_embeds)."""
         kwargs.pop("position_ids", None)
         attention_mask = kwargs.pop("attention_mask", None)
         if "inputs_embeds" in kwargs:
             raise NotImplementedError("`inputs_embeds` is not supported")
-        if kwargs.get("do_sample", False) and kwargs.get("temperature", 0.0) not in (0, 0.0, None):
-            raise NotImplementedError("sampling is not implemented in the B200 engine; use do_sample=False")
+        sample = bool(kwargs.get("do_sample", False)) and kwargs.get("temperature", 1.0) not in (0, 0.0, None)
+        temperature = float(kwargs.get("temperature", 1.0) or 1.0)
+        top_p, top_k = float(kwargs.get("top_p", 1.0) or 1.0), int(kwargs.get("top_k", 50) or 0)
+        rng = kwargs.get("generator")
         if inputs.shape[0] != 1:
             raise NotImplementedError("generate supports batch size 1 (as the reference's inference scripts)")
         max_new = int(kwargs.get("max_new_tokens", 20))
@@ -146,8 +149,13 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         S = x.shape[0]
         logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache and max_new > 1, max_len=S + max_new)
         graphed = use_cache and max_new > 1 and dec.graph_decode
+        from ..sampling import sample_token
         for step in range(max_new):
-            tok = int(torch.argmax(logits[0]).item()) if not (graphed and step > 0) else int(tok_dev.item())
+            if sample:      # the graph's own argmax token is overridden below; its logits buffer is what we sample from
+                row = logits[0] if not (graphed and step > 0) else dec.decode_graph_logits[0]
+                tok = sample_token(row, temperature, top_p, top_k, rng)
+            else:
+                tok = int(torch.argmax(logits[0]).item()) if not (graphed and step > 0) else int(tok_dev.item())
             new_ids.append(tok)
             out_ids = torch.tensor([new_ids], dtype=torch.long)
             if tok in eos_ids or any(sc(out_ids, None) for sc in stopping) or step == max_new - 1:
@@ -155,6 +163,8 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
             if graphed:   # one graph launch per token: embed, 32 layers, lm_head, argmax all on the device
                 if step == 0:
                     dec.decode_graph_begin(tok)
+                elif sample:
+                    tok_dev.fill_(tok)           # the replay embeds *tok_dev: the sampled token, not the argmax
                 tok_dev = dec.decode_graph_step()
                 continue
             e = self.get_model().embed_tokens(torch.tensor([tok]))
