@@ -268,10 +268,12 @@ def test_sampling_generate(setup, cuda):
     and from the graph-replayed one (the sampled token is written back into the graph's token buffer)."""
     cfg, sd, px, ids, gold, model = setup
     imgs = [(px.to(cuda), "video")]
-    greedy = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=False)
-    k1 = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=True, temperature=0.7, top_p=0.9, top_k=1)
+    # eos_token_id=None: a sampled EOS must not cut the sequences short (this is a determinism test, not a stopping test)
+    greedy = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=False, eos_token_id=None)
+    k1 = model.generate(ids, images=imgs, max_new_tokens=5, do_sample=True, temperature=0.7, top_p=0.9, top_k=1,
+                        eos_token_id=None)
     assert torch.equal(k1, greedy)
-    kw = dict(max_new_tokens=6, do_sample=True, temperature=1.5, top_p=0.95)
+    kw = dict(max_new_tokens=6, do_sample=True, temperature=1.5, top_p=0.95, eos_token_id=None)
     a = model.generate(ids, images=imgs, generator=torch.Generator(device=cuda).manual_seed(9), **kw)
     b = model.generate(ids, images=imgs, generator=torch.Generator(device=cuda).manual_seed(9), **kw)
     assert a.shape == (1, 6) and torch.equal(a, b)
