@@ -21,19 +21,19 @@ def test_frame_shard_partition():
         frame_shard(4, 2, 2)
 
 
-@pytest.mark.parametrize("F", [16, 7, 1])
-def test_all_gather_frames_world2(F):
+@pytest.mark.parametrize("F,world", [(16, 2), (7, 2), (1, 2), (7, 3), (16, 4)])
+def test_all_gather_frames_gloo(F, world):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_gloo_worker.py")
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port), OMP_NUM_THREADS="1")
         procs.append(subprocess.Popen([sys.executable, worker, str(F)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=150)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    assert "RANK0 OK" in outs[0] and "RANK1 OK" in outs[1]
+    assert all(f"RANK{r} OK" in outs[r] for r in range(world))
