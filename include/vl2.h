@@ -114,6 +114,9 @@ int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
  * for tile t at out[8t+1..8t+6]: MMA role waits for the accumulator stage / starts issuing / issued its last commit;
  * epilogue warp starts the tile / sees the accumulator complete / stored its last span.  Synchronises the device. */
 int vl2_debug_gemm_trace(long long* host_out64);
+/* Planning only, no device work: out6 = {tile width BN, 1 if the 256-row cta_group::2 tile is used, number of tiles,
+ * CTAs (or CTA pairs) the persistent grid runs, rounds = ceil(tiles / that), SM count assumed (148 without a device)}. */
+int vl2_gemm_plan(int M, int N, int K, int with_splitk_ws, int32_t* out6);
 
 /* Skinny GEMM (M <= 32 rows, HBM-bound weight streaming): C[M,N] = act(A[M,K] W[N,K]^T + bias).
  * Used for the SE excitation MLP of the RegStage blocks (timm SEModule, projector.py:153-161) and the last-position

@@ -659,6 +659,25 @@ static bool pair_enabled() {
 
 }  // namespace vl2
 
+// Host-side planning only (no launch, no device work): which tile the cost model picks for a problem and how the
+// persistent grid will be filled.  Lets tests pin the scheduler's decisions for the shapes of the path on a CPU box.
+extern "C" int vl2_gemm_plan(int M, int N, int K, int with_splitk_ws, int32_t* out6) {
+  using namespace vl2;
+  VL2_REQUIRE(M > 0 && N > 0 && K > 0 && out6 != nullptr, VL2_E_BADSHAPE, "vl2_gemm_plan: bad arguments");
+  const int sms = sm_count();
+  const TileChoice t = choose_tile(M, N, K, sms, pair_enabled(), splitk_enabled() && with_splitk_ws != 0);
+  const int tile_m = t.pair ? 2 * BM : BM;
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + t.bn - 1) / t.bn);
+  const int slots = t.pair ? sms / 2 : sms;
+  out6[0] = t.bn;
+  out6[1] = t.pair ? 1 : 0;
+  out6[2] = tiles;
+  out6[3] = slots;
+  out6[4] = (tiles + slots - 1) / slots;   // rounds of the persistent loop
+  out6[5] = sms;
+  return VL2_OK;
+}
+
 // Debug: copy the tile-boundary cycle trace of the last traced launch (args->reserved2 == 777) to host memory.
 extern "C" int vl2_debug_gemm_trace(long long* host_out64) {
   VL2_REQUIRE(host_out64 != nullptr, VL2_E_BADSHAPE, "vl2_debug_gemm_trace: null output");
