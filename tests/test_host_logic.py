@@ -142,7 +142,7 @@ def test_loader_rejects_unsupported_branches(tmp_path):
     with pytest.raises(NotImplementedError):
         load_pretrained_model(str(tmp_path), load_4bit=True)
     with pytest.raises(NotImplementedError):
-        load_pretrained_model(str(tmp_path), model_base="base")
+        load_pretrained_model(str(tmp_path), model_base="base", model_name="videollama2-lora-x")   # LoRA adapters
     (tmp_path / "config.json").write_text('{"model_type": "videollama2_mixtral"}')
     with pytest.raises(ValueError):
         load_pretrained_model(str(tmp_path))
@@ -227,3 +227,123 @@ def test_sampling_warpers_match_hf():
     assert a == b
     with pytest.raises(ValueError):
         warp_logits(logits, temperature=-1.0)
+
+
+def test_synthetic_checkpoint_matches_oracle_factory():
+    """presets.synth_tensor / state_dict_specs (what bench.py and the full-depth GPU tests load into the engine) are
+    byte-identical to oracle.synth (what the committed goldens were computed with)."""
+    import torch
+    from oracle import synth
+    from videollama2_b200 import presets
+    for name, llm in (("cfg2", presets.MISTRAL_7B), ("cfg3", presets.QWEN2_7B)):
+        ocfg = synth.CONFIGS[name]
+        ours = presets.state_dict_specs(presets.make_config(llm, ocfg.frames))
+        theirs = synth.model_specs(ocfg)
+        assert [(n, tuple(s), k) for n, s, k in ours] == [(n, tuple(s), k) for n, s, k in theirs]
+    picks = [("model.layers.3.self_attn.q_proj.weight", (64, 48), "w"), ("model.norm.weight", (96,), "gain"),
+             ("model.layers.0.self_attn.k_proj.bias", (40,), "bias"), ("model.embed_tokens.weight", (50, 32), "emb"),
+             ("model.mm_projector.sampler.0.weight", (8, 8, 2, 2, 2), "w")]
+    for name, shape, kind in picks:
+        assert torch.equal(presets.synth_tensor(name, shape, kind), synth.make_tensor(name, shape, kind))
+    cfg = presets.make_config(presets.MISTRAL_7B, 16)
+    px, ids = presets.synthetic_inputs(cfg, 16, 256)
+    opx, oids = synth.inputs(synth.CONFIGS["cfg2"])
+    assert torch.equal(px, opx) and torch.equal(ids, oids)
+
+
+def test_vision_config_family_defaults_and_hub_ids():
+    """A SigLIP config.json that omits layer_norm_eps / hidden_act must get SigLIP's defaults (1e-6, gelu-tanh), not
+    CLIP's; hub ids of the two supported towers resolve without a local directory."""
+    from videollama2_b200.model.config import VisionConfig
+    s = VisionConfig.from_dict({"model_type": "siglip_vision_model", "hidden_size": 1152, "num_attention_heads": 16})
+    assert s.layer_norm_eps == 1e-6 and s.hidden_act == "gelu_pytorch_tanh"
+    c = VisionConfig.from_dict({"vision_config": {"model_type": "clip_vision_model", "hidden_size": 1024}})
+    assert c.layer_norm_eps == 1e-5 and c.hidden_act == "quick_gelu"
+    so = VisionConfig.from_dir("google/siglip-so400m-patch14-384")
+    assert (so.hidden_size, so.intermediate_size, so.num_hidden_layers, so.image_size, so.layer_norm_eps) == (1152, 4304, 27, 384, 1e-6)
+    cl = VisionConfig.from_dir("openai/clip-vit-large-patch14-336")
+    assert (cl.hidden_size, cl.num_hidden_layers, cl.image_size, cl.layer_norm_eps, cl.hidden_act) == (1024, 24, 336, 1e-5, "quick_gelu")
+    with pytest.raises(FileNotFoundError):
+        VisionConfig.from_dir("some/unknown-tower")
+
+
+def test_assemble_state_dict_base_plus_projector(tmp_path):
+    """model/__init__.py:138-164: LLM from model_base, mm_projector.bin from model_path, tower from its local directory."""
+    import torch
+    from safetensors.torch import save_file
+    from videollama2_b200.model import assemble_state_dict
+    base, path, tower = tmp_path / "base", tmp_path / "ckpt", tmp_path / "clip-tower"
+    for d in (base, path, tower):
+        d.mkdir()
+    llm = {"model.embed_tokens.weight": torch.randn(8, 4), "lm_head.weight": torch.randn(8, 4)}
+    save_file(llm, str(base / "model.safetensors"))
+    proj = {"model.mm_projector.readout.0.weight": torch.randn(4, 4), "model.mm_projector.readout.0.bias": torch.randn(4)}
+    torch.save(proj, str(path / "mm_projector.bin"))
+    tw = {"vision_model.embeddings.class_embedding": torch.randn(4), "text_model.ignored": torch.randn(2)}
+    save_file(tw, str(tower / "model.safetensors"))
+    cfg = type("C", (), {"mm_vision_tower": str(tower)})()
+    sd = assemble_state_dict(str(path), str(base), cfg)
+    assert torch.equal(sd["lm_head.weight"], llm["lm_head.weight"])
+    assert torch.equal(sd["model.mm_projector.readout.0.weight"], proj["model.mm_projector.readout.0.weight"].to(torch.float16))
+    assert torch.equal(sd["model.vision_tower.vision_tower.vision_model.embeddings.class_embedding"],
+                       tw["vision_model.embeddings.class_embedding"])
+    assert not any("text_model" in k for k in sd)
+    cfg.mm_vision_tower = "openai/clip-vit-large-patch14-336"
+    with pytest.raises(FileNotFoundError):
+        assemble_state_dict(str(path), str(base), cfg)
+    # SFT branch: everything from model_path
+    save_file({**llm, **{k: v for k, v in proj.items()}}, str(path / "model.safetensors"))
+    assert set(assemble_state_dict(str(path))) == set(llm) | set(proj)
+
+
+class _DecodingToyTokenizer:
+    """Word-piece toy with a decoder: id 3 + i <-> _VOCAB[i]; pieces are concatenated without spaces, so a keyword can
+    straddle several ids (what the decoded-text branch of KeywordsStoppingCriteria exists for)."""
+    bos_token_id = 1
+    _VOCAB = ["he", "llo", " wor", "ld", "hello!", " stop", "x", "y"]
+
+    class _Enc:
+        def __init__(self, ids):
+            self.input_ids = ids
+
+    def __call__(self, text, add_special_tokens=True):
+        ids, rest = [], text
+        while rest:
+            for i, p in sorted(enumerate(self._VOCAB), key=lambda t: -len(t[1])):
+                if rest.startswith(p):
+                    ids.append(3 + i)
+                    rest = rest[len(p):]
+                    break
+            else:
+                raise ValueError(rest)
+        return self._Enc(([self.bos_token_id] if add_special_tokens else []) + ids)
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return ["".join(self._VOCAB[int(t) - 3] for t in row if int(t) >= 3) for row in ids]
+
+
+def test_keywords_stopping_criteria_decoded_text_branch_matches_reference():
+    """mm_utils.py:332-337: the keyword may be spelled by different ids than tokenizer(keyword) produced; the decoded tail
+    (window = longest keyword, in ids) is searched too.  Compared call by call with the reference class when
+    /root/reference exists."""
+    from videollama2_b200.mm_utils import KeywordsStoppingCriteria
+    tok = _DecodingToyTokenizer()
+    prompt = torch.zeros(1, 2, dtype=torch.long)
+    ours = KeywordsStoppingCriteria(["hello"], tok, prompt)
+    kw = tok("hello", add_special_tokens=False).input_ids             # ["he", "llo"]
+    bang = tok("hello!", add_special_tokens=False).input_ids          # one id spelling "hello!"
+    assert len(kw) == 2 and len(bang) == 1
+    x, y = tok("x", add_special_tokens=False).input_ids[0], tok("y", add_special_tokens=False).input_ids[0]
+    cases = [torch.tensor([[x, y] + kw]), torch.tensor([[x, y, x] + bang]), torch.tensor([[x, y, x, y]]),
+             torch.tensor([bang]), torch.tensor([[x] + bang + [y, y, y, y]]), torch.tensor([[x, y, y] + bang + [y]]),
+             torch.tensor([[x, y] + kw, [x, y, y, y]]), torch.tensor([[x] + kw, [y] + kw])]
+    got = [ours(c, None) for c in cases]
+    assert got[0] is True and got[2] is False and got[6] is False and got[7] is True
+    assert got[1] is True          # id tail differs from tokenizer("hello"), the decoded window contains it
+    from oracle import ref_loader
+    if ref_loader.available():
+        import importlib
+        ref_loader.load()
+        ref_cls = importlib.import_module("videollama2.mm_utils").KeywordsStoppingCriteria
+        ref = ref_cls(["hello"], tok, prompt)
+        assert got == [bool(ref(c, None)) for c in cases]

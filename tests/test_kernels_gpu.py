@@ -180,6 +180,8 @@ def test_gemm_rejects_bad_args(cuda):
     # head widths between the native 64 / 128 (SigLIP-so400m: 16 heads x 72): heads packed at their true width
     (3, 729, 16, 16, 72, False), (2, 25, 2, 2, 72, False), (1, 200, 4, 2, 96, True), (2, 130, 3, 3, 40, False),
     (1, 77, 2, 2, 8, False),
+    # Qwen2-7B geometry: 28 query heads over 4 kv heads (GQA group 7), full config-3 sequence length
+    (1, 1776, 28, 4, 128, True), (1, 300, 14, 2, 128, True), (2, 130, 7, 1, 64, False),
 ])
 def test_attention(cuda, B, S, Hq, Hkv, D, causal):
     from videollama2_b200 import ops

@@ -703,18 +703,10 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
   p.trace = (a->reserved == 777) ? 1 : 0;
   p.out = a->out; p.ldo = a->ldo; p.d_true = a->D; p.n_batch = a->B; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  VL2_SMEM_OPT_IN(attn_fwd_kernel<D>, Cfg::kSmemBytes);
   const int n_qt = (a->S + BQ - 1) / BQ;
   if (attn_persistent_enabled()) {
-    static bool attr_p = false;
-    if (!attr_p) {
-      VL2_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_persistent_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-      attr_p = true;
-    }
+    VL2_SMEM_OPT_IN(attn_fwd_persistent_kernel<D>, Cfg::kSmemBytes);
     const int n_items = n_qt * a->Hq * a->B;
     const int ctas = n_items < sm_count() ? n_items : sm_count();
     VL2_CHECK_CUDA(launch_kernel(attn_fwd_persistent_kernel<D>, dim3(ctas), dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, p));

@@ -355,12 +355,8 @@ int vl2::launch_gemv(const void* x, const void* W, const float* bias, const void
   const int blocks = (N + rows_per_cta - 1) / rows_per_cta;
   const size_t smem = two ? (size_t)kGemvWarps * GemvCfg<2>::kStages * 2 * kGemvChunk
                           : (size_t)kGemvWarps * GemvCfg<1>::kStages * kGemvChunk;
-  static bool attr = false;
-  if (!attr) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
+  VL2_SMEM_OPT_IN((gemv_kernel<2, true>), 64 * 1024);
+  VL2_SMEM_OPT_IN((gemv_kernel<2, false>), 64 * 1024);
 #define VL2_GEMV(RR, RMS_)                                                                                                  \
   launch_kernel(gemv_kernel<RR, RMS_>, dim3(blocks), dim3(kGemvWarps * 32), smem, stream, 1, (const bf16*)x, (const bf16*)W, \
                 bias, (const bf16*)residual, y, out_f32, N, K, act, rms_eps)

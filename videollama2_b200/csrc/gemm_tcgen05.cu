@@ -533,12 +533,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   const int tile_m = PAIR ? 2 * BM : BM;
   p.num_m_tiles = (a->M + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + BN - 1) / BN;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VL2_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR>), Cfg::kSmemBytes);
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
   // Split-K of the last, partial round (wave quantisation): the `rem` tiles left for `slots` CTAs (pairs) are cut into s

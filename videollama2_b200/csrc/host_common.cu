@@ -35,15 +35,22 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 int sm_count() {
-  static int cached = -1;
-  if (cached < 0) {
+  static int cached[kMaxDevices] = {};
+  const int slot = device_slot();
+  if (cached[slot] <= 0) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
+    cached[slot] = n;
   }
-  return cached;
+  return cached[slot];
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -12,7 +12,9 @@ namespace vl2 {
 
 int set_error(int code, const char* fmt, ...);
 void count_launch(int n = 1);
-int sm_count();
+int sm_count();        // of the CURRENT device (cached per device)
+int device_slot();     // cudaGetDevice(), clamped to [0, kMaxDevices): index of per-device host caches
+static constexpr int kMaxDevices = 64;
 
 // Encode a tiled bf16 tensor map with 128-byte swizzle and zero OOB fill.
 // dims/strides are innermost-first; strides (bytes) are given for dims 1..rank-1.
@@ -38,6 +40,18 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 #define VL2_REQUIRE(cond, code, ...)                           \
   do {                                                         \
     if (!(cond)) return ::vl2::set_error(code, __VA_ARGS__);   \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device (context): opt in once per (kernel, device), so a
+// process that drives several GPUs (torch.cuda.device(i) around the calls) gets the attribute on each of them.
+#define VL2_SMEM_OPT_IN(kernel, bytes)                                                                              \
+  do {                                                                                                              \
+    static bool _vl2_done[::vl2::kMaxDevices] = {};                                                                 \
+    const int _vl2_dev = ::vl2::device_slot();                                                                      \
+    if (!_vl2_done[_vl2_dev]) {                                                                                     \
+      VL2_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      _vl2_done[_vl2_dev] = true;                                                                                   \
+    }                                                                                                               \
   } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -116,11 +116,7 @@ extern "C" int vl2_preprocess_frames(const vl2_preprocess_args* a, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)a->canvas_w * 3;
   if (smem > 48 * 1024) {
-    static bool attr = false;
-    if (!attr) {
-      VL2_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
-    }
+    VL2_SMEM_OPT_IN(resample_h_kernel, 64 * 1024);
   }
   const uint32_t pad = (uint32_t)a->pad_rgb[0] | ((uint32_t)a->pad_rgb[1] << 8) | ((uint32_t)a->pad_rgb[2] << 16);
   launch_kernel(resample_h_kernel, dim3(a->canvas_h, a->T), dim3(256), smem, st, 1, a->frames, a->tmp, a->H, a->W, a->canvas_h,

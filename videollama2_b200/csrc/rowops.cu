@@ -727,11 +727,7 @@ extern "C" int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void*
   float* partial = pooled ? pooled + (int64_t)F * C : nullptr;
   const size_t dw_smem = (size_t)9 * C * sizeof(bf16);
   if (dw_smem > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      VL2_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_ln_silu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 4096 * 2));
-      attr_set = true;
-    }
+    VL2_SMEM_OPT_IN(dwconv3x3_ln_silu_kernel, 9 * 4096 * 2);
   }
   launch_kernel(dwconv3x3_ln_silu_kernel, dim3((unsigned)(F * H)), dim3(threads), dw_smem, (cudaStream_t)stream, 1, 
       (const bf16*)x, (const bf16*)w9c, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, partial, H, W, C, eps);

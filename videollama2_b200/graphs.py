@@ -6,6 +6,7 @@ kernels on the current stream, so it can be captured once per input shape and re
 launch-latency bound."""
 from __future__ import annotations
 
+import collections
 from typing import Callable, Dict, Tuple
 
 import torch
@@ -15,10 +16,11 @@ class GraphedStage:
     """Caches one CUDA graph per (shape, dtype) signature of the inputs.  Outputs live in static buffers owned by the
     graph: they are valid until the next call with the same signature (callers consume them immediately)."""
 
-    def __init__(self, fn: Callable[..., torch.Tensor], warmup: int = 2):
+    def __init__(self, fn: Callable[..., torch.Tensor], warmup: int = 2, max_entries: int = 8):
         self.fn = fn
         self.warmup = warmup
-        self.cache: Dict[Tuple, Tuple] = {}
+        self.max_entries = max_entries      # LRU bound: every entry owns a graph + its activation pool (varied prompt
+        self.cache: "collections.OrderedDict[Tuple, Tuple]" = collections.OrderedDict()   # lengths must not grow memory forever)
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
         key = tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs)
@@ -36,6 +38,10 @@ class GraphedStage:
                 static_out = self.fn(*static_in)
             entry = (graph, static_in, static_out)
             self.cache[key] = entry
+            while len(self.cache) > self.max_entries:
+                self.cache.popitem(last=False)          # least recently used graph and its buffers are released
+        else:
+            self.cache.move_to_end(key)
         graph, static_in, static_out = entry
         for dst, src in zip(static_in, inputs):
             if dst.data_ptr() != src.data_ptr():

@@ -121,23 +121,41 @@ def spliced_labels(labels: torch.Tensor, input_ids: torch.Tensor, mm_lengths: Se
 
 
 class KeywordsStoppingCriteria:
-    """Stop when the tail of the generated ids equals one of the keyword id sequences (mm_utils.py:314-345)."""
+    """mm_utils.py:314-345.  A row stops when (a) the tail of its ids equals one of the keyword id sequences, or (b) the
+    decoded text of its last `offset` ids contains a keyword, offset = min(len(ids) - start_len, longest keyword) exactly
+    as the reference computes it (with `generate(inputs_embeds=...)` the ids hold only NEW tokens while start_len is the
+    prompt length, so the window `ids[-offset:]` follows Python's slicing of a possibly negative / zero offset); the batch
+    stops when every row does."""
 
     def __init__(self, keywords, tokenizer, input_ids):
+        self.keywords = list(keywords)
         self.keyword_ids = []
-        for kw in keywords:
+        self.max_keyword_len = 0
+        for kw in self.keywords:
             cur = tokenizer(kw).input_ids
             if len(cur) > 1 and cur[0] == tokenizer.bos_token_id:
                 cur = cur[1:]
+            self.max_keyword_len = max(self.max_keyword_len, len(cur))
             self.keyword_ids.append(torch.tensor(cur))
+        self.tokenizer = tokenizer
         self.start_len = input_ids.shape[1]
 
-    def __call__(self, output_ids: torch.Tensor, scores=None, **kw) -> bool:
+    def _row_stops(self, row: torch.Tensor) -> bool:
+        row = row.cpu()
         for kid in self.keyword_ids:
             n = kid.numel()
-            if output_ids.shape[1] >= n and torch.equal(output_ids[0, -n:].cpu(), kid):
+            tail = row[-n:]
+            if tail.numel() == n and torch.equal(tail, kid):
                 return True
-        return False
+        decode = getattr(self.tokenizer, "batch_decode", None)
+        if decode is None:
+            return False
+        offset = min(row.numel() - self.start_len, self.max_keyword_len)
+        text = decode(row[-offset:].unsqueeze(0), skip_special_tokens=True)[0]
+        return any(kw in text for kw in self.keywords)
+
+    def __call__(self, output_ids: torch.Tensor, scores=None, **kw) -> bool:
+        return all(self._row_stops(output_ids[i]) for i in range(output_ids.shape[0]))
 
 
 # ----------------------------------------------------------------------------------------------------------------

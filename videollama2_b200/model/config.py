@@ -21,13 +21,49 @@ class VisionConfig:
     hidden_act: str = "quick_gelu"
     model_type: str = "clip_vision_model"
 
+    # defaults of the two tower families when a config.json omits a key (HF CLIPVisionConfig / SiglipVisionConfig defaults)
+    _FAMILY_DEFAULTS = {
+        "clip": dict(layer_norm_eps=1e-5, hidden_act="quick_gelu", model_type="clip_vision_model"),
+        "siglip": dict(layer_norm_eps=1e-6, hidden_act="gelu_pytorch_tanh", model_type="siglip_vision_model"),
+    }
+    # the two towers the reference's released checkpoints name by hub id (README.md:117-126); used when the id is not a
+    # local directory (there is no hub access in this engine)
+    _KNOWN_TOWERS = {
+        "clip-vit-large-patch14-336": dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
+                                           num_attention_heads=16, image_size=336, patch_size=14),
+        "siglip-so400m-patch14-384": dict(hidden_size=1152, intermediate_size=4304, num_hidden_layers=27,
+                                          num_attention_heads=16, image_size=384, patch_size=14),
+    }
+
     @classmethod
-    def from_dir(cls, path: str) -> "VisionConfig":
-        with open(os.path.join(path, "config.json")) as fh:
-            d = json.load(fh)
+    def _family(cls, d: dict, hint: str = "") -> str:
+        mt = str(d.get("model_type", "")).lower()
+        return "siglip" if ("siglip" in mt or (not mt and "siglip" in hint.lower())) else "clip"
+
+    @classmethod
+    def from_dict(cls, d: dict, hint: str = "") -> "VisionConfig":
+        """A (possibly partial) HF vision config dict -> VisionConfig; keys the file omits take the defaults of ITS
+        family (SigLIP: eps 1e-6 / gelu_pytorch_tanh, CLIP: eps 1e-5 / quick_gelu), not CLIP's for both."""
         d = d.get("vision_config", d)
         names = {f.name for f in dataclasses.fields(cls)}
-        return cls(**{k: v for k, v in d.items() if k in names})
+        kw = dict(cls._FAMILY_DEFAULTS[cls._family(d, hint)])
+        kw.update({k: v for k, v in d.items() if k in names})
+        return cls(**kw)
+
+    @classmethod
+    def from_dir(cls, path: str) -> "VisionConfig":
+        """`path`: a local directory with config.json, or one of the hub ids the reference checkpoints carry in
+        `mm_vision_tower` (resolved from the built-in table: no network)."""
+        cfg_file = os.path.join(path, "config.json")
+        if os.path.isfile(cfg_file):
+            with open(cfg_file) as fh:
+                return cls.from_dict(json.load(fh), hint=path)
+        base = os.path.basename(os.path.normpath(path)).lower()
+        for key, dims in cls._KNOWN_TOWERS.items():
+            if key in base:
+                return cls(**dims, **cls._FAMILY_DEFAULTS["siglip" if "siglip" in key else "clip"])
+        raise FileNotFoundError(f"vision tower '{path}' is neither a local directory with config.json nor a known tower "
+                                f"({', '.join(cls._KNOWN_TOWERS)})")
 
 
 @dataclasses.dataclass

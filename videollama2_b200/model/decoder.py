@@ -108,11 +108,13 @@ class DecoderEngine:
         return x, ss_out
 
     def prefill(self, embeds: torch.Tensor, all_logits: bool = False, keep_cache: bool = False,
-                max_len: Optional[int] = None, _no_graph: bool = False):
-        """embeds [S,H] bf16 -> (logits fp32 [S,V] or [1,V], final hidden [S,H] or None when graph-replayed)."""
+                max_len: Optional[int] = None, _no_graph: bool = False, tap=None):
+        """embeds [S,H] bf16 -> (logits fp32 [S,V] or [1,V], final hidden [S,H] or None when graph-replayed).
+        `tap(layer_index, stream)` (parity checks only) sees the residual stream after every layer; it forces the
+        eager path."""
         if not self.is_loaded:
             raise RuntimeError("DecoderEngine: weights not loaded")
-        if self._graphed is not None and not _no_graph and not all_logits and not keep_cache:
+        if self._graphed is not None and not _no_graph and not all_logits and not keep_cache and tap is None:
             return self._graphed(embeds.contiguous()), None
         S = embeds.shape[0]
         x = embeds
@@ -122,6 +124,8 @@ class DecoderEngine:
         ss_x = ops.row_sumsq(x)
         for i, L in enumerate(self.layers):
             x, ss_x = self._layer(L, x, S, 0, self.kv[i][:S] if keep_cache else None, ss_x)
+            if tap is not None:
+                tap(i, x)
         if all_logits:
             logits = ops.gemm(x, self.w["lm_head"], out_dtype=torch.float32, rms_in=ss_x, rms_eps=self.eps)
         else:

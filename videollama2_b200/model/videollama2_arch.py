@@ -35,6 +35,9 @@ class Videollama2MetaModel:
 
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         """Embedding lookup through the gather kernel (ids >= 0)."""
+        bad = (ids < 0) | (ids >= self.config.vocab_size)
+        if bool(bad.any()):     # the reference's nn.Embedding raises on these (e.g. a modal placeholder left without images)
+            raise IndexError(f"embed_tokens: id {int(ids[bad].reshape(-1)[0])} outside [0, {self.config.vocab_size})")
         flat = ids.reshape(-1).to(device=self.decoder.device, dtype=torch.int64).contiguous()
         out = torch.empty((flat.numel(), self.config.hidden_size), device=self.decoder.device, dtype=torch.bfloat16)
         if flat.numel():

@@ -3,6 +3,7 @@ stream and returns the output tensor; nothing here computes with torch ops (torc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -27,9 +28,20 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    """Every operand must live on the CURRENT CUDA device: the kernels are enqueued on that device's current stream
+    (`_stream`), so a tensor of another GPU would be dereferenced from the wrong device.  Callers that drive several GPUs
+    from one process wrap the call in `torch.cuda.device(i)` (the engine classes do: model/_device_guard)."""
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.Vl2Error("videollama2_b200 kernels need CUDA tensors; there is no CPU fallback")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.Vl2Error(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: run the call under "
+                                f"`torch.cuda.device({t.device.index})` (kernels launch on the current device's stream)")
 
 
 def _bf16(*ts: Optional[torch.Tensor]) -> None:
@@ -102,8 +114,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         args.mc_out = mc_ptr or None
     if trace:
         args.reserved2 = 777
-    if splitk:
-        if splitk is not True and int(splitk) > 1:
+    forced = splitk is not True and splitk and int(splitk) > 1
+    if forced or (splitk and _SPLITK_ENV):          # the workspace exists only when the split-K tail can actually run
+        if forced:
             args.reserved3 = int(splitk)            # test hook: force the number of K-slices
         ws = _splitk_workspace(a.device)
         args.splitk_ws = ws.data_ptr()
@@ -113,6 +126,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 
 
 _SPLITK_WS_BYTES = 48 << 20
+_SPLITK_ENV = os.environ.get("VL2_GEMM_SPLITK", "0") == "1"   # same switch as the library's splitk_enabled()
 _splitk_ws = {}
 
 

@@ -110,6 +110,63 @@ def random_state_dict(cfg: Videollama2Config, device, seed: int = 20240603):
     return sd
 
 
+SYNTH_SEED = 20240603
+
+
+def synth_tensor(name: str, shape, kind: str):
+    """One tensor of the deterministic synthetic checkpoint: its own torch CPU generator seeded with
+    crc32(name) ^ SYNTH_SEED, so any subset regenerates identically on any box with the same torch build.  Byte-identical
+    to the weight factory the parity goldens were produced with (tests/test_host_logic.py pins the two together)."""
+    import zlib
+
+    import torch
+    g = torch.Generator(device="cpu").manual_seed((zlib.crc32(name.encode()) ^ SYNTH_SEED) & 0x7FFFFFFF)
+    x = torch.randn(tuple(shape), generator=g, dtype=torch.float32)
+    if kind == "w":
+        fan_in = 1
+        for d in shape[1:]:
+            fan_in *= d
+        x *= fan_in ** -0.5
+    elif kind == "gain":
+        x = 1.0 + 0.1 * x
+    elif kind == "bias":
+        x *= 0.02
+    elif kind == "emb":
+        x *= 0.05
+    else:
+        raise ValueError(kind)
+    return x.to(torch.bfloat16)
+
+
+def synthetic_state_dict(cfg: Videollama2Config, device, threads: int = 8):
+    """The deterministic synthetic checkpoint of `cfg`, generated on the HOST RNG (so that it equals the weights the
+    committed full-depth goldens were computed with) and moved to `device` tensor by tensor."""
+    import concurrent.futures as cf
+
+    import torch
+    dev = torch.device(device)
+    specs = state_dict_specs(cfg)
+
+    def one(spec):
+        name, shape, kind = spec
+        return name, synth_tensor(name, shape, kind).to(dev, non_blocking=False)
+
+    with cf.ThreadPoolExecutor(max(1, threads)) as ex:
+        return dict(ex.map(one, specs))
+
+
+def synthetic_inputs(cfg: Videollama2Config, frames: int, prompt: int):
+    """(pixels bf16 [T,3,H,W], input_ids int64 [1,P] with <video> = -201 at index 4) — SURVEY.md §8d."""
+    import torch
+    v = cfg.vision_config
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    px = torch.randn((frames, 3, v.image_size, v.image_size), generator=g).to(torch.bfloat16)
+    g2 = torch.Generator(device="cpu").manual_seed(1235)
+    ids = torch.randint(3, cfg.vocab_size, (1, prompt), generator=g2, dtype=torch.int64)
+    ids[0, 4] = -201
+    return px, ids
+
+
 def flops(cfg: Videollama2Config, frames: int, prompt: int, all_logits: bool = False) -> dict:
     """Algorithmic FLOPs of one video->text prefill (2*M*N*K per GEMM; attention 4*S^2*d per head, causal halved;
     ViT counted for the layers actually consumed; last-position logits).  Matches BASELINE.md §2."""
