@@ -27,7 +27,7 @@ def _w(sd: SD, name: str, dtype) -> torch.Tensor:
 # :339-351 (MLP, quick_gelu), :354-385 (layer), :647-696 (encoder + hidden_states), feature_select encoder.py:31-39
 # ----------------------------------------------------------------------------------------------------------------
 def vit_hidden_states(sd: SD, v, pixels: torch.Tensor, dtype=torch.float32, n_layers: Optional[int] = None,
-                      pfx: str = VPFX) -> List[torch.Tensor]:
+                      pfx: str = VPFX, sdpa: bool = False) -> List[torch.Tensor]:
     x = pixels.to(dtype)
     Fn = x.shape[0]
     siglip = getattr(v, "kind", "clip") == "siglip"
@@ -55,8 +55,11 @@ def vit_hidden_states(sd: SD, v, pixels: torch.Tensor, dtype=torch.float32, n_la
         q = q.view(Fn, S, v.heads, d).transpose(1, 2)
         k = k.view(Fn, S, v.heads, d).transpose(1, 2)
         vv = vv.view(Fn, S, v.heads, d).transpose(1, 2)
-        att = torch.softmax((q @ k.transpose(-1, -2)).float() * d ** -0.5, dim=-1).to(dtype)
-        o = (att @ vv).transpose(1, 2).reshape(Fn, S, v.hidden)
+        if sdpa:    # what HF runs with attn_implementation="sdpa" (the timing baseline); the eager form below is the golden
+            o = F.scaled_dot_product_attention(q, k, vv, scale=d ** -0.5).transpose(1, 2).reshape(Fn, S, v.hidden)
+        else:
+            att = torch.softmax((q @ k.transpose(-1, -2)).float() * d ** -0.5, dim=-1).to(dtype)
+            o = (att @ vv).transpose(1, 2).reshape(Fn, S, v.hidden)
         h = r + F.linear(o, _w(sd, p + "self_attn.out_proj.weight", dtype), _w(sd, p + "self_attn.out_proj.bias", dtype))
         r = h
         y = F.layer_norm(h, (v.hidden,), _w(sd, p + "layer_norm2.weight", dtype), _w(sd, p + "layer_norm2.bias", dtype), v.eps)
@@ -67,11 +70,11 @@ def vit_hidden_states(sd: SD, v, pixels: torch.Tensor, dtype=torch.float32, n_la
     return hs
 
 
-def vit_features(sd: SD, v, pixels: torch.Tensor, select_layer: int = -2, dtype=torch.float32) -> torch.Tensor:
+def vit_features(sd: SD, v, pixels: torch.Tensor, select_layer: int = -2, dtype=torch.float32, sdpa: bool = False) -> torch.Tensor:
     """CLIPVisionTower.forward + feature_select('patch'): hidden_states[select_layer][:, 1:] (encoder.py:31-53).
     Layers after the selected one are skipped (they do not influence the result)."""
     n = v.layers + 1 + select_layer if select_layer < 0 else select_layer
-    hs = vit_hidden_states(sd, v, pixels, dtype, n_layers=n)
+    hs = vit_hidden_states(sd, v, pixels, dtype, n_layers=n, sdpa=sdpa)
     return hs[n] if getattr(v, "kind", "clip") == "siglip" else hs[n][:, 1:]
 
 
@@ -210,7 +213,7 @@ def _rot_half(x):
     return torch.cat([-x[..., h:], x[..., :h]], dim=-1)
 
 
-def decoder_layer(sd: SD, l, i: int, h: torch.Tensor, cos, sin, dtype) -> torch.Tensor:
+def decoder_layer(sd: SD, l, i: int, h: torch.Tensor, cos, sin, dtype, sdpa: bool = False) -> torch.Tensor:
     p = f"model.layers.{i}."
     S = h.shape[0]
     d = l.head_dim
@@ -229,9 +232,13 @@ def decoder_layer(sd: SD, l, i: int, h: torch.Tensor, cos, sin, dtype) -> torch.
     g = l.heads // l.kv_heads
     k = k.repeat_interleave(g, dim=0)
     v = v.repeat_interleave(g, dim=0)
-    s = (q @ k.transpose(-1, -2)).float() * d ** -0.5
-    s = s.masked_fill(torch.ones(S, S, dtype=torch.bool).triu(1), float("-inf"))
-    o = (torch.softmax(s, dim=-1).to(dtype) @ v).transpose(0, 1).reshape(S, l.heads * d)
+    if sdpa:
+        o = F.scaled_dot_product_attention(q[None], k[None], v[None], is_causal=True, scale=d ** -0.5)[0]
+        o = o.transpose(0, 1).reshape(S, l.heads * d)
+    else:
+        s = (q @ k.transpose(-1, -2)).float() * d ** -0.5
+        s = s.masked_fill(torch.ones(S, S, dtype=torch.bool).triu(1), float("-inf"))
+        o = (torch.softmax(s, dim=-1).to(dtype) @ v).transpose(0, 1).reshape(S, l.heads * d)
     h = r + F.linear(o, _w(sd, p + "self_attn.o_proj.weight", dtype))
     r = h
     y = rmsnorm(h, _w(sd, p + "post_attention_layernorm.weight", dtype), l.eps)

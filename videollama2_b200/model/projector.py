@@ -30,6 +30,7 @@ class STCConnector:
     """Temporal Convolutional Vision-Language Connector (projector.py:133-215)."""
 
     padding = 1
+    s1_dtype = torch.bfloat16      # storage type of forward_s1's output (what the frame-parallel all-gather moves)
 
     def __init__(self, config, downsample=(2, 2, 2), depth=4, mlp_depth=2):
         if tuple(downsample) != (2, 2, 2):
@@ -47,10 +48,15 @@ class STCConnector:
         self.w: Dict[str, torch.Tensor] = {}
         self.is_loaded = False
         self._graphed = None
+        self._graphed_s1 = None
+        self._graphed_tail = None
 
     def enable_cuda_graphs(self, on: bool = True):
         from ..graphs import GraphedStage
         self._graphed = GraphedStage(lambda x: self._forward_one(x, None)) if on else None
+        # the two halves the frame-parallel path runs on either side of its all-gather (parallel.FrameParallel)
+        self._graphed_s1 = GraphedStage(self.run_s1) if on else None
+        self._graphed_tail = GraphedStage(lambda a: self.run_readout(self.run_s2(self.run_sampler(a)), None)) if on else None
         return self
 
     # ---- weights -------------------------------------------------------------------------------------------
@@ -137,6 +143,27 @@ class STCConnector:
     def _forward_one(self, x: torch.Tensor, out: Optional[torch.Tensor]) -> torch.Tensor:
         """x: [T, H, W, Cin] (one video) -> [T'*H'*W', C]; the last GEMM can write straight into `out`."""
         return self.run_readout(self.run_s2(self.run_sampler(self.run_s1(x))), out)
+
+    def forward_s1(self, x: torch.Tensor) -> torch.Tensor:
+        """[f,H,W,Cin] -> [f,H,W,C]: the per-frame half of the connector (first RegStage) on any subset of frames."""
+        if not self.is_loaded:
+            raise RuntimeError("STCConnector: weights not loaded")
+        x = x.to(torch.bfloat16).contiguous()
+        g = getattr(self, "_graphed_s1", None)
+        return g(x) if g is not None else self.run_s1(x)
+
+    def forward_from_s1(self, a: torch.Tensor) -> torch.Tensor:
+        """[b,T,H,W,C] (first-RegStage output of every frame) -> [b, l', D]: Conv3d sampler + s2 + readout."""
+        b = a.size(0)
+        out = torch.empty((b, self.num_output_tokens(a.size(1), a.size(2)), self.output_hidden_size), device=a.device,
+                          dtype=torch.bfloat16)
+        g = getattr(self, "_graphed_tail", None)
+        for i in range(b):
+            if g is not None:
+                out[i].copy_(g(a[i].contiguous()))
+            else:
+                self.run_readout(self.run_s2(self.run_sampler(a[i].contiguous())), out[i])
+        return out
 
     def num_output_tokens(self, t: int, hw: int) -> int:
         p = self.padding

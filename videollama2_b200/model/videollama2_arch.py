@@ -100,6 +100,27 @@ class Videollama2MetaForCausalLM:
             return out
         return self._encode_images_or_videos(images)
 
+    # ---- frame-parallel vision stage (videollama2_b200/parallel.py) ---------------------------------------------
+    def enable_frame_parallel(self, group=None, shard_s1: bool = True, llm_rank: int = 0):
+        """Shard the per-frame part of `encode_images_or_videos` (ViT + first RegStage) over the ranks of `group` and
+        all-gather before the connector's Conv3d.  Every rank must then call encode / forward / generate with identical
+        inputs; ranks other than `llm_rank` return None from forward / generate once the collective is done.
+        `group=None` with an initialised default process group uses WORLD; call with `group=False` to switch it off."""
+        from .. import parallel
+        if group is False:
+            self._frame_parallel = None
+        else:
+            self._frame_parallel = parallel.FrameParallel(group, shard_s1=shard_s1, llm_rank=llm_rank)
+        return self
+
+    def _vision_only_rank(self, images) -> bool:
+        """True on a frame-parallel rank that does not run the decoder: it takes part in the vision collective and stops."""
+        fp = getattr(self, "_frame_parallel", None)
+        if fp is None or fp.world == 1 or fp.rank == fp.llm_rank or images is None or self.get_vision_tower() is None:
+            return False
+        self.encode_images_or_videos(images)
+        return True
+
     # arch.py:114-134
     def _encode_images_or_videos(self, images):
         num_frames = getattr(self.config, "num_frames", NUM_FRAMES)
@@ -112,6 +133,9 @@ class Videollama2MetaForCausalLM:
         assert len(data_batch.size()) == 5
         b, t = data_batch.size(0), data_batch.size(1)
         frames = data_batch.reshape(b * t, *data_batch.shape[2:])
+        fp = getattr(self, "_frame_parallel", None)
+        if fp is not None and fp.world > 1 and "tc_connector" in self.config.mm_projector_type:
+            return fp.encode(self, frames, b, t)
         frames_features = self.get_model().get_vision_tower()(frames)
         frames_features = frames_features.view(b, t, *frames_features.shape[1:])
         return self.temporal_aggregator(frames_features)

@@ -82,6 +82,8 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
             raise NotImplementedError("output_attentions is not supported by the fused attention kernel")
         if past_key_values is not None:
             raise NotImplementedError("forward() with past_key_values is not supported; use generate()")
+        if inputs_embeds is None and input_ids is not None and input_ids.shape[1] != 1 and self._vision_only_rank(images):
+            return None
         new_len = None
         if inputs_embeds is None:
             input_ids, attention_mask, past_key_values, inputs_embeds, labels = \
@@ -134,6 +136,8 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         eos = kwargs.get("eos_token_id", getattr(self.config, "eos_token_id", None))
         eos_ids = set(eos if isinstance(eos, (list, tuple)) else [eos]) if eos is not None else set()
         stopping = kwargs.get("stopping_criteria") or []
+        if self._vision_only_rank(images):
+            return None
         if images is not None:
             _, attention_mask, _, inputs_embeds, _ = self.prepare_inputs_labels_for_multimodal(
                 input_ids=inputs, attention_mask=attention_mask, past_key_values=None, labels=None, images=images)

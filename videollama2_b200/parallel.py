@@ -63,6 +63,47 @@ def encode_frames_sharded(tower, frames: torch.Tensor, group=None) -> torch.Tens
     return all_gather_frames(local, frames.shape[0], group)
 
 
+class FrameParallel:
+    """The frame-parallel vision stage as a PRODUCT path (north_star: "per-frame ViT encode shards across the GPUs of one
+    box with an all-gather of visual tokens before the connector, the LLM running on rank 0").
+
+    Every rank of `group` calls `model.encode_images_or_videos(images)` / `generate(...)` with IDENTICAL inputs (SPMD).
+    Rank r encodes frames [a_r, b_r) of the flattened (video, frame) batch with the ViT and - `shard_s1` - the
+    connector's first RegStage, which is per-frame too (projector.py:203-205; SE pools per frame), i.e. everything in front
+    of the first op that mixes time (the Conv3d, projector.py:208).  ONE all-gather ([F, 576, 4096] bf16 with s1 sharded,
+    [F, 576, 1024] without) then puts the full tensor on every rank; sampler + s2 + readout run on what was gathered.
+    Frame sharding never changes a GEMM's K-order, so the result is bit-identical to the single-GPU path
+    (tests/test_multigpu_gpu.py).  `llm_rank`: the rank whose generate() / forward() goes on to the decoder; the other
+    ranks return None right after the collective."""
+
+    def __init__(self, group=None, shard_s1: bool = True, llm_rank: int = 0):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.shard_s1 = shard_s1
+        self.llm_rank = llm_rank
+
+    def encode(self, model, frames: torch.Tensor, b: int, t: int) -> torch.Tensor:
+        """frames [(b t),3,H,W] identical on every rank -> connector output [b, L, D] on every rank."""
+        tower = model.get_model().get_vision_tower()
+        proj = model.get_model().mm_projector
+        F = frames.shape[0]
+        a, e = frame_shard(F, self.rank, self.world)
+        n, C = tower.num_patches, tower.hidden_size
+        local = tower(frames[a:e]) if e > a else torch.empty((0, n, C), dtype=frames.dtype, device=frames.device)
+        if self.shard_s1 and hasattr(proj, "forward_from_s1"):
+            hw = int(n ** 0.5)
+            H = proj.hidden_size
+            if e > a:
+                s1 = proj.forward_s1(local.view(e - a, hw, hw, C)).reshape(e - a, n, H)
+            else:
+                s1 = torch.empty((0, n, H), dtype=proj.s1_dtype, device=frames.device)   # more ranks than frames
+            full = all_gather_frames(s1, F, self.group)
+            return proj.forward_from_s1(full.view(b, t, hw, hw, H)).to(frames.dtype)
+        feats = all_gather_frames(local, F, self.group)
+        return model.temporal_aggregator(feats.view(b, t, n, C))
+
+
 class FusedFrameGather:
     """Frame-parallel ViT whose LAST GEMM writes its output tiles straight into every rank's gather buffer.
 
