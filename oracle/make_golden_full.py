@@ -168,7 +168,7 @@ def main():
             keys = list(gs.keys())
             top = torch.topk(g["logits_last"], 5)
             fx = {
-                "config": name, "rows": rows, "dec_tap_layers": dec_tap_layers(cfg.llm.layers),
+                "config": name, "rows": rows, "dec_tap_layers": [int(i) for i in dec_tap_layers(cfg.llm.layers)],
                 "g32": {**gs, "logits_last": g["logits_last"]},
                 "hbf16_logits_last": h["logits_last"],
                 "noise_slice": {k: rel(hs[k], gs[k]) for k in keys},
@@ -178,7 +178,7 @@ def main():
                 "argmax_g32": int(top.indices[0]), "argmax_hbf16": int(h["logits_last"].argmax()),
                 "top5_g32": top.indices.tolist(), "top2_margin_g32": float(top.values[0] - top.values[1]),
                 "logit_noise_absmax": float((h["logits_last"] - g["logits_last"]).abs().max()),
-                "torch": torch.__version__,
+                "torch": str(torch.__version__),
             }
             torch.save(fx, os.path.join(OUT, f"full_{name}.pt"))
             print(name, "noise_full", {k: round(v, 4) for k, v in fx["noise_full"].items()}, "argmax g32/hbf16",

@@ -82,3 +82,24 @@ def test_preset_state_dict_names_match_oracle_contract():
         a = {n: tuple(s) for n, s, _ in synth.model_specs(cfg)}
         b = {n: tuple(s) for n, s, _ in P.state_dict_specs(engine_config(cfg))}
         assert a == b
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_fulldepth_fixtures_load_and_are_consistent(name):
+    """tests/golden/full_cfg*.pt (oracle/make_golden_full.py) load with torch's default safe unpickler (the GPU box has
+    no way to regenerate them) and are internally consistent: rows are what make_golden_full.tap_rows yields, the
+    reference's own bf16 run agrees with its fp32 run on the arg-max token, noise floors sit where BASELINE.md §4 measured
+    them (1-2e-2)."""
+    import os
+    from oracle import make_golden_full, synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"full_{name}.pt")
+    fx = torch.load(path, map_location="cpu")
+    cfg = synth.CONFIGS[name]
+    rows = make_golden_full.tap_rows(cfg)
+    assert all(torch.equal(rows[k], fx["rows"][k]) for k in rows)
+    assert fx["g32"]["logits_last"].shape == (cfg.llm.vocab,) and fx["g32"]["vit"].shape == (16, cfg.vision.hidden)
+    assert fx["g32"]["mm"].shape == (16, cfg.llm.hidden)
+    assert fx["argmax_g32"] == fx["argmax_hbf16"] == int(fx["g32"]["logits_last"].argmax())
+    assert fx["top2_margin_g32"] > 2 * fx["logit_noise_absmax"]
+    assert all(5e-3 < v < 3e-2 for v in fx["noise_full"].values()), fx["noise_full"]
+    assert sorted(fx["dec_tap_layers"]) == sorted(set(make_golden_full.dec_tap_layers(cfg.llm.layers)))
