@@ -108,6 +108,18 @@ typedef struct vl2_gemm_args {
    * the 7B shapes it pays only for K = 14336 and it makes rounding depend on M; see DESIGN.md. */
   void* splitk_ws;
   int64_t splitk_ws_bytes;
+  /* LayerNorm folded into the GEMMs around it (HF:clip/modeling_clip.py:354-385 layer_norm1 / layer_norm2 in front of
+   * q/k/v_proj and fc1): with W' = W * gamma (columns), colsum[n] = sum_k W'[n,k] and bias' = bias + W beta,
+   *     LN(x; gamma, beta) W^T + bias = rstd * (x W'^T - mu * colsum) + bias'.
+   *   ln_sum_in     fp32 [M, rms_nparts]: partial row sums of THIS GEMM's A rows; together with rms_sumsq_in (the partial
+   *                 sums of squares, REQUIRED with it) they give mu = sum/K and rstd = rsqrt(max(E[x^2] - mu^2, 0) + rms_eps);
+   *                 the accumulator becomes (acc - mu * ln_colsum[n]) * rstd before bias/activation (NULL = off)
+   *   ln_colsum     fp32 [N] (REQUIRED with ln_sum_in)
+   *   rowsum_out    fp32 [M, N/32]: like sumsq_out, the per-32-column sums of the bf16-rounded outputs (NULL = off; same
+   *                 restrictions as sumsq_out) */
+  const float* ln_sum_in;
+  const float* ln_colsum;
+  float* rowsum_out;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 /* Debug aid: with args->reserved2 == 777 CTA 0 records clock64() at its tile boundaries: out[0] = tiles traced (<= 7), and
@@ -192,6 +204,10 @@ int vl2_layernorm(const void* x, const void* gamma, const void* beta, const void
 int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t rows, int C, float eps, void* stream);
 /* out[r] = sum_c x[r,c]^2 (fp32): seeds the folded-RMSNorm statistics for the first decoder layer. */
 int vl2_row_sumsq(const void* x, float* out, int64_t rows, int C, void* stream);
+/* Row sums AND row sums of squares (fp32 [rows] each): the statistics of a LayerNorm folded into the consuming GEMM
+ * (vl2_gemm_args.ln_sum_in / rms_sumsq_in) when the rows were not produced by a GEMM epilogue, e.g. the output of
+ * pre_layrnorm in front of CLIP's first encoder layer (HF:clip/modeling_clip.py:354-385). */
+int vl2_row_stats(const void* x, float* sum_out, float* sumsq_out, int64_t rows, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * CLIP patch embedding front/back ends (HF:clip/modeling_clip.py:202-218).

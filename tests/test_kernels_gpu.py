@@ -450,3 +450,34 @@ def test_gemm_folded_rmsnorm(cuda, bn):
     y = ops.gemm(out, w2, rms_in=parts, rms_eps=1e-5, bn=bn)
     of = out.float()
     assert relerr(y, (of * torch.rsqrt(of.pow(2).mean(-1, keepdim=True) + 1e-5)) @ w2.float().t()) < 8e-3
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(1154, 3072, 1024, 0), (9232, 4096, 1024, 0), (300, 288, 288, 0), (577, 256, 128, 64),
+                                      (1154, 1024, 1024, 1128), (260, 2304, 1152, 224)])
+@pytest.mark.parametrize("stats_from", ["row_kernel", "gemm_epilogue"])
+def test_gemm_folded_layernorm(cuda, M, N, K, bn, stats_from):
+    """LayerNorm folded into the consuming GEMM (vl2_gemm_args.ln_sum_in / ln_colsum): rstd * (x W'^T - mu * colsum) + b'
+    against layer_norm + linear in fp32; the row statistics come from vl2_row_stats or from the producing GEMM's epilogue
+    (rowsum_out / sumsq_out), which must equal the sums of the bf16 outputs."""
+    from videollama2_b200 import ops
+    g = (rnd((K,), cuda, 0.1, seed=71) + 1.0).float()
+    beta = rnd((K,), cuda, 0.2, seed=72).float()
+    w = rnd((N, K), cuda, K ** -0.5, seed=73)
+    b = rnd((N,), cuda, 0.1, seed=74).float()
+    if stats_from == "row_kernel":
+        x = rnd((M, K), cuda, 1.5, seed=75) + 0.75                   # mean well away from zero: mu * colsum matters
+        stats = ops.row_stats(x)
+    else:
+        if K % 32:
+            pytest.skip("epilogue statistics need N % 32 == 0")
+        a0 = rnd((M, 64), cuda, seed=76)
+        w0 = rnd((K, 64), cuda, 0.2, seed=77)
+        res = rnd((M, K), cuda, 1.0, seed=78) + 0.5
+        stats = (torch.empty((M, K // 32), device=cuda, dtype=torch.float32), torch.empty((M, K // 32), device=cuda, dtype=torch.float32))
+        x = ops.gemm(a0, w0, residual=res, rowsum_out=stats[0], sumsq_out=stats[1])
+        assert relerr(stats[0].sum(-1), x.float().sum(-1)) < 1e-5 and relerr(stats[1].sum(-1), x.float().pow(2).sum(-1)) < 1e-5
+    wf = (w.float() * g[None, :]).to(torch.bfloat16)
+    out = ops.gemm(x, wf, bias=(b + w.float() @ beta).contiguous(), ln_in=stats, ln_colsum=wf.float().sum(1).contiguous(),
+                   rms_eps=1e-5, bn=bn)
+    ref = torch.nn.functional.layer_norm(x.float(), (K,), g, beta, 1e-5) @ w.float().t() + b
+    assert relerr(out, ref) < 8e-3

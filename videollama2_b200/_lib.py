@@ -13,7 +13,7 @@ SYMBOLS = [
     "vl2_version", "vl2_last_error", "vl2_launch_count",
     "vl2_gemm_bf16", "vl2_gemm_skinny", "vl2_attention", "vl2_attention_decode", "vl2_debug_attn_trace", "vl2_debug_gemm_trace", "vl2_gemm_plan",
     "vl2_decode_rope_append", "vl2_attention_decode_dyn", "vl2_gemv_bf16", "vl2_attention_decode_workspace", "vl2_set_pdl", "vl2_l2_prefetch", "vl2_preprocess_frames", "vl2_preprocess_workspace",
-    "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq",
+    "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq", "vl2_row_stats",
     "vl2_patch_im2col", "vl2_clip_embed_finish",
     "vl2_dwconv3x3_ln_silu", "vl2_se_scale", "vl2_conv3d_im2col",
     "vl2_rope_inplace", "vl2_embed_splice",
@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("rms_sumsq_in", C.c_void_p), ("sumsq_out", C.c_void_p), ("rms_nparts", C.c_int32), ("reserved3", C.c_int32),
         ("rms_inv_dim", C.c_float), ("rms_eps", C.c_float),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
+        ("ln_sum_in", C.c_void_p), ("ln_colsum", C.c_void_p), ("rowsum_out", C.c_void_p),
     ]
 
 
@@ -86,6 +87,7 @@ def load() -> C.CDLL:
         "vl2_layernorm": [vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
         "vl2_rmsnorm": [vp, vp, vp, i64, i32, f32, vp],
         "vl2_row_sumsq": [vp, vp, i64, i32, vp],
+        "vl2_row_stats": [vp, vp, vp, i64, i32, vp],
         "vl2_patch_im2col": [vp, vp, i32, i32, i32, i32, i32, vp],
         "vl2_clip_embed_finish": [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp],
         "vl2_dwconv3x3_ln_silu": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],

@@ -35,7 +35,7 @@ struct GemmCfg {
   static constexpr int kStageBytesB = kRowsB * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
-  static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias staging*/ + 256 /*barriers*/;
+  static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias (+ colsum) staging*/ + 256 /*barriers*/;
   static constexpr int kMaxStages = (227 * 1024 - kExtraBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kAccStride = BN > 128 ? 256 : (BN > 64 ? 128 : 64);  // TMEM columns between accumulator stages
@@ -58,8 +58,11 @@ struct GemmParams {
   __nv_bfloat16* bcast[8];
   __nv_bfloat16* mc;
   int n_bcast;
-  // folded RMSNorm (see vl2.h)
+  // folded RMSNorm / LayerNorm (see vl2.h)
   const float* rms_sumsq_in;
+  const float* ln_sum_in;
+  const float* ln_colsum;
+  float* rowsum_out;
   float* sumsq_out;
   int rms_nparts;
   float rms_inv_dim, rms_eps;
@@ -300,23 +303,40 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.M;
-      const uint32_t sb = smem_u32(sbias + as * 256);
+      // bias staging is double buffered by accumulator stage; with a folded LayerNorm the second buffer holds the column
+      // sums instead, so the pair is single buffered and one more barrier keeps this tile's writes behind the previous
+      // tile's reads
+      const bool ln = p.ln_sum_in != nullptr;
+      const int bsel = ln ? 0 : as;
+      const uint32_t sb = smem_u32(sbias + bsel * 256);
+      if (ln) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (p.bias != nullptr) {  // stage this tile's bias slice once (broadcast LDS later instead of exposed LDG latency)
-        for (int i = etid; i < BN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        for (int i = etid; i < BN; i += kEpiThreads) sbias[bsel * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      }
+      if (ln) {
+        for (int i = etid; i < BN; i += kEpiThreads) sbias[256 + i] = (n0 + i < p.N) ? __ldg(p.ln_colsum + n0 + i) : 0.f;
       }
       float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.f;
+      float mu = 0.f;
       if (p.rms_sumsq_in != nullptr && row_ok) {
         // sum the producer's per-32-column partials in a fixed order (deterministic: no atomics anywhere)
-        const float* pp = p.rms_sumsq_in + (int64_t)row * p.rms_nparts;
-        float q = 0.f;
-        int i = 0;
         const int nvec = (p.rms_nparts % 4 == 0) ? p.rms_nparts : 0;   // rows are 16-byte aligned only then
-        for (; i + 4 <= nvec; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(pp + i);
-          q += (t4.x + t4.y) + (t4.z + t4.w);
+        auto sum_parts = [&](const float* pp) {
+          float q = 0.f;
+          int i = 0;
+          for (; i + 4 <= nvec; i += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(pp + i);
+            q += (t4.x + t4.y) + (t4.z + t4.w);
+          }
+          for (; i < p.rms_nparts; ++i) q += pp[i];
+          return q;
+        };
+        float q = sum_parts(p.rms_sumsq_in + (int64_t)row * p.rms_nparts) * p.rms_inv_dim;   // E[x^2]
+        if (ln) {
+          mu = sum_parts(p.ln_sum_in + (int64_t)row * p.rms_nparts) * p.rms_inv_dim;
+          q = fmaxf(q - mu * mu, 0.f);                                                        // variance
         }
-        for (; i < p.rms_nparts; ++i) q += pp[i];
-        rs *= rsqrtf(q * p.rms_inv_dim + p.rms_eps);
+        rs *= rsqrtf(q + p.rms_eps);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       mbar_wait(&tmem_full[as], aphase);
@@ -348,7 +368,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (col0 >= p.N) break;                       // warp-uniform
         const int span = min(min(64, BN - c0), p.N - col0);   // 8..64 valid accumulator columns (multiple of 8)
         uint32_t v[32];
-        float ssq = 0.f;                              // sum of squares of this thread's (row's) outputs in the span
+        float ssq = 0.f, ssum = 0.f;                  // sum of squares / sum of this thread's (row's) outputs in the span
         tmem_ld_32x32(taddr + c0, v);
         // residual block -> smem (coalesced: 8 lanes x 16 B per row)
         if (res != nullptr) {
@@ -378,6 +398,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + g * 128));
                 x[4 * g] += t4.x; x[4 * g + 1] += t4.y; x[4 * g + 2] += t4.z; x[4 * g + 3] += t4.w;
               }
+            }
+          }
+          if (ln) {   // folded LayerNorm: remove the row mean's contribution mu * sum_k W'[n,k] before the 1/std scale
+            const uint32_t sc = smem_u32(sbias + 256);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 cq = lds_f4(sc + (c0 + hf * 32 + g * 4) * 4);
+              x[g * 4 + 0] = fmaf(-mu, cq.x, x[g * 4 + 0]); x[g * 4 + 1] = fmaf(-mu, cq.y, x[g * 4 + 1]);
+              x[g * 4 + 2] = fmaf(-mu, cq.z, x[g * 4 + 2]); x[g * 4 + 3] = fmaf(-mu, cq.w, x[g * 4 + 3]);
             }
           }
 #pragma unroll
@@ -447,6 +476,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const float a0 = bf16_lo(pk.x), a1 = bf16_hi(pk.x), a2 = bf16_lo(pk.y), a3 = bf16_hi(pk.y);
                 const float a4 = bf16_lo(pk.z), a5 = bf16_hi(pk.z), a6 = bf16_lo(pk.w), a7 = bf16_hi(pk.w);
                 ssq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+                if (p.rowsum_out != nullptr) ssum += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
               }
             }
           }
@@ -456,6 +486,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           float* slot = p.sumsq_out + (int64_t)row * (p.N >> 5) + (col0 >> 5);
           slot[0] = ssq;
           if (span > 32) slot[1] = 0.f;
+          if (p.rowsum_out != nullptr) {
+            float* slot2 = p.rowsum_out + (int64_t)row * (p.N >> 5) + (col0 >> 5);
+            slot2[0] = ssum;
+            if (span > 32) slot2[1] = 0.f;
+          }
         }
         if (!p.out_f32) {
           __syncwarp();
@@ -525,6 +560,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
   p.ldc = a->ldc; p.ldr = a->ldr; p.M = a->M; p.N = a->N; p.K = a->K; p.act = a->act; p.out_f32 = a->out_f32;
   p.rms_sumsq_in = a->rms_sumsq_in; p.sumsq_out = a->sumsq_out; p.rms_nparts = a->rms_nparts;
+  p.ln_sum_in = a->ln_sum_in; p.ln_colsum = a->ln_colsum; p.rowsum_out = a->rowsum_out;
   p.rms_inv_dim = a->rms_inv_dim; p.rms_eps = a->rms_eps;
   p.trace = (a->reserved2 == 777) ? 1 : 0;
   p.n_bcast = a->n_bcast;
@@ -698,6 +734,10 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
   VL2_REQUIRE(a->sumsq_out == nullptr || (!a->out_f32 && a->act != VL2_ACT_SWIGLU && a->N % 32 == 0), VL2_E_UNSUPPORTED,
               "vl2_gemm_bf16: sumsq_out supports bf16, non-SwiGLU outputs with N %% 32 == 0 only");
   VL2_REQUIRE(a->rms_sumsq_in == nullptr || a->rms_nparts > 0, VL2_E_BADSHAPE, "vl2_gemm_bf16: rms_nparts must be positive");
+  VL2_REQUIRE(a->ln_sum_in == nullptr || (a->rms_sumsq_in != nullptr && a->ln_colsum != nullptr), VL2_E_BADSHAPE,
+              "vl2_gemm_bf16: ln_sum_in needs rms_sumsq_in (sums of squares) and ln_colsum");
+  VL2_REQUIRE(a->rowsum_out == nullptr || a->sumsq_out != nullptr, VL2_E_UNSUPPORTED,
+              "vl2_gemm_bf16: rowsum_out is written together with sumsq_out");
   VL2_REQUIRE(a->n_bcast >= 0 && a->n_bcast <= 8, VL2_E_BADSHAPE, "vl2_gemm_bf16: n_bcast must be in [0,8]");
   if (a->n_bcast > 0 || a->mc_out != nullptr) {
     VL2_REQUIRE(!a->out_f32 && a->act != VL2_ACT_SWIGLU, VL2_E_UNSUPPORTED,

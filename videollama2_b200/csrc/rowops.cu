@@ -198,23 +198,28 @@ rmsnorm_stream_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
 }
 
 __global__ void __launch_bounds__(256)
-row_sumsq_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t rows, int C) {
+row_sumsq_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, float* __restrict__ sum_out, int64_t rows,
+                 int C) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
-  float q = 0.f;
+  float q = 0.f, s = 0.f;
 #pragma unroll 4
   for (int vi = lane; vi < C / 8; vi += 32) {
     float f[8];
     unpack8(xr[vi], f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q = fmaf(f[j], f[j], q);
+    for (int j = 0; j < 8; ++j) { q = fmaf(f[j], f[j], q); s += f[j]; }
   }
   q = warp_sum(q);
-  if (lane == 0) out[row] = q;
+  s = warp_sum(s);
+  if (lane == 0) {
+    out[row] = q;
+    if (sum_out != nullptr) sum_out[row] = s;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -688,7 +693,18 @@ extern "C" int vl2_rmsnorm(const void* x, const void* gamma, void* y, int64_t ro
 extern "C" int vl2_row_sumsq(const void* x, float* out, int64_t rows, int C, void* stream) {
   VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, VL2_E_BADSHAPE, "vl2_row_sumsq: rows=%lld C=%d unsupported", (long long)rows, C);
   VL2_REQUIRE(aligned16(x), VL2_E_BADALIGN, "vl2_row_sumsq: 16-byte alignment");
-  launch_kernel(row_sumsq_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, out, rows, C);
+  launch_kernel(row_sumsq_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, out,
+                (float*)nullptr, rows, C);
+  VL2_CHECK_LAUNCH("row_sumsq_kernel");
+  return VL2_OK;
+}
+
+extern "C" int vl2_row_stats(const void* x, float* sum_out, float* sumsq_out, int64_t rows, int C, void* stream) {
+  VL2_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && sum_out != nullptr && sumsq_out != nullptr, VL2_E_BADSHAPE,
+              "vl2_row_stats: rows=%lld C=%d unsupported", (long long)rows, C);
+  VL2_REQUIRE(aligned16(x), VL2_E_BADALIGN, "vl2_row_stats: 16-byte alignment");
+  launch_kernel(row_sumsq_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x,
+                sumsq_out, sum_out, rows, C);
   VL2_CHECK_LAUNCH("row_sumsq_kernel");
   return VL2_OK;
 }

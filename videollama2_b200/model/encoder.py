@@ -6,6 +6,7 @@ Only the layers that feed `hidden_states[select_layer]` are executed (select_lay
 the 24th layer and post_layernorm and throws the result away)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -96,18 +97,26 @@ class CLIPVisionTower:
         patch = ops.gemm(A, self.w["patch"])
         x = ops.clip_embed_finish(patch, self.w["cls"], self.w["pos"], self.w["pre_g"], self.w["pre_b"], Fn,
                                   c.layer_norm_eps)
-        x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr)
+        x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr, None)
         return x.view(Fn, S, C)
 
     _ACT = ops.ACT_QUICK_GELU
 
-    def _encoder(self, x: torch.Tensor, Fn: int, S: int, last_out=None, bcast_ptrs=None, mc_ptr: int = 0) -> torch.Tensor:
+    # LayerNorms folded into the GEMMs that consume them (VL2_VIT_FOLD_LN=0 keeps the stand-alone LayerNorm kernels):
+    # gamma goes into the weight columns, beta into the bias, and the row statistics (sum, sum of squares) come out of the
+    # epilogue of the GEMM that produced the residual stream - 2 launches and 2 round trips of the stream fewer per layer
+    fold_layernorm = os.environ.get("VL2_VIT_FOLD_LN", "1") != "0"
+
+    def _encoder(self, x: torch.Tensor, Fn: int, S: int, last_out=None, bcast_ptrs=None, mc_ptr: int = 0,
+                 stats=None) -> torch.Tensor:
         """Pre-LN transformer layers shared by both towers: LN -> fused QKV GEMM -> attention -> out_proj(+residual)
-        -> LN -> fc1(+activation) -> fc2(+residual)."""
+        -> LN -> fc1(+activation) -> fc2(+residual).  `stats` = (row sums, row sums of squares) of x for the folded form."""
         c = self._config
         C = c.hidden_size
         H = c.num_attention_heads
         D = C // H
+        if self.fold_layernorm and self.layers and C % 32 == 0 and "wqkv_f" in self.layers[0]:
+            return self._encoder_folded(x, Fn, S, last_out, bcast_ptrs, mc_ptr, stats)
         for li, L in enumerate(self.layers):
             last = li == len(self.layers) - 1
             y = ops.layernorm(x, L["ln1_g"], L["ln1_b"], c.layer_norm_eps)
@@ -123,13 +132,59 @@ class CLIPVisionTower:
                 x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x)
         return x
 
+    def _encoder_folded(self, x, Fn, S, last_out, bcast_ptrs, mc_ptr, stats):
+        c = self._config
+        C = c.hidden_size
+        H = c.num_attention_heads
+        D = C // H
+        eps = c.layer_norm_eps
+        M = x.shape[0]
+        if stats is None:
+            stats = ops.row_stats(x)
+        new_stats = lambda: (torch.empty((M, C // 32), device=x.device, dtype=torch.float32),
+                             torch.empty((M, C // 32), device=x.device, dtype=torch.float32))
+        for li, L in enumerate(self.layers):
+            last = li == len(self.layers) - 1
+            qkv = ops.gemm(x, L["wqkv_f"], bias=L["bqkv_f"], ln_in=stats, ln_colsum=L["cqkv"], rms_eps=eps)
+            o = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B=Fn, S=S, Hq=H, Hkv=H, D=D, causal=False,
+                              scale=D ** -0.5)
+            mid = new_stats()
+            x = ops.gemm(o, L["wo"], bias=L["bo"], residual=x, rowsum_out=mid[0], sumsq_out=mid[1])
+            h = ops.gemm(x, L["w1_f"], bias=L["b1_f"], act=self._ACT, ln_in=mid, ln_colsum=L["c1"], rms_eps=eps)
+            if last:
+                kw = {}
+                if last_out is not None or bcast_ptrs or mc_ptr:
+                    kw = dict(out=last_out, bcast_ptrs=bcast_ptrs, mc_ptr=mc_ptr)
+                x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x, **kw)
+            else:
+                stats = new_stats()
+                x = ops.gemm(h, L["w2"], bias=L["b2"], residual=x, rowsum_out=stats[0], sumsq_out=stats[1])
+        return x
+
     def _load_layers(self, sd, prefix, dev):
         bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
+
+        def fold(w, b, g, beta):
+            """LN(x; g, beta) w^T + b  ->  (w * g as bf16, its fp32 row sums, b + w beta)."""
+            wf = w.to(device=dev, dtype=torch.float32)
+            wg = (wf * g.to(device=dev, dtype=torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+            return wg, wg.float().sum(1).contiguous(), (b.to(device=dev, dtype=torch.float32)
+                                                        + wf @ beta.to(device=dev, dtype=torch.float32)).contiguous()
+
         self.layers = []
         for i in range(self.n_used_layers):
             p = f"{prefix}encoder.layers.{i}."
+            wqkv = torch.cat([sd[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0)
+            bqkv = torch.cat([sd[p + f"self_attn.{n}.bias"] for n in ("q_proj", "k_proj", "v_proj")], 0)
+            folded = {}
+            if self.fold_layernorm:
+                wq, cq, bq = fold(wqkv, bqkv, sd[p + "layer_norm1.weight"], sd[p + "layer_norm1.bias"])
+                w1, c1, b1 = fold(sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"], sd[p + "layer_norm2.weight"],
+                                  sd[p + "layer_norm2.bias"])
+                folded = {"wqkv_f": wq, "cqkv": cq, "bqkv_f": bq, "w1_f": w1, "c1": c1, "b1_f": b1}
             self.layers.append({
+                **folded,
                 "ln1_g": bf(sd[p + "layer_norm1.weight"]), "ln1_b": bf(sd[p + "layer_norm1.bias"]),
                 "ln2_g": bf(sd[p + "layer_norm2.weight"]), "ln2_b": bf(sd[p + "layer_norm2.bias"]),
                 "wqkv": bf(torch.cat([sd[p + f"self_attn.{n}.weight"] for n in ("q_proj", "k_proj", "v_proj")], 0)),
@@ -252,8 +307,15 @@ class SiglipVisionTower(CLIPVisionTower):
             pos = self.w["pos"].repeat(Fn, 1).contiguous()
             self._pos_rows[Fn] = pos
         A = ops.patch_im2col(images.contiguous(), c.patch_size, self.kpad)
-        x = ops.gemm(A, self.w["patch"], bias=self.w["patch_b"], residual=pos)
-        x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr)
+        stats = None
+        if self.fold_layernorm and self.layers and c.hidden_size % 32 == 0:
+            M = A.shape[0]
+            stats = (torch.empty((M, c.hidden_size // 32), device=A.device, dtype=torch.float32),
+                     torch.empty((M, c.hidden_size // 32), device=A.device, dtype=torch.float32))
+            x = ops.gemm(A, self.w["patch"], bias=self.w["patch_b"], residual=pos, rowsum_out=stats[0], sumsq_out=stats[1])
+        else:
+            x = ops.gemm(A, self.w["patch"], bias=self.w["patch_b"], residual=pos)
+        x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr, stats)
         return x.view(Fn, S, c.hidden_size)
 
     def feature_select(self, hidden: torch.Tensor) -> torch.Tensor:

@@ -13,7 +13,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SI
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "l2_prefetch", "layernorm", "rmsnorm", "row_sumsq", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "l2_prefetch", "layernorm", "rmsnorm", "row_sumsq", "row_stats", "patch_im2col", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
@@ -59,14 +59,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
          bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
          rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None, trace: bool = False,
-         splitk=True) -> torch.Tensor:
+         splitk=True, ln_in=None, ln_colsum: Optional[torch.Tensor] = None,
+         rowsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
     `bn` forces the tile width (tests); 0 = library heuristic.
     `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
     (epilogue-fused all-gather over NVLink); `mc_ptr`: NVSwitch multicast address used instead when non-zero.
     `rms_in` (fp32 [M, parts] partial row sums of squares of `a`) scales row m by rsqrt(sum(rms_in[m])/K + rms_eps):
     RMSNorm folded into the GEMM (gamma must already be folded into w); `sumsq_out` (fp32 [M, N/32]) receives the
-    per-32-column sums of squares of the bf16 outputs (no atomics: bit-reproducible)."""
+    per-32-column sums of squares of the bf16 outputs (no atomics: bit-reproducible).
+    `ln_in` = (row sums, row sums of squares) of `a`, both fp32 [M, parts], with `ln_colsum` (fp32 [N] = sum_k w[n,k]):
+    LayerNorm folded into the GEMM (gamma folded into w, beta into bias; eps = `rms_eps`):
+    rstd * (a w^T - mu * colsum) + bias.  `rowsum_out` (fp32 [M, N/32], together with `sumsq_out`): per-32-column sums of
+    the bf16 outputs, i.e. the statistics the NEXT folded LayerNorm needs."""
     _need_cuda(a, w, bias, residual, row_scale, out)
     _bf16(a, w, residual)
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1, "gemm: 2-D, unit inner stride"
@@ -96,6 +101,26 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         args.rms_nparts = rms_in.numel() // M
         args.rms_inv_dim = 1.0 / K
         args.rms_eps = float(rms_eps)
+    if ln_in is not None:
+        if rms_in is not None or ln_colsum is None:
+            raise ValueError("gemm: ln_in excludes rms_in and needs ln_colsum")
+        ln_sum, ln_sq = ln_in
+        for t in (ln_sum, ln_sq):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == M
+        assert ln_sum.shape == ln_sq.shape and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N and ln_colsum.is_contiguous()
+        _need_cuda(ln_sum, ln_sq, ln_colsum)
+        args.ln_sum_in = ln_sum.data_ptr()
+        args.rms_sumsq_in = ln_sq.data_ptr()
+        args.ln_colsum = ln_colsum.data_ptr()
+        args.rms_nparts = ln_sq.numel() // M
+        args.rms_inv_dim = 1.0 / K
+        args.rms_eps = float(rms_eps)
+    if rowsum_out is not None:
+        if sumsq_out is None:
+            raise ValueError("gemm: rowsum_out is written together with sumsq_out")
+        assert rowsum_out.is_cuda and rowsum_out.dtype == torch.float32 and rowsum_out.is_contiguous()
+        assert tuple(rowsum_out.shape) == (M, N // 32)
+        args.rowsum_out = rowsum_out.data_ptr()
     if sumsq_out is not None:
         if out.dtype != torch.bfloat16 or act == ACT_SWIGLU or N % 32:
             raise NotImplementedError("gemm: sumsq_out supports bf16, non-SwiGLU outputs with N % 32 == 0")
@@ -313,6 +338,18 @@ def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torc
     check(_lib.load().vl2_rmsnorm(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), x.numel() // Cc, Cc, float(eps),
                                   _stream()), "vl2_rmsnorm")
     return out
+
+
+def row_stats(x: torch.Tensor):
+    """(sum, sum of squares) of every row of x [rows, C], each fp32 [rows, 1]: the statistics a folded LayerNorm reads
+    when its input does not come out of a GEMM epilogue."""
+    _need_cuda(x)
+    _bf16(x)
+    assert x.is_contiguous() and x.dim() == 2
+    s = torch.empty((x.shape[0], 1), device=x.device, dtype=torch.float32)
+    q = torch.empty((x.shape[0], 1), device=x.device, dtype=torch.float32)
+    check(_lib.load().vl2_row_stats(x.data_ptr(), s.data_ptr(), q.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_stats")
+    return s, q
 
 
 def row_sumsq(x: torch.Tensor) -> torch.Tensor:
