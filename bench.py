@@ -257,6 +257,9 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch
+    # host threads: a container whose cgroup CPU quota is smaller than os.cpu_count() must not run 128 OpenMP threads (they
+    # spin after every parallel region, burn the quota and get the whole process - including the launching thread - throttled)
+    torch.set_num_threads(max(1, host_threads()["threads"] // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
     import torch.distributed as dist
     from videollama2_b200 import ops, presets
     from videollama2_b200.model import VLLMs
@@ -420,15 +423,7 @@ def main():
                 "h2d_bytes": int(in_bytes)}
         del raw_dev
 
-    # dominant-kernel roofline: every tcgen05 GEMM launch of one step bracketed by CUDA events on the launch stream
-    roof = None
-    model.enable_cuda_graphs(False)      # per-kernel event timing needs eager launches
-    l0 = ops.launch_count()
-    step_resident()                      # the same step launched eagerly: how many libvl2 kernels one step runs
-    torch.cuda.synchronize()
-    launches = ops.launch_count() - l0
-
-    # stage split (device events, same stream)
+    # stage split (device events, same stream; graph replays when graphs are on, like the timed step)
     def stage_times():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         torch.cuda.synchronize()
@@ -442,10 +437,18 @@ def main():
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
 
-    st = [stage_times() for _ in range(3)]
+    st = [stage_times() for _ in range(5)]
     t_vit = statistics.median(s[0] for s in st)
     t_vis = statistics.median(s[1] for s in st)      # ViT + STC + splice (encode_images_or_videos inside)
     t_llm = statistics.median(s[2] for s in st)
+
+    # dominant-kernel roofline: every tcgen05 GEMM launch of one step bracketed by CUDA events on the launch stream
+    roof = None
+    model.enable_cuda_graphs(False)      # per-kernel event timing needs eager launches
+    l0 = ops.launch_count()
+    step_resident()                      # the same step launched eagerly: how many libvl2 kernels one step runs
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - l0
 
     if not args.no_kernel_profile and rank == 0:
         recs = []

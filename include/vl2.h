@@ -120,6 +120,13 @@ typedef struct vl2_gemm_args {
   const float* ln_sum_in;
   const float* ln_colsum;
   float* rowsum_out;
+  /* Implicit-GEMM front end for nn.Conv3d(C, N, kernel_size = stride = 2, padding = conv_pad) on channels-last input
+   * (projector.py:164-174, the STC connector's sampler): with conv_C > 0, A is NOT a matrix but the
+   * activation x bf16 [conv_T, conv_H, conv_W, conv_C]; W is the kernel as [N, 8*conv_C] with K index = tap*C + cin,
+   * tap = dt*4 + dh*2 + dw; M must equal To*Ho*Wo and K = 8*conv_C; C rows are the output positions (to, ho, wo) row-major.
+   * The TMA producer gathers each k-block (one tap x 64 channels) of an output line straight from x through a 4-D tensor
+   * map (out-of-bounds = the zero padding): no im2col matrix exists.  lda is ignored.  bias + activation epilogues only. */
+  int32_t conv_C, conv_T, conv_H, conv_W, conv_pad, reserved4;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 /* Debug aid: with args->reserved2 == 777 CTA 0 records clock64() at its tile boundaries: out[0] = tiles traced (<= 7), and

@@ -481,3 +481,33 @@ def test_gemm_folded_layernorm(cuda, M, N, K, bn, stats_from):
                    rms_eps=1e-5, bn=bn)
     ref = torch.nn.functional.layer_norm(x.float(), (K,), g, beta, 1e-5) @ w.float().t() + b
     assert relerr(out, ref) < 8e-3
+
+
+@pytest.mark.parametrize("pad", [1, 0])
+@pytest.mark.parametrize("T,H,W,C,N,bn", [(16, 24, 24, 4096, 512, 0), (4, 6, 6, 64, 64, 0), (8, 27, 27, 128, 256, 0), (3, 5, 7, 64, 96, 0),
+                                          (16, 24, 24, 256, 512, 1256), (16, 24, 24, 256, 512, 128), (2, 32, 32, 64, 64, 0)])
+def test_conv3d_implicit_gemm(cuda, T, H, W, C, N, bn, pad):
+    """The Conv3d(k=s=2) front end of vl2_gemm_bf16 (TMA gathers the taps from x, out-of-bounds = zero padding) equals the
+    explicit tap-gather + GEMM BIT FOR BIT (same K order) and nn.functional.conv3d within bf16 tolerance."""
+    from videollama2_b200 import ops
+    if W % 2 == 1 and pad == 1:
+        pytest.skip("odd W with padding is not a configuration of the path")
+    x = rnd((T, H, W, C), cuda, seed=81)
+    wt = rnd((N, C, 2, 2, 2), cuda, (8 * C) ** -0.5, seed=82)
+    b = rnd((N,), cuda, 0.1, seed=83).float()
+    wk = wt.permute(0, 2, 3, 4, 1).reshape(N, 8 * C).contiguous()
+    out = ops.conv3d_k2s2(x, wk, bias=b, act=ops.ACT_SILU, pad=pad, bn=bn)
+    explicit = ops.gemm(ops.conv3d_im2col(x, pad), wk, bias=b, act=ops.ACT_SILU)
+    assert torch.equal(out, explicit)
+    ref = torch.nn.functional.conv3d(x.float().permute(3, 0, 1, 2)[None], wt.float(), b, stride=2, padding=pad)
+    ref = torch.nn.functional.silu(ref)[0].permute(1, 2, 3, 0).reshape(-1, N)
+    assert out.shape == ref.shape and relerr(out, ref) < 8e-3
+
+
+def test_conv3d_implicit_gemm_rejects_bad_shapes(cuda):
+    from videollama2_b200 import ops
+    x = rnd((4, 40, 40, 64), cuda)                                   # 21 output columns > 16 per padded line
+    with pytest.raises((ValueError, NotImplementedError)):
+        ops.conv3d_k2s2(x, rnd((64, 512), cuda), pad=1)
+    with pytest.raises(ValueError):
+        ops.conv3d_k2s2(rnd((4, 8, 8, 64), cuda), rnd((64, 256), cuda), pad=1)     # K != 8*C

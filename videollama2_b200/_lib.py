@@ -35,6 +35,8 @@ class GemmArgs(C.Structure):
         ("rms_inv_dim", C.c_float), ("rms_eps", C.c_float),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
         ("ln_sum_in", C.c_void_p), ("ln_colsum", C.c_void_p), ("rowsum_out", C.c_void_p),
+        ("conv_C", C.c_int32), ("conv_T", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_pad", C.c_int32),
+        ("reserved4", C.c_int32),
     ]
 
 

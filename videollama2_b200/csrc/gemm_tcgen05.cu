@@ -23,6 +23,7 @@ static constexpr int BK = 64;
 static constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quarter: they split the 32-column chunks
 static constexpr int kEpiThreads = kEpiWarps * 32;
 static constexpr int kGemmThreads = 128 + kEpiThreads;    // warps 0..3: TMA / MMA / TMEM alloc / spare
+static constexpr int kConvLine = 16;                      // padded rows per output line of the Conv3d front end (Wo <= 16)
 
 // PAIR = true: two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 on a 256 x BN tile; each CTA stages its own
 // 128 rows of A and HALF of the B tile, so a k-block costs 16 KB + BN*64 B of smem/L2 traffic per CTA instead of
@@ -70,6 +71,11 @@ struct GemmParams {
   int split_first, split_s, num_items;
   float* ws_partial;      // [tiles past split_first][split_s - 1][tile rows][BN] fp32 partial accumulators
   unsigned* ws_flags;     // [tiles past split_first][2] arrival counters (self-resetting)
+  // implicit-GEMM Conv3d(k = s = 2) front end (see vl2.h: conv_C > 0).  A rows are the output positions in a padded
+  // enumeration (to, ho, wo16): kConvLine rows per output line, so that one 128-row tile is 8 whole lines and every line
+  // of a k-block (one tap x 64 channels) is ONE 4-D TMA box over x viewed as [T, H, ceil(W/2), 2C]; the spatial zero
+  // padding and the rows past the end are TMA out-of-bounds fill.  conv_M = real output rows (To*Ho*Wo).
+  int conv_C, conv_pad, conv_Ho, conv_Wo, conv_lines, conv_T, conv_M;
   int trace;   // debug: CTA 0 records clock64() at tile boundaries of its MMA and epilogue roles (vl2_debug_gemm_trace)
 };
 
@@ -198,13 +204,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (PAIR) {
             // both CTAs' bytes land on the leader's full barrier
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
-            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
-            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           }
+          if (p.conv_C > 0) {
+            // implicit im2col: k-block = (tap, 64-channel slab); tile rows = 8 output lines x 16 padded positions
+            const int slabs = p.conv_C / BK;
+            const int tap = kb / slabs, c0 = (kb - tap * slabs) * BK;
+            const int dt = tap >> 2, dh = (tap >> 1) & 1, dw = tap & 1;
+            const int e = dw - p.conv_pad;              // w = 2 wo + e, e in {-1, 0, 1}
+            const int pw = e & 1;                       // parity of w  -> which half of the merged (pw, C) dimension
+            const int wc0 = (e - pw) / 2;               // first coarse column (-1 for the padded left border)
+#pragma unroll 1
+            for (int li = 0; li < BM / kConvLine; ++li) {
+              const int line = m0 / kConvLine + li;
+              int t = p.conv_T, h = 0;                  // lines past the end: t out of bounds -> zero fill
+              if (line < p.conv_lines) {
+                const int to = line / p.conv_Ho, ho = line - to * p.conv_Ho;
+                t = 2 * to - p.conv_pad + dt;
+                h = 2 * ho - p.conv_pad + dh;
+              }
+              uint8_t* dst = smem_a + stage * Cfg::kStageBytesA + li * (kConvLine * 128);
+              if (PAIR) tma_load_4d_pair(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + c0, wc0, h, t);
+              else tma_load_4d(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + c0, wc0, h, t);
+            }
+          } else if (PAIR) {
+            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+          } else {
+            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+          }
+          if (PAIR) tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          else tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -501,7 +531,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = t_row + 4 * i;
-            const int gr = rbase + rr;
+            int gr = rbase + rr;
+            if (p.conv_C > 0) {   // padded (line, wo16) row -> real output row, or nothing for the padding positions
+              const int line = gr / kConvLine, wo = gr - line * kConvLine;
+              gr = (wo < p.conv_Wo && line < p.conv_lines) ? line * p.conv_Wo + wo : p.M;
+            }
             if (gr < p.M && t_chunk * 8 < out_span) {
               const uint4 val = lds128(stg + rr * 128 + ((t_chunk ^ (rr & 7)) << 4));
               const int64_t off = (int64_t)gr * p.ldc + out_col0 + t_chunk * 8;
@@ -542,7 +576,25 @@ template <int BN, bool PAIR>
 static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, PAIR>;
   CUtensorMap ta, tb;
-  {
+  const bool conv = a->conv_C > 0;
+  int conv_To = 0, conv_Ho = 0, conv_Wo = 0;
+  if (conv) {
+    // x [T,H,W,C] viewed as [T, H, ceil(W/2), 2C]: a tap's stride-2 walk along W is a unit walk over the coarse columns
+    // at channel offset parity*C; H and T are walked one element per box.  Box = 64 channels x one padded output line.
+    const int p_ = a->conv_pad;
+    conv_To = (a->conv_T + 2 * p_ - 2) / 2 + 1;
+    conv_Ho = (a->conv_H + 2 * p_ - 2) / 2 + 1;
+    conv_Wo = (a->conv_W + 2 * p_ - 2) / 2 + 1;
+    // odd W without padding (SigLIP 27 x 27, stc_connector_v35): the last coarse column would pair w = W-1 with the next
+    // row's first pixel; no stored output needs it, so it is declared out of bounds (zero fill, no read past the tensor)
+    const uint64_t wcols = (a->conv_W % 2 == 1 && p_ == 0) ? (uint64_t)a->conv_W / 2 : (uint64_t)(a->conv_W + 1) / 2;
+    uint64_t dims[4] = {(uint64_t)2 * a->conv_C, wcols, (uint64_t)a->conv_H, (uint64_t)a->conv_T};
+    uint64_t str[3] = {(uint64_t)2 * a->conv_C * 2, (uint64_t)a->conv_W * a->conv_C * 2,
+                       (uint64_t)a->conv_H * a->conv_W * a->conv_C * 2};
+    uint32_t box[4] = {BK, (uint32_t)kConvLine, 1, 1};
+    int rc = make_tmap_bf16(&ta, a->A, 4, dims, str, box);
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     uint64_t str[1] = {(uint64_t)a->lda * 2};
     uint32_t box[2] = {BK, BM};
@@ -567,7 +619,10 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
   for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
   const int tile_m = PAIR ? 2 * BM : BM;
-  p.num_m_tiles = (a->M + tile_m - 1) / tile_m;
+  p.conv_C = conv ? a->conv_C : 0; p.conv_pad = a->conv_pad; p.conv_Ho = conv_Ho; p.conv_Wo = conv_Wo;
+  p.conv_lines = conv_To * conv_Ho; p.conv_T = a->conv_T; p.conv_M = a->M;
+  const int m_rows = conv ? conv_To * conv_Ho * kConvLine : a->M;     // rows of the (padded) A enumeration
+  p.num_m_tiles = (m_rows + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + BN - 1) / BN;
   VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR>), Cfg::kSmemBytes);
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -751,7 +806,24 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
                 "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  TileChoice t = choose_tile(a->M, a->N, a->K, sm_count(), pair_enabled(), splitk_enabled() && a->splitk_ws != nullptr);
+  int m_plan = a->M;
+  if (a->conv_C > 0) {
+    const int p_ = a->conv_pad;
+    VL2_REQUIRE(a->conv_T > 0 && a->conv_H > 0 && a->conv_W > 0 && (p_ == 0 || p_ == 1) && a->conv_C % 64 == 0,
+                VL2_E_BADSHAPE, "vl2_gemm_bf16: conv front end needs T,H,W > 0, pad in {0,1}, C %% 64 == 0");
+    const int To = (a->conv_T + 2 * p_ - 2) / 2 + 1, Ho = (a->conv_H + 2 * p_ - 2) / 2 + 1, Wo = (a->conv_W + 2 * p_ - 2) / 2 + 1;
+    VL2_REQUIRE(a->conv_W % 2 == 0 || p_ == 0, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: conv front end: odd W needs pad 0");
+    VL2_REQUIRE(To > 0 && Ho > 0 && Wo > 0 && Wo <= kConvLine, VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: conv front end supports up to %d output columns per line (got %d)", kConvLine, Wo);
+    VL2_REQUIRE(a->K == 8 * a->conv_C && a->M == To * Ho * Wo, VL2_E_BADSHAPE,
+                "vl2_gemm_bf16: conv front end needs K == 8*C and M == To*Ho*Wo (M=%d, expected %d)", a->M, To * Ho * Wo);
+    VL2_REQUIRE(a->residual == nullptr && a->row_scale == nullptr && a->rms_sumsq_in == nullptr && a->sumsq_out == nullptr &&
+                    !a->out_f32 && a->act != VL2_ACT_SWIGLU && a->n_bcast == 0 && a->mc_out == nullptr,
+                VL2_E_UNSUPPORTED, "vl2_gemm_bf16: the conv front end supports bias + activation epilogues, bf16 output");
+    m_plan = To * Ho * kConvLine;
+  }
+  TileChoice t = choose_tile(m_plan, a->N, a->K, sm_count(), pair_enabled(),
+                             splitk_enabled() && a->splitk_ws != nullptr && a->conv_C == 0);
   // test hook: reserved = BN forces a single-CTA tile width, 1000 + BN forces the cta_group::2 pair kernel
   if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) { t.bn = a->reserved; t.pair = false; }
   if (a->reserved >= 1128 && a->reserved <= 1256 && (a->reserved - 1000) % 32 == 0) { t.bn = a->reserved - 1000; t.pair = true; }

@@ -32,6 +32,8 @@ class DecoderEngine:
         self.kv_len = 0
         self._graphed = None
         self._decode_graph = None   # (graph, tok_dev, pos_dev, logits) of the captured single-token step
+        self._decode_log = None     # (device id buffer, device step counter) the graph appends its arg-max tokens to
+        self._decode_read = 0
         self.graph_decode = False
         self.decode_pdl = os.environ.get("VL2_DECODE_PDL", "0") == "1"   # PDL edges inside the decode graph
         # MB of o_proj + gate/up weights pulled into L2 on a forked graph branch while the attention phase runs
@@ -166,7 +168,7 @@ class DecoderEngine:
         return ops.gemv(x, self.w["lm_head"], rms_eps=self.eps, out_dtype=torch.float32)
 
     # ---- the same step as ONE CUDA graph ---------------------------------------------------------------------
-    def _decode_body(self, tok_dev: torch.Tensor, pos_dev: torch.Tensor, stage: torch.Tensor) -> torch.Tensor:
+    def _decode_body(self, tok_dev: torch.Tensor, pos_dev: torch.Tensor, stage: torch.Tensor, log=None) -> torch.Tensor:
         """Single-token step whose position and token live in device memory: embeds *tok_dev, appends K/V at *pos_dev,
         writes argmax(logits) back to tok_dev and increments pos_dev, so one captured graph serves every token."""
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
@@ -202,6 +204,10 @@ class DecoderEngine:
         logits = ops.gemv(x, self.w["lm_head"], rms_eps=self.eps, out_dtype=torch.float32)
         tok_dev.copy_(torch.argmax(logits, dim=1))
         pos_dev.add_(1)
+        if log is not None:          # device-side log of the generated ids: the host reads it in chunks, not per token
+            gen_buf, step_dev = log
+            gen_buf.scatter_(0, step_dev, tok_dev)
+            step_dev.add_(1)
         return logits
 
     def decode_graph_begin(self, first_token: int) -> None:
@@ -213,22 +219,45 @@ class DecoderEngine:
             tok_dev = torch.zeros((1,), device=dev, dtype=torch.int64)
             pos_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
             stage = torch.empty((1, (self.Hq + 2 * self.Hkv) * self.D), device=dev, dtype=torch.bfloat16)
+            gen_buf = torch.zeros((self.kv[0].shape[0] + 1,), device=dev, dtype=torch.int64)
+            step_dev = torch.zeros((1,), device=dev, dtype=torch.int64)
+            log = (gen_buf, step_dev)
             scratch_pos = self.kv[0].shape[0] - 1     # warm-up writes land in the last cache row (rewritten when reached)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
                     pos_dev.fill_(scratch_pos)
+                    step_dev.zero_()
                     with ops.pdl(self.decode_pdl):
-                        self._decode_body(tok_dev, pos_dev, stage)
+                        self._decode_body(tok_dev, pos_dev, stage, log)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph), ops.pdl(self.decode_pdl):
-                logits = self._decode_body(tok_dev, pos_dev, stage)
+                logits = self._decode_body(tok_dev, pos_dev, stage, log)
             self._decode_graph = (graph, tok_dev, pos_dev, logits, stage)
+            self._decode_log = log
         _, tok_dev, pos_dev, _, _ = self._decode_graph
         tok_dev.fill_(int(first_token))
         pos_dev.fill_(self.kv_len)
+        self._decode_log[1].zero_()
+        self._decode_read = 0
+
+    def decode_graph_run(self, k: int) -> None:
+        """Enqueue k token steps back to back (no host round trip in between: each replay embeds the token the previous one
+        left in device memory and logs its own arg-max into the device-side id buffer)."""
+        graph = self._decode_graph[0]
+        if self.kv_len + k > self.kv[0].shape[0]:
+            raise RuntimeError(f"KV cache full ({self.kv_len} + {k} positions)")
+        for _ in range(k):
+            graph.replay()
+        self.kv_len += k
+
+    def decode_graph_tokens(self, k: int) -> list:
+        """The next k logged token ids (one device->host copy, one synchronisation for the whole chunk)."""
+        a = self._decode_read
+        self._decode_read = a + k
+        return self._decode_log[0][a:a + k].tolist()
 
     def decode_graph_step(self) -> torch.Tensor:
         """Replay one token; returns the device int64[1] holding the NEW token (argmax), logits stay in the graph's

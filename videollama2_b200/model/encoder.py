@@ -102,10 +102,13 @@ class CLIPVisionTower:
 
     _ACT = ops.ACT_QUICK_GELU
 
-    # LayerNorms folded into the GEMMs that consume them (VL2_VIT_FOLD_LN=0 keeps the stand-alone LayerNorm kernels):
-    # gamma goes into the weight columns, beta into the bias, and the row statistics (sum, sum of squares) come out of the
-    # epilogue of the GEMM that produced the residual stream - 2 launches and 2 round trips of the stream fewer per layer
-    fold_layernorm = os.environ.get("VL2_VIT_FOLD_LN", "1") != "0"
+    # LayerNorms folded into the GEMMs that consume them (VL2_VIT_FOLD_LN=1): gamma goes into the weight columns, beta into
+    # the bias, and the row statistics (sum, sum of squares) come out of the epilogue of the GEMM that produced the residual
+    # stream - 2 launches and 2 round trips of the stream fewer per layer.  Parity-tested, but OFF by default: measured on
+    # B200 (profiles/r02_vit_shard_probe.json) the K = 1024 tower GEMMs are epilogue-bound, so the extra epilogue work costs
+    # more than the 46 stand-alone LayerNorm launches it removes at 8-16 frames (8.22 vs 7.71 ms) and only pays at 2 frames
+    # per GPU (2.51 vs 2.61 ms).
+    fold_layernorm = os.environ.get("VL2_VIT_FOLD_LN", "0") == "1"
 
     def _encoder(self, x: torch.Tensor, Fn: int, S: int, last_out=None, bcast_ptrs=None, mc_ptr: int = 0,
                  stats=None) -> torch.Tensor:

@@ -154,6 +154,8 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache and max_new > 1, max_len=S + max_new)
         graphed = use_cache and max_new > 1 and dec.graph_decode
         from ..sampling import sample_token
+        if graphed and not sample:
+            return self._generate_greedy_graphed(dec, logits, max_new, eos_ids, stopping, int(kwargs.get("decode_chunk", 8)))
         for step in range(max_new):
             if sample:      # the graph's own argmax token is overridden below; its logits buffer is what we sample from
                 row = logits[0] if not (graphed and step > 0) else dec.decode_graph_logits[0]
@@ -178,6 +180,36 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
                 x = torch.cat([x, e], 0)
                 logits, _ = dec.prefill(x, all_logits=False)
         return torch.tensor([new_ids], dtype=torch.long, device=self.device)
+
+    def _generate_greedy_graphed(self, dec, logits, max_new: int, eos_ids, stopping, chunk: int):
+        """Greedy decoding with the host off the critical path: the captured single-token graph feeds itself (token and
+        position live in device memory) and appends every arg-max to a device-side id log, so the host enqueues `chunk`
+        replays at a time and reads the log once per chunk.  EOS / stopping criteria are evaluated on the host in token
+        order; tokens the device produced past the stopping point are discarded (at most chunk - 1 wasted steps), so the
+        returned ids equal the token-by-token loop's (tests/test_e2e_gpu.py)."""
+        ids_buf = torch.empty((1, max_new), dtype=torch.long)
+
+        def stops(n):          # n = number of ids so far
+            tok = int(ids_buf[0, n - 1])
+            return tok in eos_ids or any(sc(ids_buf[:, :n], None) for sc in stopping) or n == max_new
+
+        ids_buf[0, 0] = int(torch.argmax(logits[0]).item())
+        n = 1
+        if not stops(n):
+            dec.decode_graph_begin(int(ids_buf[0, 0]))
+            done = False
+            first = True
+            while not done:
+                k = min(max_new - n, 2 if first else max(1, chunk))     # a short first chunk: early EOS costs little
+                first = False
+                dec.decode_graph_run(k)
+                for tok in dec.decode_graph_tokens(k):
+                    ids_buf[0, n] = tok
+                    n += 1
+                    if stops(n):
+                        done = True
+                        break
+        return ids_buf[:, :n].to(self.device)
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
         images = kwargs.pop("images", None)

@@ -14,7 +14,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SI
 
 __all__ = [
     "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "l2_prefetch", "layernorm", "rmsnorm", "row_sumsq", "row_stats", "patch_im2col", "clip_embed_finish",
-    "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "rope_inplace", "embed_splice", "launch_count",
+    "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "conv3d_k2s2", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
 
@@ -411,6 +411,33 @@ def se_scale(y: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     HW = y.numel() // (F * Cc)
     check(_lib.load().vl2_se_scale(y.data_ptr(), s.data_ptr(), F, HW, Cc, _stream()), "vl2_se_scale")
     return y
+
+
+def conv3d_k2s2(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, pad: int = 1,
+                out: Optional[torch.Tensor] = None, bn: int = 0) -> torch.Tensor:
+    """nn.Conv3d(C, N, kernel_size=2, stride=2, padding=pad) (+bias, +activation) on channels-last x [T,H,W,C] as an
+    IMPLICIT GEMM: out[(to,ho,wo), N] = act(sum_tap x[2to-pad+dt, 2ho-pad+dh, 2wo-pad+dw, :] w[:, tap*C:(tap+1)*C]^T + bias).
+    The GEMM's TMA producer gathers every k-block of every output line straight from x (4-D tensor map, out-of-bounds =
+    zero padding); no im2col matrix is materialised.  w: [N, 8*C], K index = tap*C + cin, tap = dt*4 + dh*2 + dw."""
+    _need_cuda(x, w, bias, out)
+    _bf16(x, w)
+    assert x.is_contiguous() and x.dim() == 4 and w.dim() == 2 and w.stride(1) == 1
+    T, H, W, Cc = x.shape
+    N, K = w.shape
+    if K != 8 * Cc:
+        raise ValueError(f"conv3d_k2s2: weight K {K} != 8*C {8 * Cc}")
+    To, Ho, Wo = (T + 2 * pad - 2) // 2 + 1, (H + 2 * pad - 2) // 2 + 1, (W + 2 * pad - 2) // 2 + 1
+    M = To * Ho * Wo
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == torch.bfloat16
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    args = GemmArgs(A=x.data_ptr(), W=w.data_ptr(), C=out.data_ptr(), bias=_ptr(bias), lda=K, ldw=w.stride(0),
+                    ldc=out.stride(0), ldr=0, M=M, N=N, K=K, act=act, out_f32=0, reserved=bn, conv_C=Cc, conv_T=T, conv_H=H,
+                    conv_W=W, conv_pad=pad)
+    check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16(conv3d)")
+    return out
 
 
 def conv3d_im2col(x: torch.Tensor, pad: int) -> torch.Tensor:
