@@ -127,6 +127,15 @@ typedef struct vl2_gemm_args {
    * The TMA producer gathers each k-block (one tap x 64 channels) of an output line straight from x through a 4-D tensor
    * map (out-of-bounds = the zero padding): no im2col matrix exists.  lda is ignored.  bias + activation epilogues only. */
   int32_t conv_C, conv_T, conv_H, conv_W, conv_pad, reserved4;
+  /* RoPE in the epilogue of the fused QKV projection (HF:mistral/modeling_mistral.py:51-82 apply_rotary_pos_emb): output
+   * columns [0, rope_cols) are q and k heads of width rope_D whose weight rows were permuted at load so that the rotation
+   * partners (i, i + D/2) of a head are ADJACENT output columns (2i, 2i+1); the epilogue rotates each pair of row m with
+   * the angle of position rope_pos0 + m and frequency i:  (a, b) -> (a cos - b sin, b cos + a sin).  q.k dot products are
+   * invariant under the (consistent) permutation, so attention and the KV cache need no un-permute.
+   *   rope_tab  uint32 [positions, rope_D/2]: bf16 cos in the low half, bf16 sin in the high half (HF rounds cos/sin to
+   *             the activation dtype), device memory; NULL = off.  bf16 output, no activation. */
+  const uint32_t* rope_tab;
+  int32_t rope_cols, rope_D, rope_pos0, reserved5;
 } vl2_gemm_args;
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 /* Debug aid: with args->reserved2 == 777 CTA 0 records clock64() at its tile boundaries: out[0] = tiles traced (<= 7), and
@@ -195,7 +204,7 @@ int vl2_attention_decode(const void* q, const void* k_cache, const void* v_cache
  * and copies the row into cache[*pos_dev]; vl2_attention_decode_dyn attends to cache rows 0..*pos_dev and is
  * bit-identical to vl2_attention_decode(n_pos = *pos_dev + 1). */
 int vl2_decode_rope_append(void* qkv_row, void* cache, int64_t cache_ld, const int32_t* pos_dev, int Hq, int Hkv, int D,
-                           const float* inv_freq, void* stream);
+                           const float* inv_freq, int interleaved /* pairing, see vl2_rope_inplace */, void* stream);
 int vl2_attention_decode_dyn(const void* q, const void* k_cache, const void* v_cache, void* out, int64_t ldkv,
                              const int32_t* pos_dev, int Hq, int Hkv, int D, float scale, void* workspace, void* stream);
 
@@ -250,7 +259,11 @@ int vl2_conv3d_im2col(const void* x, void* A, int T, int H, int W, int C, int pa
  *   directly by the readout GEMM.  videollama2_arch.py:198-220.
  * ---------------------------------------------------------------------------------------------------------- */
 int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off, int k_off, int pos0,
-                     const float* inv_freq /* fp32 [D/2], device */, void* stream);
+                     const float* inv_freq /* fp32 [D/2], device */,
+                     int interleaved /* 0: HF rotate-half pairing (i, i + D/2); 1: pairs are adjacent columns (2i, 2i+1) -
+                                        the layout of a QKV projection whose q/k weight rows were permuted for the
+                                        RoPE-in-epilogue GEMM (vl2_gemm_args.rope_tab) */,
+                     void* stream);
 int vl2_embed_splice(const int64_t* ids, const int32_t* dst_row, int n, const void* table, int64_t vocab, void* out,
                      int H, void* stream);
 

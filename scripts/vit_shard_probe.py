@@ -92,4 +92,15 @@ if "--sweep" in sys.argv:
                 fn()
         att[f"frames={frames}"] = round(timed(g.replay, 10) / 6 * 1e3, 2)
     out["attention_us"] = att
+if "--conv" in sys.argv:
+    # Conv3d sampler of the connector: implicit GEMM (TMA gathers the taps) against explicit tap gather + GEMM
+    T, H, W, C = 16, 24, 24, 4096
+    x = torch.randn((T, H, W, C), device=dev, dtype=torch.bfloat16)
+    wk = torch.randn((C, 8 * C), device=dev, dtype=torch.bfloat16) * (8 * C) ** -0.5
+    b = torch.randn((C,), device=dev)
+    conv = {}
+    for bn in (0, 256, 1256, 1224, 1192):
+        conv[f"implicit bn={bn}"] = round(timed(lambda: ops.conv3d_k2s2(x, wk, bias=b, act=ops.ACT_SILU, pad=1, bn=bn), 10) * 1e3, 1)
+    conv["explicit im2col+gemm"] = round(timed(lambda: ops.gemm(ops.conv3d_im2col(x, 1), wk, bias=b, act=ops.ACT_SILU), 10) * 1e3, 1)
+    out["conv3d_us"] = conv
 print(json.dumps(out))

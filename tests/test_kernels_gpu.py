@@ -485,7 +485,7 @@ def test_gemm_folded_layernorm(cuda, M, N, K, bn, stats_from):
 
 @pytest.mark.parametrize("pad", [1, 0])
 @pytest.mark.parametrize("T,H,W,C,N,bn", [(16, 24, 24, 4096, 512, 0), (4, 6, 6, 64, 64, 0), (8, 27, 27, 128, 256, 0), (3, 5, 7, 64, 96, 0),
-                                          (16, 24, 24, 256, 512, 1256), (16, 24, 24, 256, 512, 128), (2, 32, 32, 64, 64, 0)])
+                                          (16, 24, 24, 256, 512, 1256), (16, 24, 24, 256, 512, 128), (2, 30, 30, 64, 64, 0)])
 def test_conv3d_implicit_gemm(cuda, T, H, W, C, N, bn, pad):
     """The Conv3d(k=s=2) front end of vl2_gemm_bf16 (TMA gathers the taps from x, out-of-bounds = zero padding) equals the
     explicit tap-gather + GEMM BIT FOR BIT (same K order) and nn.functional.conv3d within bf16 tolerance."""
@@ -511,3 +511,37 @@ def test_conv3d_implicit_gemm_rejects_bad_shapes(cuda):
         ops.conv3d_k2s2(x, rnd((64, 512), cuda), pad=1)
     with pytest.raises(ValueError):
         ops.conv3d_k2s2(rnd((4, 8, 8, 64), cuda), rnd((64, 256), cuda), pad=1)     # K != 8*C
+
+
+@pytest.mark.parametrize("S,Hq,Hkv,D,pos0,bn", [(1776, 8, 2, 128, 0, 0), (300, 28, 4, 128, 5, 0), (130, 4, 2, 64, 0, 64),
+                                               (260, 2, 1, 128, 17, 1256), (77, 4, 4, 32, 3, 0)])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_gemm_rope_epilogue(cuda, S, Hq, Hkv, D, pos0, bn, with_bias):
+    """RoPE fused into the QKV GEMM epilogue on permuted (adjacent-pair) columns == HF apply_rotary_pos_emb
+    (rotate-half pairing, HF:mistral/modeling_mistral.py:51-82) on the un-permuted projection, up to the column
+    permutation; v columns untouched; vl2_rope_inplace(interleaved=1) reproduces the epilogue's layout."""
+    from videollama2_b200 import ops
+    K = 256
+    nqk, nv = (Hq + Hkv) * D, Hkv * D
+    x = rnd((S, K), cuda, seed=91)
+    w = rnd((nqk + nv, K), cuda, K ** -0.5, seed=92)
+    b = rnd((nqk + nv,), cuda, 0.1, seed=93).float() if with_bias else None
+    perm = torch.cat([ops.rope_interleave_rows(Hq + Hkv, D), torch.arange(nqk, nqk + nv)]).to(cuda)
+    tab = ops.rope_table(pos0 + S + 3, D, 1e6, cuda)
+    out = ops.gemm(x, w[perm].contiguous(), bias=None if b is None else b[perm].contiguous(), rope=(tab, pos0, D, nqk), bn=bn)
+    # reference: plain projection, HF rotation, then the same permutation
+    y = x.float() @ w.float().t() + (0 if b is None else b)
+    inv = 1.0 / (1e6 ** (torch.arange(0, D, 2, device=cuda).float() / D))
+    ang = torch.outer(torch.arange(pos0, pos0 + S, device=cuda).float(), inv)
+    cos = torch.cat([ang, ang], -1).cos().to(torch.bfloat16).float()
+    sin = torch.cat([ang, ang], -1).sin().to(torch.bfloat16).float()
+    qk = y[:, :nqk].view(S, Hq + Hkv, D)
+    rot = torch.cat([-qk[..., D // 2:], qk[..., :D // 2]], -1)
+    ref = torch.cat([(qk * cos[:, None] + rot * sin[:, None]).reshape(S, nqk), y[:, nqk:]], 1)[:, perm]
+    assert relerr(out, ref) < 6e-3
+    assert relerr(out[:, nqk:], y[:, nqk:]) < 6e-3
+    # the stand-alone kernel in interleaved mode on the un-rotated projection gives the same layout
+    plain = ops.gemm(x, w[perm].contiguous(), bias=None if b is None else b[perm].contiguous(), bn=bn)
+    inv_dev = inv.contiguous()
+    ops.rope_inplace(plain, S, Hq, Hkv, D, 0, Hq * D, pos0, inv_dev, interleaved=True)
+    assert relerr(plain, ref) < 8e-3

@@ -37,6 +37,8 @@ class GemmArgs(C.Structure):
         ("ln_sum_in", C.c_void_p), ("ln_colsum", C.c_void_p), ("rowsum_out", C.c_void_p),
         ("conv_C", C.c_int32), ("conv_T", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_pad", C.c_int32),
         ("reserved4", C.c_int32),
+        ("rope_tab", C.c_void_p), ("rope_cols", C.c_int32), ("rope_D", C.c_int32), ("rope_pos0", C.c_int32),
+        ("reserved5", C.c_int32),
     ]
 
 
@@ -76,7 +78,7 @@ def load() -> C.CDLL:
         "vl2_debug_attn_trace": [vp],
         "vl2_debug_gemm_trace": [vp],
         "vl2_gemm_plan": [i32, i32, i32, i32, vp],
-        "vl2_decode_rope_append": [vp, vp, i64, vp, i32, i32, i32, vp, vp],
+        "vl2_decode_rope_append": [vp, vp, i64, vp, i32, i32, i32, vp, i32, vp],
         "vl2_attention_decode_dyn": [vp, vp, vp, vp, i64, vp, i32, i32, i32, f32, vp, vp],
         "vl2_gemv_bf16": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "vl2_attention_decode_workspace": [i32, i32, i32],
@@ -95,7 +97,7 @@ def load() -> C.CDLL:
         "vl2_dwconv3x3_ln_silu": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "vl2_se_scale": [vp, vp, i32, i32, i32, vp],
         "vl2_conv3d_im2col": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
-        "vl2_rope_inplace": [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp],
+        "vl2_rope_inplace": [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp],
         "vl2_embed_splice": [vp, vp, i32, vp, i64, vp, i32, vp],
     }
     for name, argtypes in sigs.items():

@@ -76,6 +76,9 @@ struct GemmParams {
   // of a k-block (one tap x 64 channels) is ONE 4-D TMA box over x viewed as [T, H, ceil(W/2), 2C]; the spatial zero
   // padding and the rows past the end are TMA out-of-bounds fill.  conv_M = real output rows (To*Ho*Wo).
   int conv_C, conv_pad, conv_Ho, conv_Wo, conv_lines, conv_T, conv_M;
+  // RoPE in the QKV epilogue (see vl2.h): adjacent output columns (2i, 2i+1) of a head are a rotation pair
+  const uint32_t* rope_tab;
+  int rope_cols, rope_D, rope_pos0;
   int trace;   // debug: CTA 0 records clock64() at tile boundaries of its MMA and epilogue roles (vl2_debug_gemm_trace)
 };
 
@@ -191,50 +194,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t tmem_base = *tmem_base_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer =====================
+    // Dense A: lane 0 issues both loads of a k-block.  Conv3d front end: the A stage is 8 line boxes, issued by lanes
+    // 0..7 in parallel (each lane owns one output line of the tile and keeps its coordinates in registers), B by lane 8;
+    // the whole warp walks the ring together so the waits stay warp-uniform.
+    const bool conv = p.conv_C > 0;
+    if (lane == 0 || conv) {
       int stage = 0;
       uint32_t phase = 0;
+      const int slabs = conv ? p.conv_C / BK : 1;
       for (int item = tile0; item < p.num_items; item += tile_stride) {
         const WorkItem w = decode_item(item, p, num_k_blocks);
         const int m0 = (w.tile % p.num_m_tiles) * kTileM + (int)rank * BM;
         const int n0 = (w.tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
+        // this lane's output line of the tile (conv): input coordinates of tap (0,0,0); out-of-range lines read t = T
+        int t0 = p.conv_T + 2, h0 = 0;
+        if (conv && lane < BM / kConvLine) {
+          const int line = m0 / kConvLine + lane;
+          if (line < p.conv_lines) {
+            const int to = line / p.conv_Ho, ho = line - to * p.conv_Ho;
+            t0 = 2 * to - p.conv_pad;
+            h0 = 2 * ho - p.conv_pad;
+          }
+        }
+        int tap = w.kb0 / slabs, slab = w.kb0 - tap * slabs;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (PAIR) {
-            // both CTAs' bytes land on the leader's full barrier
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          }
-          if (p.conv_C > 0) {
-            // implicit im2col: k-block = (tap, 64-channel slab); tile rows = 8 output lines x 16 padded positions
-            const int slabs = p.conv_C / BK;
-            const int tap = kb / slabs, c0 = (kb - tap * slabs) * BK;
-            const int dt = tap >> 2, dh = (tap >> 1) & 1, dw = tap & 1;
-            const int e = dw - p.conv_pad;              // w = 2 wo + e, e in {-1, 0, 1}
-            const int pw = e & 1;                       // parity of w  -> which half of the merged (pw, C) dimension
-            const int wc0 = (e - pw) / 2;               // first coarse column (-1 for the padded left border)
-#pragma unroll 1
-            for (int li = 0; li < BM / kConvLine; ++li) {
-              const int line = m0 / kConvLine + li;
-              int t = p.conv_T, h = 0;                  // lines past the end: t out of bounds -> zero fill
-              if (line < p.conv_lines) {
-                const int to = line / p.conv_Ho, ho = line - to * p.conv_Ho;
-                t = 2 * to - p.conv_pad + dt;
-                h = 2 * ho - p.conv_pad + dh;
-              }
-              uint8_t* dst = smem_a + stage * Cfg::kStageBytesA + li * (kConvLine * 128);
-              if (PAIR) tma_load_4d_pair(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + c0, wc0, h, t);
-              else tma_load_4d(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + c0, wc0, h, t);
+          if (lane == 0) {
+            if (PAIR) {
+              // both CTAs' bytes land on the leader's full barrier
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             }
+          }
+          if (conv) {
+            __syncwarp();   // expect_tx is posted before any lane's copy can complete
+            if (lane < BM / kConvLine) {
+              // implicit im2col: k-block = (tap, 64-channel slab); w = 2 wo + e with e = dw - pad in {-1, 0, 1}
+              const int dt = tap >> 2, dh = (tap >> 1) & 1, dw = tap & 1;
+              const int e = dw - p.conv_pad;
+              const int pw = e & 1;                     // parity of w -> which half of the merged (pw, C) dimension
+              const int wc0 = (e - pw) / 2;             // first coarse column (-1 for the padded left border)
+              uint8_t* dst = smem_a + stage * Cfg::kStageBytesA + lane * (kConvLine * 128);
+              if (PAIR) tma_load_4d_pair(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + slab * BK, wc0, h0 + dh, t0 + dt);
+              else tma_load_4d(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + slab * BK, wc0, h0 + dh, t0 + dt);
+            } else if (lane == BM / kConvLine) {
+              if (PAIR) tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+              else tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+            }
+            if (++slab == slabs) { slab = 0; ++tap; }
           } else if (PAIR) {
             tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           } else {
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           }
-          if (PAIR) tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
-          else tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -477,6 +493,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
           }
+          if (p.rope_tab != nullptr && col0 + hf * 32 < p.rope_cols && row_ok) {
+            // 32 accumulator columns = 16 rotation pairs of one head, frequencies i0 .. i0 + 15, angle of this row's position
+            const int i0 = ((col0 + hf * 32) % p.rope_D) >> 1;
+            const uint4* tr = reinterpret_cast<const uint4*>(p.rope_tab + (int64_t)(p.rope_pos0 + row) * (p.rope_D >> 1) + i0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 cs = __ldg(tr + g);
+              const uint32_t e[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float c = bf16_lo(e[j]), sn = bf16_hi(e[j]);
+                const float a = x[g * 8 + 2 * j], b = x[g * 8 + 2 * j + 1];
+                x[g * 8 + 2 * j] = a * c - b * sn;
+                x[g * 8 + 2 * j + 1] = b * c + a * sn;
+              }
+            }
+          }
           if (res != nullptr) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -619,6 +652,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   p.mc = reinterpret_cast<__nv_bfloat16*>(a->mc_out);
   for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
   const int tile_m = PAIR ? 2 * BM : BM;
+  p.rope_tab = a->rope_tab; p.rope_cols = a->rope_cols; p.rope_D = a->rope_D; p.rope_pos0 = a->rope_pos0;
   p.conv_C = conv ? a->conv_C : 0; p.conv_pad = a->conv_pad; p.conv_Ho = conv_Ho; p.conv_Wo = conv_Wo;
   p.conv_lines = conv_To * conv_Ho; p.conv_T = a->conv_T; p.conv_M = a->M;
   const int m_rows = conv ? conv_To * conv_Ho * kConvLine : a->M;     // rows of the (padded) A enumeration
@@ -804,6 +838,13 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
   if (a->act == VL2_ACT_SWIGLU) {
     VL2_REQUIRE(a->residual == nullptr && !a->out_f32 && a->N % 16 == 0, VL2_E_UNSUPPORTED,
                 "vl2_gemm_bf16: SWIGLU epilogue needs N %% 16 == 0, bf16 output and no residual");
+  }
+  if (a->rope_tab != nullptr) {
+    VL2_REQUIRE(a->rope_D >= 32 && a->rope_D % 32 == 0 && a->rope_cols > 0 && a->rope_cols % a->rope_D == 0 &&
+                    a->rope_cols <= a->N && a->rope_pos0 >= 0 && aligned16(a->rope_tab),
+                VL2_E_BADSHAPE, "vl2_gemm_bf16: rope epilogue needs head width %% 32 == 0, rope_cols a multiple of it (<= N)");
+    VL2_REQUIRE(!a->out_f32 && a->act == VL2_ACT_NONE && a->residual == nullptr, VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: the rope epilogue supports bf16 output without activation / residual");
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int m_plan = a->M;

@@ -475,7 +475,7 @@ __global__ void conv3d_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
 // head with 16-byte accesses.
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off,
                             int k_off, int pos0, const float* __restrict__ inv_freq, const int* __restrict__ pos_ptr,
-                            __nv_bfloat16* __restrict__ append_base, int64_t append_ld, int append_width) {
+                            __nv_bfloat16* __restrict__ append_base, int64_t append_ld, int append_width, int interleaved) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float cs[];  // [D/2] cos, [D/2] sin
@@ -495,6 +495,26 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, int S, 
   for (int t = threadIdx.x; t < (Hq + Hkv) * vph; t += blockDim.x) {
     const int h = t / vph, i0 = (t % vph) * 8;
     __nv_bfloat16* p = row + (h < Hq ? q_off + h * D : k_off + (h - Hq) * D) + i0;
+    if (interleaved) {
+      // pairs are adjacent columns (2i, 2i+1): this thread's 8 frequencies i0..i0+7 cover 16 consecutive elements
+      __nv_bfloat16* pi = row + (h < Hq ? q_off + h * D : k_off + (h - Hq) * D) + 2 * i0;
+      float lo[8], hi[8];
+      unpack8(*reinterpret_cast<const uint4*>(pi), lo);
+      unpack8(*reinterpret_cast<const uint4*>(pi + 8), hi);
+      float o0[8], o1[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float c0 = cs[i0 + j], s0 = cs[half + i0 + j];
+        o0[2 * j] = lo[2 * j] * c0 - lo[2 * j + 1] * s0;
+        o0[2 * j + 1] = lo[2 * j + 1] * c0 + lo[2 * j] * s0;
+        const float c1 = cs[i0 + 4 + j], s1 = cs[half + i0 + 4 + j];
+        o1[2 * j] = hi[2 * j] * c1 - hi[2 * j + 1] * s1;
+        o1[2 * j + 1] = hi[2 * j + 1] * c1 + hi[2 * j] * s1;
+      }
+      *reinterpret_cast<uint4*>(pi) = pack8(o0);
+      *reinterpret_cast<uint4*>(pi + 8) = pack8(o1);
+      continue;
+    }
     float a[8], b[8], oa[8], ob[8];
     unpack8(*reinterpret_cast<const uint4*>(p), a);
     unpack8(*reinterpret_cast<const uint4*>(p + half), b);
@@ -776,14 +796,14 @@ extern "C" int vl2_conv3d_im2col(const void* x, void* A, int T, int H, int W, in
 }
 
 extern "C" int vl2_rope_inplace(void* qkv, int64_t ld, int S, int Hq, int Hkv, int D, int q_off, int k_off, int pos0,
-                                const float* inv_freq, void* stream) {
+                                const float* inv_freq, int interleaved, void* stream) {
   VL2_REQUIRE(S > 0 && D % 2 == 0 && Hq > 0 && Hkv >= 0 && inv_freq != nullptr, VL2_E_BADSHAPE, "vl2_rope_inplace: bad shape");
   VL2_REQUIRE(D % 16 == 0 && ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && aligned16(qkv), VL2_E_BADALIGN,
               "vl2_rope_inplace: D %% 16 == 0 and 16-byte aligned heads required");
   int threads = (Hq + Hkv) * (D / 16);
   threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
   launch_kernel(rope_kernel, dim3(S), dim3(threads), D * sizeof(float), (cudaStream_t)stream, 1, (bf16*)qkv, ld, S, Hq, Hkv, D, q_off, k_off, pos0,
-                inv_freq, (const int*)nullptr, (bf16*)nullptr, (int64_t)0, 0);
+                inv_freq, (const int*)nullptr, (bf16*)nullptr, (int64_t)0, 0, interleaved);
   VL2_CHECK_LAUNCH("rope_kernel");
   return VL2_OK;
 }
@@ -818,14 +838,14 @@ extern "C" int vl2_gemm_skinny(const void* A, int a_f32, const void* W, const fl
 
 // ---- graph-replayable decode step: the token position is read from device memory ------------------------------
 extern "C" int vl2_decode_rope_append(void* qkv_row, void* cache, int64_t cache_ld, const int32_t* pos_dev, int Hq, int Hkv,
-                                      int D, const float* inv_freq, void* stream) {
+                                      int D, const float* inv_freq, int interleaved, void* stream) {
   VL2_REQUIRE(qkv_row && cache && pos_dev && inv_freq && D % 16 == 0 && cache_ld % 8 == 0, VL2_E_BADSHAPE,
               "vl2_decode_rope_append: bad arguments");
   const int width = (Hq + 2 * Hkv) * D;
   int threads = (Hq + Hkv) * (D / 16);
   threads = threads > 512 ? 512 : ((threads + 31) / 32 * 32);
   launch_kernel(rope_kernel, dim3(1), dim3(threads), D * sizeof(float), (cudaStream_t)stream, 1, (bf16*)qkv_row, (int64_t)width, 1,
-                Hq, Hkv, D, 0, Hq * D, 0, inv_freq, (const int*)pos_dev, (bf16*)cache, cache_ld, width);
+                Hq, Hkv, D, 0, Hq * D, 0, inv_freq, (const int*)pos_dev, (bf16*)cache, cache_ld, width, interleaved);
   VL2_CHECK_LAUNCH("rope_kernel");
   return VL2_OK;
 }

@@ -57,6 +57,12 @@ class DecoderEngine:
         bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         self.layers = []
+        # RoPE runs in the epilogue of the fused QKV GEMM on ADJACENT column pairs: permute the q / k weight rows (and
+        # biases) so that the partners (i, i + D/2) of a head come out as columns (2i, 2i+1).  q.k is invariant under the
+        # permutation (same one for q and k), v is untouched, so attention and the KV cache consume the rows as they are.
+        nqk = (self.Hq + self.Hkv) * self.D
+        qk_perm = torch.cat([ops.rope_interleave_rows(self.Hq + self.Hkv, self.D),
+                             torch.arange(nqk, nqk + self.Hkv * self.D)]).to(dev)
         for i in range(self.config.num_hidden_layers):
             p = f"model.layers.{i}."
             names = ("q_proj", "k_proj", "v_proj")
@@ -65,6 +71,7 @@ class DecoderEngine:
             g1 = sd[p + "input_layernorm.weight"].to(device=dev, dtype=torch.float32)
             g2 = sd[p + "post_attention_layernorm.weight"].to(device=dev, dtype=torch.float32)
             wqkv = torch.cat([sd[p + f"self_attn.{n}.weight"] for n in names], 0).to(device=dev, dtype=torch.float32)
+            wqkv = wqkv[qk_perm]          # RoPE partners of every q / k head become adjacent output columns
             wgu = torch.stack([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], 1).reshape(
                 2 * self.I, self.H).to(device=dev, dtype=torch.float32)
             L = {
@@ -75,7 +82,7 @@ class DecoderEngine:
             }
             del wqkv, wgu
             if p + "self_attn.q_proj.bias" in sd:
-                L["bqkv"] = f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in names], 0))
+                L["bqkv"] = f32(torch.cat([sd[p + f"self_attn.{n}.bias"] for n in names], 0).to(dev)[qk_perm])
             self.layers.append(L)
         self.w = {"embed": bf(sd["model.embed_tokens.weight"]), "norm": bf(sd["model.norm.weight"]),
                   # final-norm gain folded into the lm_head columns (the GEMV / GEMM epilogue applies 1/rms itself)
@@ -85,6 +92,9 @@ class DecoderEngine:
                   "ones": torch.ones((self.H,), device=dev, dtype=torch.bfloat16)}
         inv = 1.0 / (self.config.rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))
         self.w["inv_freq"] = inv.to(dev)
+        # one table for every position the model can see (8 MB at 32768 x 64): captured graphs keep its address
+        self._rope_tab = ops.rope_table(int(getattr(self.config, "max_position_embeddings", 32768) or 32768), self.D,
+                                        self.config.rope_theta, dev)
         self.device = dev
         self.is_loaded = True
         return self
@@ -93,13 +103,20 @@ class DecoderEngine:
     def embed_tokens(self) -> torch.Tensor:
         return self.w["embed"]
 
+    def rope_table(self, n_pos: int) -> torch.Tensor:
+        """Packed bf16 (cos, sin) of every (position, frequency), built once at load."""
+        if self._rope_tab.shape[0] < n_pos:
+            raise ValueError(f"sequence of {n_pos} positions exceeds max_position_embeddings ({self._rope_tab.shape[0]})")
+        return self._rope_tab
+
     # ---- prefill ---------------------------------------------------------------------------------------------
     def _layer(self, L, x: torch.Tensor, S: int, pos0: int, qkv_out: Optional[torch.Tensor], ss_x: torch.Tensor):
         """One decoder layer.  ss_x [S, parts]: partial sums of squares of the incoming residual stream's rows.
         Returns (outgoing stream, its partial sums of squares [S, H/32] written by the down_proj epilogue)."""
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
-        qkv = ops.gemm(x, L["wqkv"], bias=L.get("bqkv"), out=qkv_out, rms_in=ss_x, rms_eps=self.eps)
-        ops.rope_inplace(qkv, S, Hq, Hkv, D, 0, Hq * D, pos0, self.w["inv_freq"])
+        # RMSNorm scale, bias and RoPE all happen in this GEMM's epilogue; K / V land in the cache layout directly
+        qkv = ops.gemm(x, L["wqkv"], bias=L.get("bqkv"), out=qkv_out, rms_in=ss_x, rms_eps=self.eps,
+                       rope=(self.rope_table(pos0 + S), pos0, D, (Hq + Hkv) * D))
         o = ops.attention(qkv[:, : Hq * D], qkv[:, Hq * D: (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], B=1, S=S, Hq=Hq,
                           Hkv=Hkv, D=D, causal=True, scale=D ** -0.5)
         ss_mid = torch.empty((S, self.H // 32), device=x.device, dtype=torch.float32)
@@ -158,7 +175,7 @@ class DecoderEngine:
             cache = self.kv[i]
             row = cache[pos:pos + 1]
             ops.gemv(x, L["wqkv"], bias=L.get("bqkv"), out=row, rms_eps=self.eps)
-            ops.rope_inplace(row, 1, Hq, Hkv, D, 0, Hq * D, pos, self.w["inv_freq"])
+            ops.rope_inplace(row, 1, Hq, Hkv, D, 0, Hq * D, pos, self.w["inv_freq"], interleaved=True)
             o = ops.attention_decode(row[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
                                      n_pos=pos + 1, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5)
             x = ops.gemv(o, L["wo"], residual=x)
@@ -193,7 +210,7 @@ class DecoderEngine:
                         ops.l2_prefetch(L["wgu"], budget - n_wo)
                     joined = torch.cuda.Event()
                     joined.record(self._side_stream)
-            ops.decode_rope_append(stage, cache, pos_dev, Hq, Hkv, D, self.w["inv_freq"])
+            ops.decode_rope_append(stage, cache, pos_dev, Hq, Hkv, D, self.w["inv_freq"], interleaved=True)
             ops.attention_decode_dyn(stage[0, : Hq * D], cache[:, Hq * D: (Hq + Hkv) * D], cache[:, (Hq + Hkv) * D:],
                                      pos_dev, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, out=o)
             if joined is not None:

@@ -60,7 +60,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
          rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None, trace: bool = False,
          splitk=True, ln_in=None, ln_colsum: Optional[torch.Tensor] = None,
-         rowsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         rowsum_out: Optional[torch.Tensor] = None, rope=None) -> torch.Tensor:
     """out[M,Nout] = epi(a[M,K] @ w[N,K]^T); a/w may be row-strided views (last dim contiguous).
     `bn` forces the tile width (tests); 0 = library heuristic.
     `bcast_ptrs`: device pointers of peer buffers (same layout as `out`) that receive every output vector too
@@ -101,6 +101,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         args.rms_nparts = rms_in.numel() // M
         args.rms_inv_dim = 1.0 / K
         args.rms_eps = float(rms_eps)
+    if rope is not None:
+        # (table uint32 [positions, D/2] packed bf16 cos|sin, first position, head width D, number of leading q/k columns):
+        # RoPE applied in the epilogue to adjacent column pairs (weights permuted accordingly, see rope_interleave_rows)
+        tab, pos0, hd, cols = rope
+        _need_cuda(tab)
+        assert tab.dtype == torch.int32 and tab.is_contiguous() and tab.shape[1] == hd // 2 and tab.shape[0] >= pos0 + M
+        args.rope_tab = tab.data_ptr()
+        args.rope_cols, args.rope_D, args.rope_pos0 = int(cols), int(hd), int(pos0)
     if ln_in is not None:
         if rms_in is not None or ln_colsum is None:
             raise ValueError("gemm: ln_in excludes rms_in and needs ln_colsum")
@@ -289,14 +297,15 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, S: i
 
 
 def decode_rope_append(qkv_row: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tensor, Hq: int, Hkv: int, D: int,
-                       inv_freq: torch.Tensor) -> None:
+                       inv_freq: torch.Tensor, interleaved: bool = False) -> None:
     """Graph-replayable: rotate q/k of the fused row at position *pos_dev and append the row to cache[*pos_dev]."""
     _need_cuda(qkv_row, cache, pos_dev, inv_freq)
     _bf16(qkv_row, cache)
     assert qkv_row.is_contiguous() and qkv_row.numel() == (Hq + 2 * Hkv) * D and cache.stride(1) == 1
     assert pos_dev.dtype == torch.int32 and pos_dev.numel() == 1
     check(_lib.load().vl2_decode_rope_append(qkv_row.data_ptr(), cache.data_ptr(), cache.stride(0), pos_dev.data_ptr(),
-                                             Hq, Hkv, D, inv_freq.data_ptr(), _stream()), "vl2_decode_rope_append")
+                                             Hq, Hkv, D, inv_freq.data_ptr(), 1 if interleaved else 0, _stream()),
+          "vl2_decode_rope_append")
 
 
 def attention_decode_dyn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, pos_dev: torch.Tensor, *,
@@ -454,13 +463,31 @@ def conv3d_im2col(x: torch.Tensor, pad: int) -> torch.Tensor:
 
 
 def rope_inplace(qkv: torch.Tensor, S: int, Hq: int, Hkv: int, D: int, q_off: int, k_off: int, pos0: int,
-                 inv_freq: torch.Tensor) -> torch.Tensor:
+                 inv_freq: torch.Tensor, interleaved: bool = False) -> torch.Tensor:
     _need_cuda(qkv, inv_freq)
     _bf16(qkv)
     assert qkv.dim() == 2 and qkv.stride(1) == 1 and inv_freq.dtype == torch.float32 and inv_freq.numel() == D // 2
     check(_lib.load().vl2_rope_inplace(qkv.data_ptr(), qkv.stride(0), S, Hq, Hkv, D, q_off, k_off, pos0,
-                                       inv_freq.data_ptr(), _stream()), "vl2_rope_inplace")
+                                       inv_freq.data_ptr(), 1 if interleaved else 0, _stream()), "vl2_rope_inplace")
     return qkv
+
+
+def rope_interleave_rows(n_heads: int, D: int) -> torch.Tensor:
+    """Row permutation of a q / k projection weight [n_heads*D, K] that makes the RoPE partners (i, i + D/2) of every head
+    adjacent output columns (2i, 2i+1): new_row[h*D + 2i] = old_row[h*D + i], new_row[h*D + 2i + 1] = old_row[h*D + i + D/2]."""
+    i = torch.arange(D // 2)
+    per_head = torch.stack([i, i + D // 2], 1).reshape(-1)                       # [D]
+    return (torch.arange(n_heads)[:, None] * D + per_head[None, :]).reshape(-1)
+
+
+def rope_table(n_pos: int, D: int, theta: float, device) -> torch.Tensor:
+    """[n_pos, D/2] int32: bf16 cos (low half) | bf16 sin (high half) of angle pos * theta^(-2i/D), computed in fp32 and
+    rounded to bf16 as HF does before applying them (HF:mistral/modeling_mistral.py:311-324).  Built once per engine."""
+    inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+    ang = torch.outer(torch.arange(n_pos, dtype=torch.float32), inv)
+    c = ang.cos().to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF
+    sn = ang.sin().to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF
+    return (c | (sn << 16)).to(torch.int32).contiguous().to(device)
 
 
 def embed_splice(ids: torch.Tensor, dst_row: torch.Tensor, table: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
