@@ -227,6 +227,97 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: VideoLLaMA2-72B (Qwen2-72B) decoder, tensor-parallel over the ranks of one box
+# ------------------------------------------------------------------------------------------------------------------
+def bench_tp72b(args, rank, world, dev):
+    """Decoder prefill of the 72B geometry (80 layers, H 8192, I 29568, 64q/8kv heads) sharded tensor-parallel over `world`
+    GPUs (model/tp_decoder.py), S = 1776 synthetic input embeddings -> last-position logits.  The vision stage is not part
+    of this line (the CLIP tower is the 7B configs' tower; the connector at C = 8192 exceeds the depthwise kernel's 4096
+    channels).  Reports whole-job prefill tokens/s, the tensor roofline fraction per GPU and the all-reduce share of the
+    step (the same step timed with the collectives skipped)."""
+    import torch
+    import torch.distributed as dist
+    from videollama2_b200 import presets
+    from videollama2_b200.model.tp_decoder import TPDecoderEngine
+    layers = int(os.environ.get("VL2_TP_LAYERS", "80"))
+    cfg = presets.make_config(dict(presets.QWEN2_72B, num_hidden_layers=layers), FRAMES)
+    fl = presets.flops(cfg, FRAMES, PROMPT)
+    S = fl["S"]
+    eng = TPDecoderEngine(cfg, None)
+    eng.load_state_dict(presets.random_tp_shard(cfg, rank, world, dev), dev, presharded=True)
+    torch.cuda.empty_cache()
+    emb = (0.5 * torch.randn((S, cfg.hidden_size), generator=torch.Generator(device=dev).manual_seed(7), device=dev)).to(torch.bfloat16)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k
+
+    step = lambda: eng.prefill(emb, all_logits=False)[0]
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    t0 = time.time()
+    ms = timed(step, args.steps)
+    clocks = sampler.stop(t0, time.time()) if rank == 0 else None
+    # the same step without the collectives: what the all-reduces cost on the critical path
+    real = eng._all_reduce
+    eng._all_reduce = lambda part: part
+    for _ in range(2):
+        step()
+    ms_noar = timed(step, max(3, args.steps // 2))
+    eng._all_reduce = real
+    # the collective alone: [S, H] bf16 sum over the group, back to back
+    buf = torch.randn((S, cfg.hidden_size), device=dev).to(torch.bfloat16)
+    n_ar = 2 * layers
+    ms_ar = timed(lambda: [dist.all_reduce(buf) for _ in range(n_ar)], 3)
+    logits = step()
+    same = torch.tensor([float(logits.float().abs().sum())], device=dev)
+    lo, hi = same.clone(), same.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        pk = peaks()
+        dec_fl = fl["llm"]
+        per_gpu = dec_fl / world / (ms * 1e-3) / 1e12
+        ar_bytes = S * cfg.hidden_size * 2
+        line = {
+            "metric": METRIC, "value": S / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"VideoLLaMA2-72B (Qwen2-72B geometry, {layers} layers) decoder prefill S={S} (16 frames@336 + "
+                                   f"256-token prompt), last-position logits, tensor-parallel x{world}; vision stage not included",
+                       "frames": FRAMES, "prompt": PROMPT, "seq": S, "parallelism": f"tp{world}", "weights": "device RNG, sharded",
+                       "flops_per_step": dec_fl, "cuda_graphs": False},
+            "llm_prefill_tok_per_s": S / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": pk["bf16_sustained"], "unit": "TFLOP/s per GPU",
+                         "frac": per_gpu / pk["bf16_sustained"], "peak_src": pk["src"] + " sustained", "traffic": None},
+            "tensor_parallel": {"ranks": world, "ms_per_step": ms, "ms_without_all_reduce": ms_noar,
+                                "all_reduce_share_of_step": 1.0 - ms_noar / ms, "all_reduces_per_step": n_ar,
+                                "all_reduce_bytes": ar_bytes, "all_reduce_alone_ms_per_step": ms_ar,
+                                "all_reduce_alone_us_each": ms_ar / n_ar * 1e3,
+                                "all_reduce_busbw_gbs": ar_bytes * 2 * (world - 1) / world / (ms_ar / n_ar * 1e-3) / 1e9,
+                                "logits_identical_on_all_ranks": bool(float(lo) == float(hi)),
+                                "collective": "NCCL all-reduce (torch.distributed), bf16"},
+            "clocks": clocks, "gpu_launches": None, "e2e": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
 def main():
@@ -235,7 +326,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vl2", choices=["vl2", "reference"])
-    ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b", "qwen2_7b_v21"],
+    ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b", "qwen2_7b_v21", "qwen2_72b"],
                     help="qwen2_7b_v21 = the released VideoLLaMA2.1 geometry: SigLIP-so400m@384 tower + stc_connector_v35")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true",
@@ -281,6 +372,12 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    if args.model == "qwen2_72b":       # config 5: tensor-parallel decoder (needs the process group; 8 GPUs for all 80 layers)
+        if world < 2:
+            raise SystemExit("--model qwen2_72b is the tensor-parallel configuration: launch with torchrun, --gpus 2/4/8")
+        bench_tp72b(args, rank, world, dev)
+        dist.destroy_process_group()
+        return
     llm = presets.MISTRAL_7B if args.model == "mistral7b" else presets.QWEN2_7B
     if args.model == "qwen2_7b_v21":
         cfg = presets.make_config(llm, FRAMES, "stc_connector_v35", presets.SIGLIP_SO400M_384)

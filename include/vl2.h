@@ -124,8 +124,10 @@ typedef struct vl2_gemm_args {
    * (projector.py:164-174, the STC connector's sampler): with conv_C > 0, A is NOT a matrix but the
    * activation x bf16 [conv_T, conv_H, conv_W, conv_C]; W is the kernel as [N, 8*conv_C] with K index = tap*C + cin,
    * tap = dt*4 + dh*2 + dw; M must equal To*Ho*Wo and K = 8*conv_C; C rows are the output positions (to, ho, wo) row-major.
-   * The TMA producer gathers each k-block (one tap x 64 channels) of an output line straight from x through a 4-D tensor
-   * map (out-of-bounds = the zero padding): no im2col matrix exists.  lda is ignored.  bias + activation epilogues only. */
+   * The TMA producer gathers each k-block (one tap x 64 channels) of 8 output lines straight from x with ONE box of a 5-D
+   * tensor map over x viewed as [T, H/2, 2, W/2, 2C] (out-of-bounds = the zero padding): no im2col matrix exists.
+   * Up to 16 x 16 output positions per time step; odd H / W only with conv_pad = 0.  lda is ignored.  bias + activation
+   * epilogues only. */
   int32_t conv_C, conv_T, conv_H, conv_W, conv_pad, reserved4;
   /* RoPE in the epilogue of the fused QKV projection (HF:mistral/modeling_mistral.py:51-82 apply_rotary_pos_emb): output
    * columns [0, rope_cols) are q and k heads of width rope_D whose weight rows were permuted at load so that the rotation

@@ -23,7 +23,7 @@ static constexpr int BK = 64;
 static constexpr int kEpiWarps = 8;                       // 2 per TMEM lane quarter: they split the 32-column chunks
 static constexpr int kEpiThreads = kEpiWarps * 32;
 static constexpr int kGemmThreads = 128 + kEpiThreads;    // warps 0..3: TMA / MMA / TMEM alloc / spare
-static constexpr int kConvLine = 16;                      // padded rows per output line of the Conv3d front end (Wo <= 16)
+static constexpr int kConvLine = 16;                      // Conv3d front end: output lines and columns per time step are padded to 16
 
 // PAIR = true: two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 on a 256 x BN tile; each CTA stages its own
 // 128 rows of A and HALF of the B tile, so a k-block costs 16 KB + BN*64 B of smem/L2 traffic per CTA instead of
@@ -72,10 +72,11 @@ struct GemmParams {
   float* ws_partial;      // [tiles past split_first][split_s - 1][tile rows][BN] fp32 partial accumulators
   unsigned* ws_flags;     // [tiles past split_first][2] arrival counters (self-resetting)
   // implicit-GEMM Conv3d(k = s = 2) front end (see vl2.h: conv_C > 0).  A rows are the output positions in a padded
-  // enumeration (to, ho, wo16): kConvLine rows per output line, so that one 128-row tile is 8 whole lines and every line
-  // of a k-block (one tap x 64 channels) is ONE 4-D TMA box over x viewed as [T, H, ceil(W/2), 2C]; the spatial zero
-  // padding and the rows past the end are TMA out-of-bounds fill.  conv_M = real output rows (To*Ho*Wo).
-  int conv_C, conv_pad, conv_Ho, conv_Wo, conv_lines, conv_T, conv_M;
+  // enumeration (to, ho16, wo16): 16 x 16 rows per output time step, so that one 128-row tile is 8 whole output lines of
+  // one time step and a k-block (one tap x 64 channels) of the tile is ONE 5-D TMA box over x viewed as
+  // [T, H/2, 2, W/2, 2C] (the stride-2 walks along H and W become unit walks over the coarse indices at a fixed parity);
+  // the spatial zero padding and the padded rows are TMA out-of-bounds fill.
+  int conv_C, conv_pad, conv_Ho, conv_Wo, conv_To;
   // RoPE in the QKV epilogue (see vl2.h): adjacent output columns (2i, 2i+1) of a head are a rotation pair
   const uint32_t* rope_tab;
   int rope_cols, rope_D, rope_pos0;
@@ -194,63 +195,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t tmem_base = *tmem_base_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    // Dense A: lane 0 issues both loads of a k-block.  Conv3d front end: the A stage is 8 line boxes, issued by lanes
-    // 0..7 in parallel (each lane owns one output line of the tile and keeps its coordinates in registers), B by lane 8;
-    // the whole warp walks the ring together so the waits stay warp-uniform.
-    const bool conv = p.conv_C > 0;
-    if (lane == 0 || conv) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      const bool conv = p.conv_C > 0;
       const int slabs = conv ? p.conv_C / BK : 1;
       for (int item = tile0; item < p.num_items; item += tile_stride) {
         const WorkItem w = decode_item(item, p, num_k_blocks);
         const int m0 = (w.tile % p.num_m_tiles) * kTileM + (int)rank * BM;
         const int n0 = (w.tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
-        // this lane's output line of the tile (conv): input coordinates of tap (0,0,0); out-of-range lines read t = T
-        int t0 = p.conv_T + 2, h0 = 0;
-        if (conv && lane < BM / kConvLine) {
-          const int line = m0 / kConvLine + lane;
-          if (line < p.conv_lines) {
-            const int to = line / p.conv_Ho, ho = line - to * p.conv_Ho;
-            t0 = 2 * to - p.conv_pad;
-            h0 = 2 * ho - p.conv_pad;
-          }
-        }
+        // conv: this 128-row tile = output lines ho_base .. ho_base + 7 of time step `to`
+        const int line0 = m0 / kConvLine, to = line0 / kConvLine, ho_base = line0 % kConvLine;
         int tap = w.kb0 / slabs, slab = w.kb0 - tap * slabs;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (lane == 0) {
-            if (PAIR) {
-              // both CTAs' bytes land on the leader's full barrier
-              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-            } else {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            }
+          if (PAIR) {
+            // both CTAs' bytes land on the leader's full barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           }
+          uint8_t* dst_a = smem_a + stage * Cfg::kStageBytesA;
           if (conv) {
-            __syncwarp();   // expect_tx is posted before any lane's copy can complete
-            if (lane < BM / kConvLine) {
-              // implicit im2col: k-block = (tap, 64-channel slab); w = 2 wo + e with e = dw - pad in {-1, 0, 1}
-              const int dt = tap >> 2, dh = (tap >> 1) & 1, dw = tap & 1;
-              const int e = dw - p.conv_pad;
-              const int pw = e & 1;                     // parity of w -> which half of the merged (pw, C) dimension
-              const int wc0 = (e - pw) / 2;             // first coarse column (-1 for the padded left border)
-              uint8_t* dst = smem_a + stage * Cfg::kStageBytesA + lane * (kConvLine * 128);
-              if (PAIR) tma_load_4d_pair(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + slab * BK, wc0, h0 + dh, t0 + dt);
-              else tma_load_4d(dst, &tmap_a, &full_bar[stage], pw * p.conv_C + slab * BK, wc0, h0 + dh, t0 + dt);
-            } else if (lane == BM / kConvLine) {
-              if (PAIR) tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
-              else tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
-            }
+            // implicit im2col: k-block = (tap, 64-channel slab).  Input index along each axis = 2 * out + e, e = d - pad in
+            // {-1, 0, 1}: parity e & 1, coarse index out + floor(e / 2)  (-1 = the zero-padded border -> out of bounds)
+            const int et = (tap >> 2) - p.conv_pad, eh = ((tap >> 1) & 1) - p.conv_pad, ew = (tap & 1) - p.conv_pad;
+            const int ph = eh & 1, pw = ew & 1;
+            const int c0 = pw * p.conv_C + slab * BK, wc0 = (ew - pw) / 2, hc0 = ho_base + (eh - ph) / 2, t = 2 * to + et;
+            if (PAIR) tma_load_5d_pair(dst_a, &tmap_a, &full_bar[stage], c0, wc0, ph, hc0, t);
+            else tma_load_5d(dst_a, &tmap_a, &full_bar[stage], c0, wc0, ph, hc0, t);
             if (++slab == slabs) { slab = 0; ++tap; }
           } else if (PAIR) {
-            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
-            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+            tma_load_2d_pair(dst_a, &tmap_a, &full_bar[stage], kb * BK, m0);
           } else {
-            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage], kb * BK, m0);
-            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+            tma_load_2d(dst_a, &tmap_a, &full_bar[stage], kb * BK, m0);
           }
+          if (PAIR) tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          else tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -565,9 +547,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int i = 0; i < 8; ++i) {
             const int rr = t_row + 4 * i;
             int gr = rbase + rr;
-            if (p.conv_C > 0) {   // padded (line, wo16) row -> real output row, or nothing for the padding positions
-              const int line = gr / kConvLine, wo = gr - line * kConvLine;
-              gr = (wo < p.conv_Wo && line < p.conv_lines) ? line * p.conv_Wo + wo : p.M;
+            if (p.conv_C > 0) {   // padded (to, ho16, wo16) row -> real output row, or nothing for the padding positions
+              const int wo = gr % kConvLine, ho = (gr / kConvLine) % kConvLine, to = gr / (kConvLine * kConvLine);
+              gr = (wo < p.conv_Wo && ho < p.conv_Ho && to < p.conv_To) ? (to * p.conv_Ho + ho) * p.conv_Wo + wo : p.M;
             }
             if (gr < p.M && t_chunk * 8 < out_span) {
               const uint4 val = lds128(stg + rr * 128 + ((t_chunk ^ (rr & 7)) << 4));
@@ -612,20 +594,22 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   const bool conv = a->conv_C > 0;
   int conv_To = 0, conv_Ho = 0, conv_Wo = 0;
   if (conv) {
-    // x [T,H,W,C] viewed as [T, H, ceil(W/2), 2C]: a tap's stride-2 walk along W is a unit walk over the coarse columns
-    // at channel offset parity*C; H and T are walked one element per box.  Box = 64 channels x one padded output line.
+    // x [T,H,W,C] viewed as [T, H/2, 2, W/2, 2C]: a tap's stride-2 walks along H and W are unit walks over the coarse
+    // indices at fixed parities (the W parity is folded into the channel coordinate: offset parity*C of the merged 2C axis).
+    // Box = 64 channels x 16 coarse columns (one padded output line) x 8 coarse rows (the tile's 8 output lines).
     const int p_ = a->conv_pad;
     conv_To = (a->conv_T + 2 * p_ - 2) / 2 + 1;
     conv_Ho = (a->conv_H + 2 * p_ - 2) / 2 + 1;
     conv_Wo = (a->conv_W + 2 * p_ - 2) / 2 + 1;
-    // odd W without padding (SigLIP 27 x 27, stc_connector_v35): the last coarse column would pair w = W-1 with the next
-    // row's first pixel; no stored output needs it, so it is declared out of bounds (zero fill, no read past the tensor)
+    // odd H / W without padding (SigLIP 27 x 27, stc_connector_v35): the last coarse index would pair the last pixel with
+    // the first one of the next row / frame; no stored output needs it, so it is declared out of bounds (zero fill)
     const uint64_t wcols = (a->conv_W % 2 == 1 && p_ == 0) ? (uint64_t)a->conv_W / 2 : (uint64_t)(a->conv_W + 1) / 2;
-    uint64_t dims[4] = {(uint64_t)2 * a->conv_C, wcols, (uint64_t)a->conv_H, (uint64_t)a->conv_T};
-    uint64_t str[3] = {(uint64_t)2 * a->conv_C * 2, (uint64_t)a->conv_W * a->conv_C * 2,
-                       (uint64_t)a->conv_H * a->conv_W * a->conv_C * 2};
-    uint32_t box[4] = {BK, (uint32_t)kConvLine, 1, 1};
-    int rc = make_tmap_bf16(&ta, a->A, 4, dims, str, box);
+    const uint64_t hrows = (a->conv_H % 2 == 1 && p_ == 0) ? (uint64_t)a->conv_H / 2 : (uint64_t)(a->conv_H + 1) / 2;
+    const uint64_t C_ = (uint64_t)a->conv_C, W_ = (uint64_t)a->conv_W, H_ = (uint64_t)a->conv_H;
+    uint64_t dims[5] = {2 * C_, wcols, 2, hrows, (uint64_t)a->conv_T};
+    uint64_t str[4] = {2 * C_ * 2, W_ * C_ * 2, 2 * W_ * C_ * 2, H_ * W_ * C_ * 2};
+    uint32_t box[5] = {BK, (uint32_t)kConvLine, 1, (uint32_t)(BM / kConvLine), 1};
+    int rc = make_tmap_bf16(&ta, a->A, 5, dims, str, box);
     if (rc) return rc;
   } else {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
@@ -653,9 +637,8 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   for (int i = 0; i < 8; ++i) p.bcast[i] = reinterpret_cast<__nv_bfloat16*>(i < a->n_bcast ? a->bcast_out[i] : nullptr);
   const int tile_m = PAIR ? 2 * BM : BM;
   p.rope_tab = a->rope_tab; p.rope_cols = a->rope_cols; p.rope_D = a->rope_D; p.rope_pos0 = a->rope_pos0;
-  p.conv_C = conv ? a->conv_C : 0; p.conv_pad = a->conv_pad; p.conv_Ho = conv_Ho; p.conv_Wo = conv_Wo;
-  p.conv_lines = conv_To * conv_Ho; p.conv_T = a->conv_T; p.conv_M = a->M;
-  const int m_rows = conv ? conv_To * conv_Ho * kConvLine : a->M;     // rows of the (padded) A enumeration
+  p.conv_C = conv ? a->conv_C : 0; p.conv_pad = a->conv_pad; p.conv_Ho = conv_Ho; p.conv_Wo = conv_Wo; p.conv_To = conv_To;
+  const int m_rows = conv ? conv_To * kConvLine * kConvLine : a->M;     // rows of the (padded) A enumeration
   p.num_m_tiles = (m_rows + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + BN - 1) / BN;
   VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR>), Cfg::kSmemBytes);
@@ -853,15 +836,17 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
     VL2_REQUIRE(a->conv_T > 0 && a->conv_H > 0 && a->conv_W > 0 && (p_ == 0 || p_ == 1) && a->conv_C % 64 == 0,
                 VL2_E_BADSHAPE, "vl2_gemm_bf16: conv front end needs T,H,W > 0, pad in {0,1}, C %% 64 == 0");
     const int To = (a->conv_T + 2 * p_ - 2) / 2 + 1, Ho = (a->conv_H + 2 * p_ - 2) / 2 + 1, Wo = (a->conv_W + 2 * p_ - 2) / 2 + 1;
-    VL2_REQUIRE(a->conv_W % 2 == 0 || p_ == 0, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: conv front end: odd W needs pad 0");
-    VL2_REQUIRE(To > 0 && Ho > 0 && Wo > 0 && Wo <= kConvLine, VL2_E_UNSUPPORTED,
-                "vl2_gemm_bf16: conv front end supports up to %d output columns per line (got %d)", kConvLine, Wo);
+    VL2_REQUIRE((a->conv_W % 2 == 0 && a->conv_H % 2 == 0) || p_ == 0, VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: conv front end: odd H / W needs pad 0");
+    VL2_REQUIRE(To > 0 && Ho > 0 && Wo > 0 && Wo <= kConvLine && Ho <= kConvLine, VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: conv front end supports up to %d x %d output positions per time step (got %d x %d)", kConvLine,
+                kConvLine, Ho, Wo);
     VL2_REQUIRE(a->K == 8 * a->conv_C && a->M == To * Ho * Wo, VL2_E_BADSHAPE,
                 "vl2_gemm_bf16: conv front end needs K == 8*C and M == To*Ho*Wo (M=%d, expected %d)", a->M, To * Ho * Wo);
     VL2_REQUIRE(a->residual == nullptr && a->row_scale == nullptr && a->rms_sumsq_in == nullptr && a->sumsq_out == nullptr &&
                     !a->out_f32 && a->act != VL2_ACT_SWIGLU && a->n_bcast == 0 && a->mc_out == nullptr,
                 VL2_E_UNSUPPORTED, "vl2_gemm_bf16: the conv front end supports bias + activation epilogues, bf16 output");
-    m_plan = To * Ho * kConvLine;
+    m_plan = To * kConvLine * kConvLine;
   }
   TileChoice t = choose_tile(m_plan, a->N, a->K, sm_count(), pair_enabled(),
                              splitk_enabled() && a->splitk_ws != nullptr && a->conv_C == 0);

@@ -126,10 +126,10 @@ class STCConnector:
         T, H, W, C = x.shape
         p = self.padding
         To, Ho, Wo = (T + 2 * p - 2) // 2 + 1, (H + 2 * p - 2) // 2 + 1, (W + 2 * p - 2) // 2 + 1
-        if Wo <= 16 and C % 64 == 0 and (W % 2 == 0 or p == 0):
+        if Wo <= 16 and Ho <= 16 and C % 64 == 0 and ((W % 2 == 0 and H % 2 == 0) or p == 0):
             # implicit GEMM: the TMA producer of vl2_gemm_bf16 gathers the taps from x itself (no im2col matrix)
             return ops.conv3d_k2s2(x.contiguous(), self.w["wc"], bias=self.w["bc"], act=ops.ACT_SILU, pad=p).view(To, Ho, Wo, C)
-        A = ops.conv3d_im2col(x.contiguous(), p)       # wide frames (> 16 output columns): explicit tap gather
+        A = ops.conv3d_im2col(x.contiguous(), p)       # frames beyond 16 x 16 output positions: explicit tap gather
         return ops.gemm(A, self.w["wc"], bias=self.w["bc"], act=ops.ACT_SILU).view(To, Ho, Wo, C)
 
     def run_s2(self, y: torch.Tensor) -> torch.Tensor:

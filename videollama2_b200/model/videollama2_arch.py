@@ -18,14 +18,18 @@ from .projector import build_vision_projector
 class Videollama2MetaModel:
     """Holds the tower, the projector and the decoder (reference: Videollama2MetaModel + the HF *Model it is mixed into)."""
 
-    def __init__(self, config):
+    def __init__(self, config, tp_group=None):
         self.config = config
         self.vision_tower = None
         self.mm_projector = None
         if getattr(config, "mm_vision_tower", None) is not None:
             self.vision_tower = build_vision_tower(config)
             self.mm_projector = build_vision_projector(config)
-        self.decoder = DecoderEngine(config)
+        if tp_group is not None:        # tensor-parallel decoder over the ranks of `tp_group` (True = the default group)
+            from .tp_decoder import TPDecoderEngine
+            self.decoder = TPDecoderEngine(config, None if tp_group is True else tp_group)
+        else:
+            self.decoder = DecoderEngine(config)
 
     def get_vision_tower(self):
         vision_tower = getattr(self, "vision_tower", None)
@@ -104,7 +108,8 @@ class Videollama2MetaForCausalLM:
     def enable_frame_parallel(self, group=None, shard_s1: bool = True, llm_rank: int = 0):
         """Shard the per-frame part of `encode_images_or_videos` (ViT + first RegStage) over the ranks of `group` and
         all-gather before the connector's Conv3d.  Every rank must then call encode / forward / generate with identical
-        inputs; ranks other than `llm_rank` return None from forward / generate once the collective is done.
+        inputs; ranks other than `llm_rank` return None from forward / generate once the collective is done
+        (`llm_rank=None`: every rank goes on to the decoder - the tensor-parallel configuration).
         `group=None` with an initialised default process group uses WORLD; call with `group=False` to switch it off."""
         from .. import parallel
         if group is False:
@@ -116,7 +121,8 @@ class Videollama2MetaForCausalLM:
     def _vision_only_rank(self, images) -> bool:
         """True on a frame-parallel rank that does not run the decoder: it takes part in the vision collective and stops."""
         fp = getattr(self, "_frame_parallel", None)
-        if fp is None or fp.world == 1 or fp.rank == fp.llm_rank or images is None or self.get_vision_tower() is None:
+        if fp is None or fp.world == 1 or fp.llm_rank is None or fp.rank == fp.llm_rank or images is None \
+                or self.get_vision_tower() is None:
             return False
         self.encode_images_or_videos(images)
         return True

@@ -26,17 +26,19 @@ class CausalLMOutput(SimpleNamespace):
 class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
     config_class = Videollama2MistralConfig
 
-    def __init__(self, config, **kwargs):
+    def __init__(self, config, tp_group=None, **kwargs):
         self.config = config
-        self.model = Videollama2MetaModel(config)
+        self.model = Videollama2MetaModel(config, tp_group=tp_group)
         self.vocab_size = config.vocab_size
         self._device = torch.device("cpu")
 
     # ---- construction -----------------------------------------------------------------------------------------
     @classmethod
-    def from_state_dict(cls, config, state_dict: Dict[str, torch.Tensor], device="cuda"):
-        """Build from HF-named weights (the reference's checkpoint format) and repack for the kernels."""
-        self = cls(config)
+    def from_state_dict(cls, config, state_dict: Dict[str, torch.Tensor], device="cuda", tp_group=None):
+        """Build from HF-named weights (the reference's checkpoint format) and repack for the kernels.
+        `tp_group` (a process group, or True for the default one): shard the decoder tensor-parallel over its ranks
+        (model/tp_decoder.py); every rank passes the same full state dict and keeps its slices."""
+        self = cls(config, tp_group=tp_group)
         self.load_state_dict(state_dict, device)
         return self
 

@@ -20,6 +20,48 @@ QWEN2_7B = dict(model_type="videollama2_qwen2", hidden_size=3584, intermediate_s
                 attention_bias=True)
 
 
+# Qwen/Qwen2-72B-Instruct (BASELINE.json configs[4]: VideoLLaMA2-72B; SURVEY.md §8a row "HF Qwen2*")
+QWEN2_72B = dict(model_type="videollama2_qwen2", hidden_size=8192, intermediate_size=29568, num_hidden_layers=80,
+                 num_attention_heads=64, num_key_value_heads=8, vocab_size=152064, rms_norm_eps=1e-6, rope_theta=1e6,
+                 attention_bias=True)
+
+
+def random_tp_shard(cfg: Videollama2Config, rank: int, world: int, device, seed: int = 20240603):
+    """This rank's slices of a random decoder checkpoint of `cfg` (HF names, shapes of tp_decoder.shard_state_dict), drawn on
+    the device: the 72B model's 145 GB never exist in one place.  Replicated tensors (embedding, norms) use a rank-independent
+    generator so that every rank holds the same values."""
+    import torch
+    from .model.tp_decoder import shard_plan
+    plan = shard_plan(cfg, rank, world)
+    H, D = cfg.hidden_size, plan["D"]
+    g_loc = torch.Generator(device=device).manual_seed(seed + 1000 * (rank + 1))
+    g_rep = torch.Generator(device=device).manual_seed(seed)
+
+    def w(shape, fan_in, g):
+        return (torch.randn(shape, generator=g, device=device, dtype=torch.float32) * fan_in ** -0.5).to(torch.bfloat16)
+
+    def gain():
+        return (1.0 + 0.1 * torch.randn((H,), generator=g_rep, device=device, dtype=torch.float32)).to(torch.bfloat16)
+
+    sd = {"model.embed_tokens.weight": (0.05 * torch.randn((cfg.vocab_size, H), generator=g_rep, device=device,
+                                                            dtype=torch.float32)).to(torch.bfloat16)}
+    for i in range(cfg.num_hidden_layers):
+        p = f"model.layers.{i}."
+        sd[p + "input_layernorm.weight"] = gain()
+        sd[p + "post_attention_layernorm.weight"] = gain()
+        for nm, n in (("q_proj", plan["Hq"] * D), ("k_proj", plan["Hkv"] * D), ("v_proj", plan["Hkv"] * D)):
+            sd[p + f"self_attn.{nm}.weight"] = w((n, H), H, g_loc)
+            if cfg.attention_bias:
+                sd[p + f"self_attn.{nm}.bias"] = (0.02 * torch.randn((n,), generator=g_loc, device=device)).to(torch.bfloat16)
+        sd[p + "self_attn.o_proj.weight"] = w((H, plan["Hq"] * D), cfg.num_attention_heads * D, g_loc)
+        sd[p + "mlp.gate_proj.weight"] = w((plan["I"], H), H, g_loc)
+        sd[p + "mlp.up_proj.weight"] = w((plan["I"], H), H, g_loc)
+        sd[p + "mlp.down_proj.weight"] = w((H, plan["I"]), cfg.intermediate_size, g_loc)
+    sd["model.norm.weight"] = gain()
+    sd["lm_head.weight"] = w((plan["V"], H), H, g_loc)
+    return sd
+
+
 def make_config(llm: dict, frames: int, projector: str = "stc_connector", vision: dict = CLIP_L_336) -> Videollama2Config:
     vc = VisionConfig(**vision)
     siglip = "siglip" in vc.model_type
