@@ -102,111 +102,3 @@ class FrameParallel:
             return proj.forward_from_s1(full.view(b, t, hw, hw, H)).to(frames.dtype)
         feats = all_gather_frames(local, F, self.group)
         return model.temporal_aggregator(feats.view(b, t, n, C))
-
-
-class FusedFrameGather:
-    """Frame-parallel ViT whose LAST GEMM writes its output tiles straight into every rank's gather buffer.
-
-    The buffer [F*(np+1), C] lives in symmetric memory (torch.distributed._symmetric_memory: same allocation mapped
-    into every process of the node over NVLink/NVSwitch).  Rank r computes frames [a_r, b_r) and its final fc2 GEMM
-    (vl2_gemm_bf16 with bcast_out / mc_out) stores each output vector to its own rows of the local buffer AND to the
-    same rows of the peers' buffers (P2P stores, or one multimem.st through the switch when multicast is available),
-    tile by tile while the remaining tiles are still being computed.  A symmetric-memory barrier then stands in for the
-    collective's completion.  No NCCL kernel, no separate copy pass."""
-
-    def __init__(self, tower, num_frames: int, group=None, use_multicast: bool = True):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.tower = tower
-        self.group = group if group is not None else dist.group.WORLD
-        self.rank = dist.get_rank(self.group)
-        self.world = dist.get_world_size(self.group)
-        self.F = num_frames
-        self.S = tower.seq_len              # tokens per frame in the residual stream (CLIP: patches + CLS)
-        self.C = tower.hidden_size
-        dev = tower.device
-        self.buf = symm_mem.empty((num_frames * self.S, self.C), dtype=torch.bfloat16, device=dev)
-        self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        mc = 0
-        if use_multicast:
-            try:
-                mc = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support(dev.type, dev.index) else 0
-            except Exception:
-                mc = 0
-        self.mc_ptr = mc
-
-    def encode(self, frames: torch.Tensor) -> torch.Tensor:
-        """frames [F,3,H,W] (identical on every rank) -> [F, np, C] on every rank."""
-        if frames.shape[0] != self.F:
-            raise ValueError(f"FusedFrameGather was built for {self.F} frames, got {frames.shape[0]}")
-        a, b = frame_shard(self.F, self.rank, self.world)
-        row_bytes = self.C * 2
-        self.hdl.barrier(channel=0)              # every rank finished reading the previous result (buffer reuse)
-        if b > a:
-            local = self.buf[a * self.S: b * self.S]
-            off = a * self.S * row_bytes
-            if self.mc_ptr:
-                self.tower.hidden_states(frames[a:b].to(torch.bfloat16).contiguous(), last_out=local,
-                                         mc_ptr=self.mc_ptr + off)
-            else:
-                peers = [ptr + off for r, ptr in enumerate(self.ptrs) if r != self.rank]
-                self.tower.hidden_states(frames[a:b].to(torch.bfloat16).contiguous(), last_out=local, bcast_ptrs=peers)
-        self.hdl.barrier(channel=1)              # all ranks' tiles have landed everywhere
-        return self.tower.feature_select(self.buf.view(self.F, self.S, self.C)).contiguous()
-
-
-def bench_frame_parallel(model, px_dev: torch.Tensor, rank: int, world: int, dev, iters: int = 5,
-                         fused: bool = True) -> dict:
-    """Device-timed (CUDA events, max over ranks) ViT(shard) + all-gather for one 16-frame video."""
-    tower = model.get_vision_tower()
-    F = px_dev.shape[0]
-    for _ in range(2):
-        encode_frames_sharded(tower, px_dev)
-    times = []
-    for _ in range(iters):
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a, b = frame_shard(F, rank, world)
-        e0.record()
-        local = tower(px_dev[a:b])
-        e1.record()
-        all_gather_frames(local, F)
-        e2.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1), e1.elapsed_time(e2)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        times.append(t.tolist())
-    times.sort(key=lambda x: x[0])
-    tot, vit, gat = times[len(times) // 2]
-    if not fused:
-        return {"ranks": world, "frames_per_rank": shard_sizes(F, world), "vit_shard_plus_gather_ms": tot,
-                "vit_shard_ms": vit, "all_gather_ms": gat, "frames_per_s": F / (tot * 1e-3),
-                "gather_bytes": int(F * tower.num_patches * tower.hidden_size * 2)}
-    fused = None
-    try:
-        import os
-        fg = FusedFrameGather(tower, F, use_multicast=os.environ.get("VL2_BENCH_MULTICAST", "0") == "1")
-        ref = encode_frames_sharded(tower, px_dev)
-        got = fg.encode(px_dev)
-        exact = bool(torch.equal(got, ref))
-        ft = []
-        for _ in range(iters):
-            dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fg.encode(px_dev)
-            e1.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ft.append(float(t.item()))
-        ft.sort()
-        fused = {"ms": ft[len(ft) // 2], "frames_per_s": F / (ft[len(ft) // 2] * 1e-3), "bit_exact_vs_nccl": exact,
-                 "multicast": bool(fg.mc_ptr)}
-    except Exception as e:  # symmetric memory may be unavailable on a given box: report, do not fail the bench
-        fused = {"error": repr(e)[:300]}
-    return {"ranks": world, "fused_epilogue_gather": fused, "frames_per_rank": shard_sizes(F, world), "vit_shard_plus_gather_ms": tot, "vit_shard_ms": vit,
-            "all_gather_ms": gat, "frames_per_s": F / (tot * 1e-3),
-            "gather_bytes": int(F * tower.num_patches * tower.hidden_size * 2)}
