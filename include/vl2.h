@@ -299,6 +299,31 @@ typedef struct vl2_preprocess_args {
 size_t vl2_preprocess_workspace(const vl2_preprocess_args* args);
 int vl2_preprocess_frames(const vl2_preprocess_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-parallel decoder (BASELINE.json configs[4], SURVEY.md §8e "TP decoder"; no counterpart in the reference, whose
+ * multi-GPU loading is accelerate's device_map="auto", videollama2/model/__init__.py:48,54):
+ * all-reduce of the row-parallel GEMMs' bf16 partials [S,H] over the ranks of one NVSwitch domain, fused with the row sums
+ * of squares the next folded RMSNorm needs, as ONE kernel with its cross-GPU barriers inside.  All buffers are symmetric
+ * memory (the same allocation on every rank, peer-mapped over NVLink): part[r] / xout[r] / stats[r] / pads[r] are rank r's
+ * buffers as seen from THIS rank; *_mc are the NVSwitch multicast addresses of the same buffers (NULL = no multicast: the
+ * kernel uses peer loads and stores instead of multimem.ld_reduce / multimem.st).  Rank r reduces rows
+ * [r*ceil(S/world), ...) and writes them to every rank.  pads: >= 17 zero-initialised uint32 per rank; `epoch` = 1, 2, 3, ...
+ * counts the calls that used these pads (the same on every rank).  Not CUDA-graph replayable (epoch is a launch argument).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vl2_tp_allreduce_args {
+  const void* part[8];
+  void* xout[8];
+  float* stats[8];
+  uint32_t* pads[8];
+  const void* part_mc;
+  void* xout_mc;
+  float* stats_mc;
+  int32_t rank, world, S, H;
+  uint32_t epoch;
+  uint32_t reserved;
+} vl2_tp_allreduce_args;
+int vl2_tp_allreduce_stats(const vl2_tp_allreduce_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

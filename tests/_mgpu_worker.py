@@ -84,6 +84,16 @@ def main():
         if not (b.shape == a.shape and err < 1e-2):
             ok = False
             msgs.append(f"TP logits differ ({name}): rel {err:.3e}")
+        # the library's own all-reduce kernel (multimem / peer path) against the NCCL path
+        for mc in (True, False):
+            tp.get_model().decoder.enable_nvls_all_reduce(256, use_multicast=mc)
+            for _ in range(2):                              # twice: buffer / epoch reuse
+                c = tp(input_ids=ids, attention_mask=torch.ones_like(ids), images=images).logits
+            e2 = rel(c, b)
+            if not e2 < 2e-3:
+                ok = False
+                msgs.append(f"own all-reduce kernel differs from the NCCL path ({name}, multicast={mc}): rel {e2:.3e}")
+        tp.get_model().decoder._nvls = None
         ta = single.generate(ids, images=images, max_new_tokens=4, do_sample=False)
         tb = tp.generate(ids, images=images, max_new_tokens=4, do_sample=False)
         allb = [torch.empty_like(tb) for _ in range(world)]

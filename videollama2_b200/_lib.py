@@ -16,7 +16,7 @@ SYMBOLS = [
     "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq", "vl2_row_stats",
     "vl2_patch_im2col", "vl2_clip_embed_finish",
     "vl2_dwconv3x3_ln_silu", "vl2_se_scale", "vl2_conv3d_im2col",
-    "vl2_rope_inplace", "vl2_embed_splice",
+    "vl2_rope_inplace", "vl2_embed_splice", "vl2_tp_allreduce_stats",
 ]
 
 ACT_NONE, ACT_QUICK_GELU, ACT_SILU, ACT_GELU_ERF, ACT_SWIGLU, ACT_GELU_TANH = 0, 1, 2, 3, 4, 5
@@ -48,6 +48,15 @@ class AttnArgs(C.Structure):
         ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
         ("B", C.c_int32), ("S", C.c_int32), ("Hq", C.c_int32), ("Hkv", C.c_int32), ("D", C.c_int32),
         ("causal", C.c_int32), ("scale", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+class TpAllReduceArgs(C.Structure):
+    _fields_ = [
+        ("part", C.c_void_p * 8), ("xout", C.c_void_p * 8), ("stats", C.c_void_p * 8), ("pads", C.c_void_p * 8),
+        ("part_mc", C.c_void_p), ("xout_mc", C.c_void_p), ("stats_mc", C.c_void_p),
+        ("rank", C.c_int32), ("world", C.c_int32), ("S", C.c_int32), ("H", C.c_int32),
+        ("epoch", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -99,6 +108,7 @@ def load() -> C.CDLL:
         "vl2_conv3d_im2col": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "vl2_rope_inplace": [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp],
         "vl2_embed_splice": [vp, vp, i32, vp, i64, vp, i32, vp],
+        "vl2_tp_allreduce_stats": [C.POINTER(TpAllReduceArgs), vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

@@ -107,6 +107,7 @@ class TPDecoderEngine(DecoderEngine):
         super().__init__(_LocalConfig(config, self.plan))
         self.D = self.plan["D"]                      # head width comes from the GLOBAL geometry (hidden / all heads)
         self.graph_decode = False                    # collectives run eagerly between kernels
+        self._nvls = None
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device, presharded: bool = False) -> "TPDecoderEngine":
         """`sd`: the full HF-named state dict (sliced here), or with presharded=True this rank's slices already."""
@@ -114,11 +115,29 @@ class TPDecoderEngine(DecoderEngine):
         return super().load_state_dict(local, device)
 
     # ---- collectives ---------------------------------------------------------------------------------------------
+    def enable_nvls_all_reduce(self, max_rows: int, use_multicast: bool = True):
+        """Route the prefill all-reduces through the library's own kernel (parallel.NvlsAllReduce: in-switch reduction +
+        RMSNorm statistics + broadcast in one launch) instead of NCCL + a statistics kernel.  The row-parallel GEMMs then
+        write their partials straight into the symmetric buffer."""
+        from ..parallel import NvlsAllReduce
+        self._nvls = NvlsAllReduce(max_rows, self.H, self.device, self.group, use_multicast) if self.world > 1 else None
+        return self
+
     def _all_reduce(self, part: torch.Tensor) -> torch.Tensor:
         """Sum of the ranks' partial [S, H] tensors, in place (rank 0's partial already carries the residual)."""
         if self.world > 1:
             dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
         return part
+
+    def _reduce_stats(self, gemm_into):
+        """Run a row-parallel GEMM (`gemm_into(out)` writes the partial) and return (reduced stream, its row sums of squares)."""
+        nv = getattr(self, "_nvls", None)
+        S = self._cur_rows
+        if nv is not None and S <= nv.max_rows:
+            gemm_into(nv.part[:S])
+            return nv.reduce(S)
+        x = self._all_reduce(gemm_into(None))
+        return x, ops.row_sumsq(x)
 
     def _gather_logits(self, local: torch.Tensor) -> torch.Tensor:
         """[rows, V/G] per rank -> [rows, V] (vocab shards are contiguous row ranges of lm_head)."""
@@ -136,10 +155,11 @@ class TPDecoderEngine(DecoderEngine):
                        rope=(self.rope_table(pos0 + S), pos0, D, (Hq + Hkv) * D))
         o = ops.attention(qkv[:, : Hq * D], qkv[:, Hq * D: (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:], B=1, S=S, Hq=Hq,
                           Hkv=Hkv, D=D, causal=True, scale=D ** -0.5)
-        x = self._all_reduce(ops.gemm(o, L["wo"], residual=res))
-        h = ops.gemm(x, L["wgu"], act=ops.ACT_SWIGLU, rms_in=ops.row_sumsq(x), rms_eps=self.eps)
-        x = self._all_reduce(ops.gemm(h, L["wd"], residual=res if res is None else x))
-        return x, ops.row_sumsq(x)
+        self._cur_rows = S
+        x, ss = self._reduce_stats(lambda out: ops.gemm(o, L["wo"], residual=res, out=out))
+        h = ops.gemm(x, L["wgu"], act=ops.ACT_SWIGLU, rms_in=ss, rms_eps=self.eps)
+        res2 = x if self.rank == 0 else None
+        return self._reduce_stats(lambda out: ops.gemm(h, L["wd"], residual=res2, out=out))
 
     def prefill(self, embeds: torch.Tensor, all_logits: bool = False, keep_cache: bool = False,
                 max_len: Optional[int] = None, _no_graph: bool = False, tap=None):

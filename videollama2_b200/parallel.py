@@ -102,3 +102,75 @@ class FrameParallel:
             return proj.forward_from_s1(full.view(b, t, hw, hw, H)).to(frames.dtype)
         feats = all_gather_frames(local, F, self.group)
         return model.temporal_aggregator(feats.view(b, t, n, C))
+
+
+class NvlsAllReduce:
+    """All-reduce of the tensor-parallel decoder's partial sums as ONE kernel over NVLink / NVSwitch (csrc/tp_allreduce.cu):
+    in-switch reduction (multimem.ld_reduce, fp32 accumulation) of the ranks' bf16 partials, the row sums of squares the
+    next folded RMSNorm needs, and the broadcast of both (multimem.st) - with the cross-GPU barriers inside the kernel.
+    Buffers live in symmetric memory (torch.distributed._symmetric_memory): `part` is where the row-parallel GEMM writes
+    its output, `out[i]` (two, alternating) receive the reduced stream.  Falls back to peer loads / stores when the
+    allocation has no multicast mapping."""
+
+    def __init__(self, max_rows: int, hidden: int, device, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("NvlsAllReduce supports up to 8 ranks (one NVSwitch domain)")
+        self.max_rows, self.hidden = max_rows, hidden
+        dev = torch.device(device)
+
+        def sym(shape, dtype):
+            t = symm_mem.empty(shape, dtype=dtype, device=dev)
+            t.zero_()
+            return t, symm_mem.rendezvous(t, self.group)
+
+        self.part, self._h_part = sym((max_rows, hidden), torch.bfloat16)
+        self.out = []
+        self._h_out = []
+        self.stats = []
+        self._h_stats = []
+        for _ in range(2):
+            t, h = sym((max_rows, hidden), torch.bfloat16)
+            self.out.append(t)
+            self._h_out.append(h)
+            t, h = sym((max_rows,), torch.float32)
+            self.stats.append(t)
+            self._h_stats.append(h)
+        self.pads, self._h_pads = sym((32,), torch.int32)
+        self.multicast = False
+        if use_multicast:
+            try:
+                self.multicast = all(int(h.multicast_ptr) != 0 for h in [self._h_part] + self._h_out + self._h_stats)
+            except Exception:
+                self.multicast = False
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)        # every rank's pads are zeroed before anybody signals
+        self.epoch = 0
+        self.turn = 0
+
+    def reduce(self, rows: int):
+        """Sum `self.part[:rows]` over the ranks.  Returns (x [rows, H] bf16, sumsq [rows, 1] fp32), valid until the call
+        after next (the two output buffers alternate)."""
+        from . import _lib
+        import ctypes as C
+        if rows > self.max_rows:
+            raise ValueError(f"{rows} rows exceed the symmetric buffers ({self.max_rows})")
+        i = self.turn
+        self.turn ^= 1
+        self.epoch += 1
+        a = _lib.TpAllReduceArgs(rank=self.rank, world=self.world, S=rows, H=self.hidden, epoch=self.epoch)
+        for r in range(self.world):
+            a.part[r] = int(self._h_part.buffer_ptrs[r])
+            a.xout[r] = int(self._h_out[i].buffer_ptrs[r])
+            a.stats[r] = int(self._h_stats[i].buffer_ptrs[r])
+            a.pads[r] = int(self._h_pads.buffer_ptrs[r])
+        if self.multicast:
+            a.part_mc = int(self._h_part.multicast_ptr)
+            a.xout_mc = int(self._h_out[i].multicast_ptr)
+            a.stats_mc = int(self._h_stats[i].multicast_ptr)
+        _lib.check(_lib.load().vl2_tp_allreduce_stats(C.byref(a), torch.cuda.current_stream().cuda_stream),
+                   "vl2_tp_allreduce_stats")
+        return self.out[i][:rows], self.stats[i][:rows].view(rows, 1)
