@@ -275,7 +275,8 @@ def bench_tp72b(args, rank, world, dev):
     ms = ms_nccl
     clocks = None
     try:
-        eng.enable_nvls_all_reduce(S, use_multicast=os.environ.get("VL2_TP_MULTICAST", "1") == "1")
+        eng.enable_nvls_all_reduce(S, use_multicast=os.environ.get("VL2_TP_MULTICAST", "1") == "1",
+                                   inswitch_reduce=os.environ.get("VL2_TP_INSWITCH", "0") == "1")
         for _ in range(max(3, args.warmup)):
             step()
         sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
@@ -285,7 +286,8 @@ def bench_tp72b(args, rank, world, dev):
         ms_nvls = timed(step, args.steps)
         clocks = sampler.stop(t0, time.time()) if rank == 0 else None
         lg = step().float()
-        nvls = {"ms_per_step": ms_nvls, "multicast": bool(eng._nvls.multicast),
+        nvls = {"ms_per_step": ms_nvls, "multicast_broadcast": bool(eng._nvls.multicast),
+                "inswitch_reduce": bool(eng._nvls.inswitch_reduce),
                 "rel_l2_vs_nccl_path": float((lg - logits_nccl).norm() / logits_nccl.norm()),
                 "same_argmax_as_nccl_path": bool(int(lg.argmax()) == int(logits_nccl.argmax()))}
         ms = ms_nvls
@@ -336,7 +338,7 @@ def bench_tp72b(args, rank, world, dev):
                                 "all_reduce_busbw_gbs": ar_bytes * 2 * (world - 1) / world / (ms_ar / n_ar * 1e-3) / 1e9,
                                 "logits_identical_on_all_ranks": bool(float(lo) == float(hi)),
                                 "ms_per_step_nccl_path": ms_nccl, "own_kernel_path": nvls,
-                                "collective": "vl2_tp_allreduce_stats (multimem.ld_reduce + multimem.st, barriers in-kernel) when "
+                                "collective": "vl2_tp_allreduce_stats (peer-load reduce in rank order + multimem.st broadcast, barriers in-kernel) when "
                                               "available, else NCCL all-reduce + vl2_row_sumsq; `ms_per_step` is the faster path "
                                               "that ran" if nvls and "error" not in nvls else "NCCL all-reduce (torch.distributed), bf16"},
             "clocks": clocks, "gpu_launches": None, "e2e": None, "cpu_baseline": None,

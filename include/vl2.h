@@ -306,7 +306,7 @@ int vl2_preprocess_frames(const vl2_preprocess_args* args, void* stream);
  * of squares the next folded RMSNorm needs, as ONE kernel with its cross-GPU barriers inside.  All buffers are symmetric
  * memory (the same allocation on every rank, peer-mapped over NVLink): part[r] / xout[r] / stats[r] / pads[r] are rank r's
  * buffers as seen from THIS rank; *_mc are the NVSwitch multicast addresses of the same buffers (NULL = no multicast: the
- * kernel uses peer loads and stores instead of multimem.ld_reduce / multimem.st).  Rank r reduces rows
+ * kernel broadcasts with peer stores instead of multimem.st).  Rank r reduces rows
  * [r*ceil(S/world), ...) and writes them to every rank.  pads: >= 17 zero-initialised uint32 per rank; `epoch` = 1, 2, 3, ...
  * counts the calls that used these pads (the same on every rank).  Not CUDA-graph replayable (epoch is a launch argument).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -320,7 +320,10 @@ typedef struct vl2_tp_allreduce_args {
   float* stats_mc;
   int32_t rank, world, S, H;
   uint32_t epoch;
-  uint32_t reserved;
+  uint32_t inswitch_reduce; /* 1: reduce inside the NVSwitch (multimem.ld_reduce; needs *_mc).  Off by default: measured on
+                               B200 the switch does not round bf16 sums to nearest (1-ulp differences on ~19 % of the
+                               elements), so the default reduces with peer loads (exact fp32 accumulation) and uses the
+                               switch for the broadcast only */
 } vl2_tp_allreduce_args;
 int vl2_tp_allreduce_stats(const vl2_tp_allreduce_args* args, void* stream);
 

@@ -90,7 +90,7 @@ def main():
             for _ in range(2):                              # twice: buffer / epoch reuse
                 c = tp(input_ids=ids, attention_mask=torch.ones_like(ids), images=images).logits
             e2 = rel(c, b)
-            if not e2 < 2e-3:
+            if not e2 < 1e-3:           # peer-load reduction == NCCL's bits; only the statistics' summation order differs
                 ok = False
                 msgs.append(f"own all-reduce kernel differs from the NCCL path ({name}, multicast={mc}): rel {e2:.3e}")
         tp.get_model().decoder._nvls = None

@@ -56,7 +56,7 @@ class TpAllReduceArgs(C.Structure):
         ("part", C.c_void_p * 8), ("xout", C.c_void_p * 8), ("stats", C.c_void_p * 8), ("pads", C.c_void_p * 8),
         ("part_mc", C.c_void_p), ("xout_mc", C.c_void_p), ("stats_mc", C.c_void_p),
         ("rank", C.c_int32), ("world", C.c_int32), ("S", C.c_int32), ("H", C.c_int32),
-        ("epoch", C.c_uint32), ("reserved", C.c_uint32),
+        ("epoch", C.c_uint32), ("inswitch_reduce", C.c_uint32),
     ]
 
 

@@ -1,9 +1,10 @@
 // Tensor-parallel all-reduce fused with the residual stream's RMSNorm statistics, over NVLink 5 / NVSwitch, as ONE kernel:
 //   x[S,H] = sum over ranks of part_r[S,H]   (bf16 partial outputs of a row-parallel GEMM; rank 0's partial carries the residual)
 //   ss[S]  = sum_h x[s,h]^2                  (what the next folded RMSNorm reads: vl2_gemm_args.rms_sumsq_in, one part per row)
-// Every rank owns a contiguous block of rows: it reduces them (NVLS: one multimem.ld_reduce through the switch with fp32
-// accumulation; without multicast: peer loads in rank order), squares what it will store, and writes rows + statistics
-// into EVERY rank's buffers (multimem.st, or peer stores) - the two-shot all-reduce with nothing else on the wire.
+// Every rank owns a contiguous block of rows: it reduces them (peer loads over NVLink in rank order, fp32 accumulation, one
+// rounding; optionally one multimem.ld_reduce through the switch), squares what it will store, and writes rows + statistics
+// into EVERY rank's buffers (one multimem.st through the NVSwitch, or peer stores) - the two-shot all-reduce, nothing else
+// on the wire.
 // Cross-GPU ordering is inside the kernel: a start barrier (every rank's partial is complete) and an end barrier (every
 // rank's rows have landed everywhere; nobody still reads a partial) over symmetric-memory signal pads, so the stream needs
 // no collective library call and no extra launches.  The reference has no counterpart (no tensor parallelism).
@@ -56,7 +57,11 @@ __device__ __forceinline__ void multimem_st_f32(float* mc_addr, float v) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
 }
 
-template <bool MC>
+// RED_MC: reduce inside the NVSwitch (multimem.ld_reduce).  Measured on B200 (scripts/tp_allreduce_check.py): the switch does
+// NOT round the bf16 result to nearest - ~19 % of the elements differ by one bf16 ulp from the correctly rounded fp32 sum
+// (which NCCL and the peer-load path both produce bit for bit) - so it is opt-in; the default reduces with peer loads in
+// rank order (exact fp32 accumulation, one rounding) and uses the switch only to BROADCAST (ST_MC: multimem.st, an exact copy).
+template <bool RED_MC, bool ST_MC>
 __global__ void __launch_bounds__(256)
 tp_allreduce_stats_kernel(const TpArParams p) {
   __shared__ float red[64];
@@ -76,7 +81,7 @@ tp_allreduce_stats_kernel(const TpArParams p) {
     float q = 0.f;
     for (int v = tid; v < nvec; v += blockDim.x) {
       uint4 out;
-      if (MC) {
+      if (RED_MC) {
         out = multimem_ld_reduce_bf16x8(p.part_mc + base + v * 8);
       } else {
         float acc[8];
@@ -94,7 +99,7 @@ tp_allreduce_stats_kernel(const TpArParams p) {
       unpack8(out, f);                                     // statistics of what the consumers will read (bf16-rounded)
 #pragma unroll
       for (int j = 0; j < 8; ++j) q = fmaf(f[j], f[j], q);
-      if (MC) {
+      if (ST_MC) {
         multimem_st_v4(p.xout_mc + base + v * 8, out);
       } else {
         for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint4*>(p.xout[r] + base + v * 8) = out;
@@ -102,7 +107,7 @@ tp_allreduce_stats_kernel(const TpArParams p) {
     }
     const float tot = block_sum2(q, 0.f, red).x;
     if (tid == 0) {
-      if (MC) multimem_st_f32(p.stats_mc + row, tot);
+      if (ST_MC) multimem_st_f32(p.stats_mc + row, tot);
       else for (int r = 0; r < p.world; ++r) p.stats[r][row] = tot;
     }
   }
@@ -141,7 +146,7 @@ extern "C" int vl2_tp_allreduce_stats(const vl2_tp_allreduce_args* a, void* stre
     p.stats[r] = used ? a->stats[r] : nullptr;
     p.pads[r] = used ? a->pads[r] : nullptr;
     if (used) {
-      VL2_REQUIRE(a->pads[r] != nullptr && (mc || (a->part[r] && a->xout[r] && a->stats[r])), VL2_E_BADSHAPE,
+      VL2_REQUIRE(a->pads[r] != nullptr && a->part[r] != nullptr && (mc || (a->xout[r] && a->stats[r])), VL2_E_BADSHAPE,
                   "vl2_tp_allreduce_stats: missing buffer of rank %d", r);
       VL2_REQUIRE(aligned16(a->part[r]) && aligned16(a->xout[r]), VL2_E_BADALIGN, "vl2_tp_allreduce_stats: 16-byte alignment");
     }
@@ -154,8 +159,10 @@ extern "C" int vl2_tp_allreduce_stats(const vl2_tp_allreduce_args* a, void* stre
   int blocks = rows_per < 2 * sm_count() ? rows_per : 2 * sm_count();
   if (blocks < 1) blocks = 1;
   cudaStream_t st = (cudaStream_t)stream;
-  if (mc) launch_kernel(tp_allreduce_stats_kernel<true>, dim3(blocks), dim3(256), 0, st, 1, p);
-  else launch_kernel(tp_allreduce_stats_kernel<false>, dim3(blocks), dim3(256), 0, st, 1, p);
+  const bool inswitch = mc && a->inswitch_reduce != 0;
+  if (inswitch) launch_kernel(tp_allreduce_stats_kernel<true, true>, dim3(blocks), dim3(256), 0, st, 1, p);
+  else if (mc) launch_kernel(tp_allreduce_stats_kernel<false, true>, dim3(blocks), dim3(256), 0, st, 1, p);
+  else launch_kernel(tp_allreduce_stats_kernel<false, false>, dim3(blocks), dim3(256), 0, st, 1, p);
   VL2_CHECK_LAUNCH("tp_allreduce_stats_kernel");
   return VL2_OK;
 }

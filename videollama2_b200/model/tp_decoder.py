@@ -115,12 +115,13 @@ class TPDecoderEngine(DecoderEngine):
         return super().load_state_dict(local, device)
 
     # ---- collectives ---------------------------------------------------------------------------------------------
-    def enable_nvls_all_reduce(self, max_rows: int, use_multicast: bool = True):
-        """Route the prefill all-reduces through the library's own kernel (parallel.NvlsAllReduce: in-switch reduction +
-        RMSNorm statistics + broadcast in one launch) instead of NCCL + a statistics kernel.  The row-parallel GEMMs then
+    def enable_nvls_all_reduce(self, max_rows: int, use_multicast: bool = True, inswitch_reduce: bool = False):
+        """Route the prefill all-reduces through the library's own kernel (parallel.NvlsAllReduce: reduction over peer memory +
+        RMSNorm statistics + NVSwitch broadcast in one launch) instead of NCCL + a statistics kernel.  The row-parallel GEMMs then
         write their partials straight into the symmetric buffer."""
         from ..parallel import NvlsAllReduce
-        self._nvls = NvlsAllReduce(max_rows, self.H, self.device, self.group, use_multicast) if self.world > 1 else None
+        self._nvls = NvlsAllReduce(max_rows, self.H, self.device, self.group, use_multicast, inswitch_reduce) \
+            if self.world > 1 else None
         return self
 
     def _all_reduce(self, part: torch.Tensor) -> torch.Tensor:

@@ -106,14 +106,18 @@ class FrameParallel:
 
 class NvlsAllReduce:
     """All-reduce of the tensor-parallel decoder's partial sums as ONE kernel over NVLink / NVSwitch (csrc/tp_allreduce.cu):
-    in-switch reduction (multimem.ld_reduce, fp32 accumulation) of the ranks' bf16 partials, the row sums of squares the
-    next folded RMSNorm needs, and the broadcast of both (multimem.st) - with the cross-GPU barriers inside the kernel.
+    reduction of the ranks' bf16 partials with peer loads (fp32 accumulation in rank order: bit-identical to NCCL's result;
+    `inswitch_reduce=True` uses multimem.ld_reduce instead, whose bf16 rounding differs - see the kernel), the row sums of
+    squares the next folded RMSNorm needs, and the broadcast of both through the switch (multimem.st) - with the cross-GPU
+    barriers inside the kernel.
     Buffers live in symmetric memory (torch.distributed._symmetric_memory): `part` is where the row-parallel GEMM writes
     its output, `out[i]` (two, alternating) receive the reduced stream.  Falls back to peer loads / stores when the
     allocation has no multicast mapping."""
 
-    def __init__(self, max_rows: int, hidden: int, device, group=None, use_multicast: bool = True):
+    def __init__(self, max_rows: int, hidden: int, device, group=None, use_multicast: bool = True,
+                 inswitch_reduce: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
+        self.inswitch_reduce = inswitch_reduce
         self.group = group if group is not None else dist.group.WORLD
         self.rank = dist.get_rank(self.group)
         self.world = dist.get_world_size(self.group)
@@ -171,6 +175,7 @@ class NvlsAllReduce:
             a.part_mc = int(self._h_part.multicast_ptr)
             a.xout_mc = int(self._h_out[i].multicast_ptr)
             a.stats_mc = int(self._h_stats[i].multicast_ptr)
+            a.inswitch_reduce = 1 if self.inswitch_reduce else 0
         _lib.check(_lib.load().vl2_tp_allreduce_stats(C.byref(a), torch.cuda.current_stream().cuda_stream),
                    "vl2_tp_allreduce_stats")
         return self.out[i][:rows], self.stats[i][:rows].view(rows, 1)
