@@ -300,6 +300,32 @@ size_t vl2_preprocess_workspace(const vl2_preprocess_args* args);
 int vl2_preprocess_frames(const vl2_preprocess_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * ViT patch embedding as one implicit-GEMM kernel (HF CLIPVisionEmbeddings.forward + pre_layrnorm,
+ * HF:clip/modeling_clip.py:202-218,739-741; HF SiglipVisionEmbeddings for encoder.py:84-151):
+ *   CLIP   (gamma != NULL): out[f, 0] = LN(cls + pos[0]);  out[f, 1+p] = LN(conv(pixels[f])[p] + pos[1+p])
+ *   SigLIP (gamma == NULL): out[f, p] = conv(pixels[f])[p] + bias + pos[p]
+ * pixels bf16 [F,3,H,W]; weight bf16 [C, Kpad] = patch_embedding.weight flattened (c, i, j)-major and zero-padded from
+ * 3*P*P to Kpad (multiple of 64, <= 640); pos bf16 [np (+1), C]; out bf16 [F*(np (+1)), C]; scratch fp32 [F*np, C] (CLIP
+ * only: the un-normalised rows between the two epilogue passes).  The A operand is gathered from the frames by the kernel
+ * (LDG -> 128B-swizzled shared memory); no im2col matrix exists.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vl2_patch_embed_args {
+  const void* pixels;
+  const void* weight;
+  const void* pos;
+  const void* cls;     /* bf16 [C] (CLIP) or NULL */
+  const void* gamma;   /* pre_layrnorm weight / bias (CLIP) or NULL */
+  const void* beta;
+  const float* bias;   /* conv bias fp32 [C] (SigLIP) or NULL */
+  void* out;
+  float* scratch;
+  int32_t F, H, W, P, C, Kpad;
+  float eps;
+  int32_t reserved;
+} vl2_patch_embed_args;
+int vl2_patch_embed(const vl2_patch_embed_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Tensor-parallel decoder (BASELINE.json configs[4], SURVEY.md §8e "TP decoder"; no counterpart in the reference, whose
  * multi-GPU loading is accelerate's device_map="auto", videollama2/model/__init__.py:48,54):
  * all-reduce of the row-parallel GEMMs' bf16 partials [S,H] over the ranks of one NVSwitch domain, fused with the row sums

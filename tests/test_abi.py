@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header():
     from videollama2_b200._lib import AttnArgs, GemmArgs
-    assert ctypes.sizeof(GemmArgs) == 6 * 8 + 4 * 8 + 6 * 4 + 8 * 8 + 8 + 2 * 4 + 2 * 8 + 2 * 4 + 2 * 4 + 2 * 8 + 3 * 8 + 6 * 4 + 8 + 4 * 4
+    assert ctypes.sizeof(GemmArgs) == 6 * 8 + 4 * 8 + 6 * 4 + 8 * 8 + 8 + 2 * 4 + 2 * 8 + 2 * 4 + 2 * 4 + 2 * 8 + 3 * 8 + 6 * 4 + 8 + 4 * 4 
     assert ctypes.sizeof(AttnArgs) == 4 * 8 + 4 * 8 + 8 * 4
 
 

@@ -545,3 +545,48 @@ def test_gemm_rope_epilogue(cuda, S, Hq, Hkv, D, pos0, bn, with_bias):
     inv_dev = inv.contiguous()
     ops.rope_inplace(plain, S, Hq, Hkv, D, 0, Hq * D, pos0, inv_dev, interleaved=True)
     assert relerr(plain, ref) < 8e-3
+
+
+@pytest.mark.parametrize("F,H,P,C", [(2, 336, 14, 1024), (3, 56, 14, 128), (1, 112, 14, 256), (16, 336, 14, 1024)])
+def test_patch_embed_fused_clip(cuda, F, H, P, C):
+    """vl2_patch_embed (patch gather -> tcgen05 conv -> + position -> class row -> pre-LayerNorm in ONE kernel) against
+    conv2d + cat(cls) + position + layer_norm in fp32, and against the three-kernel explicit path it replaces."""
+    from videollama2_b200 import ops
+    px = rnd((F, 3, H, H), cuda, seed=16)
+    wconv = rnd((C, 3, P, P), cuda, 0.05, seed=17)
+    K = 3 * P * P
+    Kpad = (K + 63) // 64 * 64
+    wpad = torch.zeros((C, Kpad), device=cuda, dtype=torch.bfloat16)
+    wpad[:, :K] = wconv.reshape(C, K)
+    np_ = (H // P) ** 2
+    cls = rnd((C,), cuda, seed=18)
+    pos = rnd((np_ + 1, C), cuda, seed=19)
+    g = rnd((C,), cuda, 0.1, seed=20) + 1
+    b = rnd((C,), cuda, 0.1, seed=21)
+    tok = ops.patch_embed(px, wpad, pos, P, cls=cls, gamma=g, beta=b, eps=1e-5)
+    patch = torch.nn.functional.conv2d(px.float(), wconv.float(), stride=P).flatten(2).transpose(1, 2)
+    emb = torch.cat([cls.float().expand(F, 1, C), patch], 1) + pos.float()
+    ref = torch.nn.functional.layer_norm(emb, (C,), g.float(), b.float(), 1e-5).reshape(-1, C)
+    assert tok.shape == ref.shape and relerr(tok, ref) < 5e-3
+    explicit = ops.clip_embed_finish(ops.gemm(ops.patch_im2col(px, P, Kpad), wpad), cls, pos, g, b, F, 1e-5)
+    assert relerr(tok, explicit.float()) < 3e-3
+    assert torch.equal(tok.view(F, np_ + 1, C)[0, 0], tok.view(F, np_ + 1, C)[F - 1, 0])      # class rows identical
+
+
+@pytest.mark.parametrize("F,H,P,C", [(2, 384, 14, 1152), (3, 70, 14, 288)])
+def test_patch_embed_fused_siglip(cuda, F, H, P, C):
+    """SigLIP form: conv + bias + position rows, no class token, no LayerNorm (27 x 27 patches out of 384 pixels: 6 unused)."""
+    from videollama2_b200 import ops
+    px = rnd((F, 3, H, H), cuda, seed=26)
+    wconv = rnd((C, 3, P, P), cuda, 0.05, seed=27)
+    K = 3 * P * P
+    Kpad = (K + 63) // 64 * 64
+    wpad = torch.zeros((C, Kpad), device=cuda, dtype=torch.bfloat16)
+    wpad[:, :K] = wconv.reshape(C, K)
+    np_ = (H // P) ** 2
+    pos = rnd((np_, C), cuda, seed=29)
+    bias = rnd((C,), cuda, 0.2, seed=30).float()
+    tok = ops.patch_embed(px, wpad, pos, P, bias=bias)
+    patch = torch.nn.functional.conv2d(px.float(), wconv.float(), bias, stride=P).flatten(2).transpose(1, 2)
+    ref = (patch + pos.float()).reshape(-1, C)
+    assert tok.shape == ref.shape and relerr(tok, ref) < 4e-3

@@ -16,7 +16,7 @@ SYMBOLS = [
     "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq", "vl2_row_stats",
     "vl2_patch_im2col", "vl2_clip_embed_finish",
     "vl2_dwconv3x3_ln_silu", "vl2_se_scale", "vl2_conv3d_im2col",
-    "vl2_rope_inplace", "vl2_embed_splice", "vl2_tp_allreduce_stats",
+    "vl2_rope_inplace", "vl2_embed_splice", "vl2_tp_allreduce_stats", "vl2_patch_embed",
 ]
 
 ACT_NONE, ACT_QUICK_GELU, ACT_SILU, ACT_GELU_ERF, ACT_SWIGLU, ACT_GELU_TANH = 0, 1, 2, 3, 4, 5
@@ -57,6 +57,15 @@ class TpAllReduceArgs(C.Structure):
         ("part_mc", C.c_void_p), ("xout_mc", C.c_void_p), ("stats_mc", C.c_void_p),
         ("rank", C.c_int32), ("world", C.c_int32), ("S", C.c_int32), ("H", C.c_int32),
         ("epoch", C.c_uint32), ("inswitch_reduce", C.c_uint32),
+    ]
+
+
+class PatchEmbedArgs(C.Structure):
+    _fields_ = [
+        ("pixels", C.c_void_p), ("weight", C.c_void_p), ("pos", C.c_void_p), ("cls", C.c_void_p), ("gamma", C.c_void_p),
+        ("beta", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("scratch", C.c_void_p),
+        ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("Kpad", C.c_int32),
+        ("eps", C.c_float), ("reserved", C.c_int32),
     ]
 
 
@@ -109,6 +118,7 @@ def load() -> C.CDLL:
         "vl2_rope_inplace": [vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp],
         "vl2_embed_splice": [vp, vp, i32, vp, i64, vp, i32, vp],
         "vl2_tp_allreduce_stats": [C.POINTER(TpAllReduceArgs), vp],
+        "vl2_patch_embed": [C.POINTER(PatchEmbedArgs), vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

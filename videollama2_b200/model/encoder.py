@@ -93,10 +93,15 @@ class CLIPVisionTower:
         H = c.num_attention_heads
         D = C // H
         S = self.num_patches + 1
-        A = ops.patch_im2col(images.contiguous(), c.patch_size, self.kpad)
-        patch = ops.gemm(A, self.w["patch"])
-        x = ops.clip_embed_finish(patch, self.w["cls"], self.w["pos"], self.w["pre_g"], self.w["pre_b"], Fn,
-                                  c.layer_norm_eps)
+        if self.fused_embed and self.kpad <= 640 and c.patch_size % 2 == 0 and C % 32 == 0:
+            # one implicit-GEMM launch: gather patches -> tcgen05 conv -> + position -> class row -> pre-LayerNorm
+            x = ops.patch_embed(images.contiguous(), self.w["patch"], self.w["pos"], c.patch_size, cls=self.w["cls"],
+                                gamma=self.w["pre_g"], beta=self.w["pre_b"], eps=c.layer_norm_eps)
+        else:
+            A = ops.patch_im2col(images.contiguous(), c.patch_size, self.kpad)
+            patch = ops.gemm(A, self.w["patch"])
+            x = ops.clip_embed_finish(patch, self.w["cls"], self.w["pos"], self.w["pre_g"], self.w["pre_b"], Fn,
+                                      c.layer_norm_eps)
         x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr, None)
         return x.view(Fn, S, C)
 
@@ -109,6 +114,8 @@ class CLIPVisionTower:
     # more than the 46 stand-alone LayerNorm launches it removes at 8-16 frames (8.22 vs 7.71 ms) and only pays at 2 frames
     # per GPU (2.51 vs 2.61 ms).
     fold_layernorm = os.environ.get("VL2_VIT_FOLD_LN", "0") == "1"
+    # embeddings as ONE implicit-GEMM kernel (vl2_patch_embed); VL2_VIT_FUSED_EMBED=0 -> explicit im2col + GEMM + finish
+    fused_embed = os.environ.get("VL2_VIT_FUSED_EMBED", "1") != "0"
 
     def _encoder(self, x: torch.Tensor, Fn: int, S: int, last_out=None, bcast_ptrs=None, mc_ptr: int = 0,
                  stats=None) -> torch.Tensor:
@@ -299,12 +306,16 @@ class SiglipVisionTower(CLIPVisionTower):
 
     def hidden_states(self, images: torch.Tensor, last_out: Optional[torch.Tensor] = None, bcast_ptrs=None,
                       mc_ptr: int = 0) -> torch.Tensor:
-        """[F,3,H,W] bf16 -> residual stream after the selected layer, [F, np, C].  The embedding is ONE GEMM: im2col
-        patches x conv weight, + bias and + position rows in its epilogue (the position table repeated per frame is the
-        GEMM's residual operand)."""
+        """[F,3,H,W] bf16 -> residual stream after the selected layer, [F, np, C].  The embedding is ONE implicit-GEMM
+        launch (vl2_patch_embed: patches gathered from the frames, conv on tcgen05, + bias + position rows in the epilogue);
+        the explicit form (im2col + GEMM with the position table as residual operand) remains for the folded-LN variant."""
         c = self._config
         Fn = images.shape[0]
         S = self.num_patches
+        if self.fused_embed and not self.fold_layernorm and self.kpad <= 640 and c.patch_size % 2 == 0 and c.hidden_size % 32 == 0:
+            x = ops.patch_embed(images.contiguous(), self.w["patch"], self.w["pos"], c.patch_size, bias=self.w["patch_b"])
+            x = self._encoder(x, Fn, S, last_out, bcast_ptrs, mc_ptr, None)
+            return x.view(Fn, S, c.hidden_size)
         pos = self._pos_rows.get(Fn)
         if pos is None:
             pos = self.w["pos"].repeat(Fn, 1).contiguous()

@@ -13,7 +13,7 @@ from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_QUICK_GELU, ACT_SI
                    check)
 
 __all__ = [
-    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "l2_prefetch", "layernorm", "rmsnorm", "row_sumsq", "row_stats", "patch_im2col", "clip_embed_finish",
+    "gemm", "gemm_skinny", "attention", "attention_decode", "decode_rope_append", "attention_decode_dyn", "gemv", "decode_workspace", "l2_prefetch", "layernorm", "rmsnorm", "row_sumsq", "row_stats", "patch_im2col", "patch_embed", "clip_embed_finish",
     "dwconv3x3_ln_silu", "se_scale", "conv3d_im2col", "conv3d_k2s2", "rope_inplace", "embed_splice", "launch_count",
     "ACT_NONE", "ACT_QUICK_GELU", "ACT_SILU", "ACT_GELU_ERF", "ACT_GELU_TANH", "ACT_SWIGLU", "ACT_SIGMOID",
 ]
@@ -378,6 +378,31 @@ def patch_im2col(pixels: torch.Tensor, P: int, Kpad: int) -> torch.Tensor:
     out = torch.empty((F * (H // P) * (W // P), Kpad), device=pixels.device, dtype=torch.bfloat16)
     check(_lib.load().vl2_patch_im2col(pixels.data_ptr(), out.data_ptr(), F, H, W, P, Kpad, _stream()),
           "vl2_patch_im2col")
+    return out
+
+
+def patch_embed(pixels: torch.Tensor, weight: torch.Tensor, pos: torch.Tensor, P: int, *, cls: Optional[torch.Tensor] = None,
+                gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                eps: float = 1e-5) -> torch.Tensor:
+    """ViT embeddings in one implicit-GEMM launch (vl2_patch_embed).  CLIP form (cls / gamma / beta given): class token +
+    patch conv + positions + pre-LayerNorm -> [F*(np+1), C]; SigLIP form (bias given): conv + bias + positions -> [F*np, C].
+    weight: [C, Kpad] (conv kernel flattened, zero-padded to a multiple of 64)."""
+    _need_cuda(pixels, weight, pos, cls, gamma, beta, bias)
+    _bf16(pixels, weight, pos, cls, gamma, beta)
+    assert pixels.is_contiguous() and pixels.dim() == 4 and pixels.shape[1] == 3 and weight.is_contiguous() and pos.is_contiguous()
+    F, _, H, W = pixels.shape
+    Cc, Kpad = weight.shape
+    npatch = (H // P) * (W // P)
+    clip = gamma is not None
+    assert pos.shape == (npatch + (1 if clip else 0), Cc)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == Cc
+    out = torch.empty((F * (npatch + (1 if clip else 0)), Cc), device=pixels.device, dtype=torch.bfloat16)
+    scratch = torch.empty((F * npatch, Cc), device=pixels.device, dtype=torch.float32) if clip else None
+    a = _lib.PatchEmbedArgs(pixels=pixels.data_ptr(), weight=weight.data_ptr(), pos=pos.data_ptr(), cls=_ptr(cls),
+                            gamma=_ptr(gamma), beta=_ptr(beta), bias=_ptr(bias), out=out.data_ptr(), scratch=_ptr(scratch),
+                            F=F, H=H, W=W, P=P, C=Cc, Kpad=Kpad, eps=float(eps))
+    check(_lib.load().vl2_patch_embed(C.byref(a), _stream()), "vl2_patch_embed")
     return out
 
 
