@@ -47,6 +47,10 @@ enum {
 };
 
 int vl2_version(void);
+/* 16-bit storage type this build of the library moves through every `bf16` pointer of this header: 0 = bfloat16
+ * (libvl2.so), 1 = IEEE float16 (libvl2_f16.so, the same sources compiled with -DVL2_HALF: the reference's own inference
+ * dtype, videollama2/__init__.py:60).  Same entry points, same structs; accumulation is fp32 in both. */
+int vl2_storage_dtype(void);
 const char* vl2_last_error(void);
 /* Number of kernel launches issued by this library in this process (bench.py's gpu_launches counter). */
 int64_t vl2_launch_count(void);

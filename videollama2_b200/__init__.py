@@ -83,7 +83,7 @@ def mm_infer(image_or_video, instruct, model, tokenizer, modal="video", **kwargs
     message, modal_token = build_messages(instruct, modal, model.config.model_type)
     images = None
     if modal != "text":
-        images = [(image_or_video.to(device=model.device, dtype=torch.bfloat16), modal)]
+        images = [(image_or_video.to(device=model.device, dtype=getattr(model, "dtype", torch.bfloat16)), modal)]
     prompt = tokenizer.apply_chat_template(message, tokenize=False, add_generation_prompt=True)
     input_ids = tokenizer_multimodal_token(prompt, tokenizer, modal_token, return_tensors="pt").unsqueeze(0).long()
     attention_masks = input_ids.ne(tokenizer.pad_token_id).long()

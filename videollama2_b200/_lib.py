@@ -7,10 +7,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VL2_LIBVL2") or os.path.join(_HERE, "libvl2.so")   # override: A/B runs of two builds
+LIB_PATH_F16 = os.environ.get("VL2_LIBVL2_F16") or os.path.join(_HERE, "libvl2_f16.so")   # same sources, fp16 storage
 
 # Every symbol include/vl2.h declares (tests/test_abi.py checks the header against this list and the .so).
 SYMBOLS = [
-    "vl2_version", "vl2_last_error", "vl2_launch_count",
+    "vl2_version", "vl2_storage_dtype", "vl2_last_error", "vl2_launch_count",
     "vl2_gemm_bf16", "vl2_gemm_skinny", "vl2_attention", "vl2_attention_decode", "vl2_debug_attn_trace", "vl2_debug_gemm_trace", "vl2_gemm_plan",
     "vl2_decode_rope_append", "vl2_attention_decode_dyn", "vl2_gemv_bf16", "vl2_attention_decode_workspace", "vl2_set_pdl", "vl2_l2_prefetch", "vl2_preprocess_frames", "vl2_preprocess_workspace",
     "vl2_layernorm", "vl2_rmsnorm", "vl2_row_sumsq", "vl2_row_stats",
@@ -73,19 +74,34 @@ class Vl2Error(RuntimeError):
     pass
 
 
-_lib = None
+_libs = {}
 
 
-def load() -> C.CDLL:
-    """Load libvl2.so or raise.  Never falls back to another implementation."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def _variant(dtype) -> str:
+    """Which build serves tensors of `dtype`: bf16 storage (libvl2.so) or fp16 storage (libvl2_f16.so)."""
+    if dtype is None:
+        return "bf16"
+    name = str(dtype)
+    if name.endswith("bfloat16") or name == "bf16":
+        return "bf16"
+    if name.endswith("float16") or name in ("f16", "half"):
+        return "f16"
+    raise TypeError(f"videollama2_b200 stores activations as bfloat16 or float16, not {dtype}")
+
+
+def load(dtype=None) -> C.CDLL:
+    """Load the library that stores 16-bit data as `dtype` (torch.bfloat16 - the default - or torch.float16) or raise.
+    Never falls back to another implementation."""
+    var = _variant(dtype)
+    lib = _libs.get(var)
+    if lib is not None:
+        return lib
+    path = LIB_PATH if var == "bf16" else LIB_PATH_F16
+    if not os.path.exists(path):
         raise Vl2Error(
-            f"{LIB_PATH} is missing: build it with `python -m videollama2_b200.build` (nvcc, sm_100a). "
+            f"{path} is missing: build it with `python -m videollama2_b200.build` (nvcc, sm_100a). "
             "videollama2_b200 has no CPU or PyTorch fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     lib.vl2_version.restype = C.c_int
     lib.vl2_last_error.restype = C.c_char_p
@@ -124,12 +140,16 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_size_t if name.endswith("_workspace") else C.c_int
-    _lib = lib
+    lib.vl2_storage_dtype.restype = C.c_int
+    if int(lib.vl2_storage_dtype()) != (0 if var == "bf16" else 1):
+        raise Vl2Error(f"{path} was built for the other storage type")
+    _libs[var] = lib
     return lib
 
 
-def check(rc: int, what: str) -> None:
+def check(rc: int, what: str, lib=None) -> None:
     if rc != 0:
-        msg = load().vl2_last_error().decode(errors="replace")
+        msgs = [l.vl2_last_error().decode(errors="replace") for l in ([lib] if lib is not None else _libs.values())]
+        msg = " | ".join(m for m in msgs if m)
         exc = ValueError if rc in (-1, -2, -3) else (NotImplementedError if rc == -6 else Vl2Error)
         raise exc(f"{what} failed (code {rc}): {msg}")

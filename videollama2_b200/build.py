@@ -48,37 +48,56 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+# The same sources build twice: bf16 storage (libvl2.so) and, with -DVL2_HALF, IEEE fp16 storage (libvl2_f16.so) - the
+# reference's own inference dtype.  See csrc/ptx.cuh.
+VARIANTS = {
+    "bf16": (OUT, OBJ_DIR, []),
+    "f16": (os.path.join(HERE, "libvl2_f16.so"), os.path.join(HERE, "build_f16"), ["-DVL2_HALF"]),
+}
+
+
+def lib_path(variant: str = "bf16") -> str:
+    return VARIANTS[variant][0]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ_DIR, exist_ok=True)
-    stamp = os.path.join(OBJ_DIR, "stamp")
+    """Builds every variant that is stale; returns the bf16 library's path."""
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+    todo = []
+    for name, (out, obj_dir, defs) in VARIANTS.items():
+        os.makedirs(obj_dir, exist_ok=True)
+        stamp = os.path.join(obj_dir, "stamp")
+        if force or not (os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig):
+            todo.append((name, out, obj_dir, defs, stamp))
+    if not todo:
         return OUT
     nvcc = _nvcc()
     srcs = _sources()
-    objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    jobs = [(src, os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o"), defs) for _, _, obj_dir, defs, _ in todo for src in srcs]
 
-    def compile_one(pair):
-        src, obj = pair
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+    def compile_one(job):
+        src, obj, defs = job
+        cmd = [nvcc, *NVCC_FLAGS, *defs, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        for src, r in ex.map(compile_one, zip(srcs, objs)):
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        for src, r in ex.map(compile_one, jobs):
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
-    r = subprocess.run(link, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("link of libvl2.so failed")
-    with open(stamp, "w") as fh:
-        fh.write(dig)
+    for name, out, obj_dir, defs, stamp in todo:
+        objs = [os.path.join(obj_dir, os.path.basename(s)[:-3] + ".o") for s in srcs]
+        link = [nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(link, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"link of {os.path.basename(out)} failed")
+        with open(stamp, "w") as fh:
+            fh.write(dig)
     return OUT
 
 

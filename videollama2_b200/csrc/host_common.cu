@@ -84,7 +84,12 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+#ifdef VL2_HALF
+  const CUtensorMapDataType elem_type = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#else
+  const CUtensorMapDataType elem_type = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#endif
+  CUresult r = enc(map, elem_type, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -97,6 +102,11 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 extern "C" {
 int vl2_version(void) { return VL2_VERSION; }
+#ifdef VL2_HALF
+int vl2_storage_dtype(void) { return 1; }
+#else
+int vl2_storage_dtype(void) { return 0; }
+#endif
 const char* vl2_last_error(void) { return vl2::g_err; }
 int64_t vl2_launch_count(void) { return vl2::g_launches.load(); }
 int vl2_set_pdl(int mode) {

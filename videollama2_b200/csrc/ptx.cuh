@@ -3,8 +3,34 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+// ----------------------------------------------------------------------------------------------
+// 16-bit storage type of the library.  The same sources build twice: libvl2.so stores activations / weights as bf16,
+// libvl2_f16.so (-DVL2_HALF) as IEEE fp16 - the reference's own inference dtype (videollama2/__init__.py:60,
+// model/__init__.py:71 load everything with torch_dtype=float16).  Every kernel moves 16-bit elements through the helpers
+// below (pack_bf16 / bf16_lo / bf16_hi / unpack8 / pack8) and the CUDA conversion intrinsics, so the half build only
+// re-targets those names; accumulation is fp32 either way and tcgen05.mma kind::f16 takes both input formats.
+// ----------------------------------------------------------------------------------------------
+#ifdef VL2_HALF
+#define __nv_bfloat16 __half
+#define __nv_bfloat162 __half2
+#define __float2bfloat16_rn __float2half_rn
+#define __bfloat162float __half2float
+#define __floats2bfloat162_rn __floats2half2_rn
+#define __bfloat16_as_ushort __half_as_ushort
+#define VL2_UMMA_FMT 0u                          // tcgen05 instruction descriptor: A / B format F16
+#define VL2_MMA_SYNC_TYPES "f16.f16"
+#define VL2_MULTIMEM_TYPE "f16x2"
+#define VL2_STORAGE_DTYPE 1
+#else
+#define VL2_UMMA_FMT 1u                          // BF16
+#define VL2_MMA_SYNC_TYPES "bf16.bf16"
+#define VL2_MULTIMEM_TYPE "bf16x2"
+#define VL2_STORAGE_DTYPE 0
+#endif
 
 namespace vl2 {
 
@@ -178,7 +204,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 //   [4,6) c_format (1 = f32)  [7,10) a_format (1 = bf16)  [10,13) b_format  [15] a_major  [16] b_major
 //   [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+  return (1u << 4) | (VL2_UMMA_FMT << 7) | (VL2_UMMA_FMT << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -330,7 +356,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+#ifdef VL2_HALF
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu))); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __half2float(__ushort_as_half((unsigned short)(u >> 16))); }
+#else
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+#endif
 
 }  // namespace vl2

@@ -42,7 +42,7 @@ __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t want) {
 // in-switch reduction of one 16-byte vector (8 bf16) over all ranks of the multicast group, fp32 accumulation
 __device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
   uint4 v;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4." VL2_MULTIMEM_TYPE " {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(mc_addr)
                : "memory");

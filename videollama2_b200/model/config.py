@@ -89,6 +89,19 @@ class Videollama2Config:
     vision_config: Optional[VisionConfig] = None
     eos_token_id: Optional[int] = 2
     pad_token_id: Optional[int] = None
+    # 16-bit storage type of weights / activations: "bfloat16" (default) or "float16" - the reference's own inference
+    # dtype (videollama2/__init__.py:60, model/__init__.py:71); selects which build of the kernel library runs
+    torch_dtype: str = "bfloat16"
+
+    @property
+    def storage_dtype(self):
+        import torch
+        name = str(self.torch_dtype).replace("torch.", "")
+        if name in ("float16", "half", "fp16"):
+            return torch.float16
+        if name in ("bfloat16", "bf16"):
+            return torch.bfloat16
+        raise ValueError(f"torch_dtype {self.torch_dtype!r} is not a storage type of the engine (bfloat16 / float16)")
 
     @property
     def head_dim(self) -> int:

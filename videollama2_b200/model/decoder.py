@@ -25,6 +25,7 @@ class DecoderEngine:
         self.D = config.hidden_size // config.num_attention_heads
         self.I = config.intermediate_size
         self.eps = config.rms_norm_eps
+        self.dtype = getattr(config, "storage_dtype", torch.bfloat16)      # bf16 or fp16 (selects the library build)
         self.layers: List[Dict[str, torch.Tensor]] = []
         self.w: Dict[str, torch.Tensor] = {}
         self.is_loaded = False
@@ -54,7 +55,7 @@ class DecoderEngine:
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device) -> "DecoderEngine":
         dev = torch.device(device)
-        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        bf = lambda t: t.to(device=dev, dtype=self.dtype).contiguous()
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         self.layers = []
         # RoPE runs in the epilogue of the fused QKV GEMM on ADJACENT column pairs: permute the q / k weight rows (and
@@ -75,9 +76,9 @@ class DecoderEngine:
             wgu = torch.stack([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], 1).reshape(
                 2 * self.I, self.H).to(device=dev, dtype=torch.float32)
             L = {
-                "wqkv": (wqkv * g1[None, :]).to(torch.bfloat16).contiguous(),
+                "wqkv": (wqkv * g1[None, :]).to(self.dtype).contiguous(),
                 "wo": bf(sd[p + "self_attn.o_proj.weight"]),
-                "wgu": (wgu * g2[None, :]).to(torch.bfloat16).contiguous(),
+                "wgu": (wgu * g2[None, :]).to(self.dtype).contiguous(),
                 "wd": bf(sd[p + "mlp.down_proj.weight"]),
             }
             del wqkv, wgu
@@ -88,13 +89,13 @@ class DecoderEngine:
                   # final-norm gain folded into the lm_head columns (the GEMV / GEMM epilogue applies 1/rms itself)
                   "lm_head": (sd["lm_head.weight"].to(device=dev, dtype=torch.float32)
                                 * sd["model.norm.weight"].to(device=dev, dtype=torch.float32)[None, :]
-                                ).to(torch.bfloat16).contiguous(),
-                  "ones": torch.ones((self.H,), device=dev, dtype=torch.bfloat16)}
+                                ).to(self.dtype).contiguous(),
+                  "ones": torch.ones((self.H,), device=dev, dtype=self.dtype)}
         inv = 1.0 / (self.config.rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))
         self.w["inv_freq"] = inv.to(dev)
         # one table for every position the model can see (8 MB at 32768 x 64): captured graphs keep its address
         self._rope_tab = ops.rope_table(int(getattr(self.config, "max_position_embeddings", 32768) or 32768), self.D,
-                                        self.config.rope_theta, dev)
+                                        self.config.rope_theta, dev, self.dtype)
         self.device = dev
         self.is_loaded = True
         return self
@@ -157,7 +158,7 @@ class DecoderEngine:
             return
         cap = (cap + 255) // 256 * 256
         width = (self.Hq + 2 * self.Hkv) * self.D
-        self.kv = [torch.empty((cap, width), device=device, dtype=torch.bfloat16) for _ in self.layers]
+        self.kv = [torch.empty((cap, width), device=device, dtype=self.dtype) for _ in self.layers]
         self._decode_graph = None
 
     # ---- KV-cache decode (one token) -----------------------------------------------------------------------
@@ -190,7 +191,7 @@ class DecoderEngine:
         writes argmax(logits) back to tok_dev and increments pos_dev, so one captured graph serves every token."""
         Hq, Hkv, D = self.Hq, self.Hkv, self.D
         x = torch.index_select(self.w["embed"], 0, tok_dev)
-        o = torch.empty((1, Hq * D), device=x.device, dtype=torch.bfloat16)
+        o = torch.empty((1, Hq * D), device=x.device, dtype=self.dtype)
         for i, L in enumerate(self.layers):
             cache = self.kv[i]
             ops.gemv(x, L["wqkv"], bias=L.get("bqkv"), out=stage, rms_eps=self.eps)
@@ -235,7 +236,7 @@ class DecoderEngine:
         if self._decode_graph is None:
             tok_dev = torch.zeros((1,), device=dev, dtype=torch.int64)
             pos_dev = torch.zeros((1,), device=dev, dtype=torch.int32)
-            stage = torch.empty((1, (self.Hq + 2 * self.Hkv) * self.D), device=dev, dtype=torch.bfloat16)
+            stage = torch.empty((1, (self.Hq + 2 * self.Hkv) * self.D), device=dev, dtype=self.dtype)
             gen_buf = torch.zeros((self.kv[0].shape[0] + 1,), device=dev, dtype=torch.int64)
             step_dev = torch.zeros((1,), device=dev, dtype=torch.int64)
             log = (gen_buf, step_dev)

@@ -38,6 +38,7 @@ class CLIPVisionTower:
         if vision_config is None:
             vision_config = getattr(args, "vision_config", None) or VisionConfig.from_dir(vision_tower)
         self._config = vision_config
+        self._dtype = getattr(args, "storage_dtype", torch.bfloat16)       # bf16 or fp16 (selects the library build)
         self.image_processor = _ImageProcessorInfo(vision_config.image_size)
         self._device = torch.device("cpu")
         self.w: Dict[str, torch.Tensor] = {}
@@ -63,11 +64,11 @@ class CLIPVisionTower:
         """Repack HF-named CLIP weights once: fused QKV [3C,C], fp32 biases, patch conv as [C, Kpad] GEMM weight."""
         c = self._config
         dev = torch.device(device)
-        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        bf = lambda t: t.to(device=dev, dtype=self._dtype).contiguous()
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         K = 3 * c.patch_size * c.patch_size
         self.kpad = (K + 63) // 64 * 64
-        wp = torch.zeros((c.hidden_size, self.kpad), dtype=torch.bfloat16, device=dev)
+        wp = torch.zeros((c.hidden_size, self.kpad), dtype=self._dtype, device=dev)
         wp[:, :K] = bf(sd[prefix + "embeddings.patch_embedding.weight"]).reshape(c.hidden_size, K)
         self.w = {
             "patch": wp,
@@ -172,13 +173,13 @@ class CLIPVisionTower:
         return x
 
     def _load_layers(self, sd, prefix, dev):
-        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        bf = lambda t: t.to(device=dev, dtype=self._dtype).contiguous()
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
 
         def fold(w, b, g, beta):
             """LN(x; g, beta) w^T + b  ->  (w * g as bf16, its fp32 row sums, b + w beta)."""
             wf = w.to(device=dev, dtype=torch.float32)
-            wg = (wf * g.to(device=dev, dtype=torch.float32)[None, :]).to(torch.bfloat16).contiguous()
+            wg = (wf * g.to(device=dev, dtype=torch.float32)[None, :]).to(self._dtype).contiguous()
             return wg, wg.float().sum(1).contiguous(), (b.to(device=dev, dtype=torch.float32)
                                                         + wf @ beta.to(device=dev, dtype=torch.float32)).contiguous()
 
@@ -218,7 +219,7 @@ class CLIPVisionTower:
         if not images.is_cuda:
             raise ops._lib.Vl2Error("CLIPVisionTower needs CUDA tensors (no CPU fallback)")
         dt = images.dtype
-        x = images.to(torch.bfloat16).contiguous()
+        x = images.to(self._dtype).contiguous()
         feats = self._graphed(x) if self._graphed is not None else self._features(x)
         return feats.to(dt)
 
@@ -230,7 +231,7 @@ class CLIPVisionTower:
     # ---- properties of the reference class (encoder.py:55-81) -----------------------------------------------
     @property
     def dtype(self):
-        return torch.bfloat16
+        return self._dtype
 
     @property
     def device(self):
@@ -291,12 +292,12 @@ class SiglipVisionTower(CLIPVisionTower):
         dev = torch.device(device)
         K = 3 * c.patch_size * c.patch_size
         self.kpad = (K + 63) // 64 * 64
-        wp = torch.zeros((c.hidden_size, self.kpad), dtype=torch.bfloat16, device=dev)
-        wp[:, :K] = sd[prefix + "embeddings.patch_embedding.weight"].to(device=dev, dtype=torch.bfloat16).reshape(c.hidden_size, K)
+        wp = torch.zeros((c.hidden_size, self.kpad), dtype=self._dtype, device=dev)
+        wp[:, :K] = sd[prefix + "embeddings.patch_embedding.weight"].to(device=dev, dtype=self._dtype).reshape(c.hidden_size, K)
         self.w = {
             "patch": wp,
             "patch_b": sd[prefix + "embeddings.patch_embedding.bias"].to(device=dev, dtype=torch.float32).contiguous(),
-            "pos": sd[prefix + "embeddings.position_embedding.weight"].to(device=dev, dtype=torch.bfloat16).contiguous(),
+            "pos": sd[prefix + "embeddings.position_embedding.weight"].to(device=dev, dtype=self._dtype).contiguous(),
         }
         self._pos_rows = {}
         self._load_layers(sd, prefix, dev)

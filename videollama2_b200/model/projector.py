@@ -30,7 +30,6 @@ class STCConnector:
     """Temporal Convolutional Vision-Language Connector (projector.py:133-215)."""
 
     padding = 1
-    s1_dtype = torch.bfloat16      # storage type of forward_s1's output (what the frame-parallel all-gather moves)
 
     def __init__(self, config, downsample=(2, 2, 2), depth=4, mlp_depth=2):
         if tuple(downsample) != (2, 2, 2):
@@ -44,6 +43,8 @@ class STCConnector:
         self.mlp_depth = mlp_depth
         self.downsample = tuple(downsample)
         self.eps = _REGSTAGE_LN_EPS
+        self.dtype = getattr(config, "storage_dtype", torch.bfloat16)      # bf16 or fp16 (selects the library build)
+        self.s1_dtype = self.dtype
         self.blocks: Dict[str, List[Dict[str, torch.Tensor]]] = {"s1": [], "s2": []}
         self.w: Dict[str, torch.Tensor] = {}
         self.is_loaded = False
@@ -62,7 +63,7 @@ class STCConnector:
     # ---- weights -------------------------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device, prefix: str = "") -> "STCConnector":
         dev = torch.device(device)
-        bf = lambda t: t.to(device=dev, dtype=torch.bfloat16).contiguous()
+        bf = lambda t: t.to(device=dev, dtype=self.dtype).contiguous()
         f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()
         C = self.hidden_size
         for stage in ("s1", "s2"):
@@ -151,7 +152,7 @@ class STCConnector:
         """[f,H,W,Cin] -> [f,H,W,C]: the per-frame half of the connector (first RegStage) on any subset of frames."""
         if not self.is_loaded:
             raise RuntimeError("STCConnector: weights not loaded")
-        x = x.to(torch.bfloat16).contiguous()
+        x = x.to(self.dtype).contiguous()
         g = getattr(self, "_graphed_s1", None)
         return g(x) if g is not None else self.run_s1(x)
 
@@ -159,7 +160,7 @@ class STCConnector:
         """[b,T,H,W,C] (first-RegStage output of every frame) -> [b, l', D]: Conv3d sampler + s2 + readout."""
         b = a.size(0)
         out = torch.empty((b, self.num_output_tokens(a.size(1), a.size(2)), self.output_hidden_size), device=a.device,
-                          dtype=torch.bfloat16)
+                          dtype=self.dtype)
         g = getattr(self, "_graphed_tail", None)
         for i in range(b):
             if g is not None:
@@ -184,11 +185,11 @@ class STCConnector:
             x = x.reshape(x.size(0), x.size(1), hw, hw, x.size(3))
         elif x.ndim != 5:
             raise ValueError(f"STCConnector expects a 4-D or 5-D input, got {x.ndim}-D")
-        x = x.to(torch.bfloat16).contiguous()
+        x = x.to(self.dtype).contiguous()
         b = x.size(0)
         n = self.num_output_tokens(x.size(1), x.size(2))
         if out is None:
-            out = torch.empty((b, n, self.output_hidden_size), device=x.device, dtype=torch.bfloat16)
+            out = torch.empty((b, n, self.output_hidden_size), device=x.device, dtype=self.dtype)
         for i in range(b):
             if self._graphed is not None:
                 out[i].copy_(self._graphed(x[i]))

@@ -87,6 +87,7 @@ class _LocalConfig:
     def __init__(self, config, plan):
         self.__dict__.update({k: getattr(config, k) for k in ("hidden_size", "num_hidden_layers", "rms_norm_eps", "rope_theta")})
         self.max_position_embeddings = getattr(config, "max_position_embeddings", 32768)
+        self.storage_dtype = getattr(config, "storage_dtype", torch.bfloat16)
         self.num_attention_heads = plan["Hq"]
         self.num_key_value_heads = plan["Hkv"]
         self.intermediate_size = plan["I"]
@@ -120,7 +121,7 @@ class TPDecoderEngine(DecoderEngine):
         RMSNorm statistics + NVSwitch broadcast in one launch) instead of NCCL + a statistics kernel.  The row-parallel GEMMs then
         write their partials straight into the symmetric buffer."""
         from ..parallel import NvlsAllReduce
-        self._nvls = NvlsAllReduce(max_rows, self.H, self.device, self.group, use_multicast, inswitch_reduce) \
+        self._nvls = NvlsAllReduce(max_rows, self.H, self.device, self.group, use_multicast, inswitch_reduce, self.dtype) \
             if self.world > 1 else None
         return self
 

@@ -43,7 +43,7 @@ class Videollama2MetaModel:
         if bool(bad.any()):     # the reference's nn.Embedding raises on these (e.g. a modal placeholder left without images)
             raise IndexError(f"embed_tokens: id {int(ids[bad].reshape(-1)[0])} outside [0, {self.config.vocab_size})")
         flat = ids.reshape(-1).to(device=self.decoder.device, dtype=torch.int64).contiguous()
-        out = torch.empty((flat.numel(), self.config.hidden_size), device=self.decoder.device, dtype=torch.bfloat16)
+        out = torch.empty((flat.numel(), self.config.hidden_size), device=self.decoder.device, dtype=self.decoder.dtype)
         if flat.numel():
             dst = torch.arange(flat.numel(), device=self.decoder.device, dtype=torch.int32)
             ops.embed_splice(flat, dst, self.decoder.embed_tokens, out)
@@ -172,13 +172,13 @@ class Videollama2MetaForCausalLM:
         B, max_len = input_ids.shape[0], plan["max_len"]
         ragged = any(n != max_len for n in plan["new_len"])
         alloc = torch.zeros if ragged else torch.empty                # right padding is zeros (arch.py:229-231)
-        embeds = alloc((B * max_len, H), device=dev, dtype=torch.bfloat16)
+        embeds = alloc((B * max_len, H), device=dev, dtype=model.decoder.dtype)
         if plan["text_dst"]:
             ids_dev = input_ids.to(dev)[torch.tensor(plan["text_b"], device=dev), torch.tensor(plan["text_src"], device=dev)]
             dst = torch.tensor(plan["text_dst"], device=dev, dtype=torch.int32)
             ops.embed_splice(ids_dev.contiguous(), dst, model.decoder.embed_tokens, embeds)
         for mm_idx, b, pos, n in plan["mm_dst"]:
-            embeds[b * max_len + pos: b * max_len + pos + n].copy_(mm_features[mm_idx].to(torch.bfloat16))
+            embeds[b * max_len + pos: b * max_len + pos + n].copy_(mm_features[mm_idx].to(model.decoder.dtype))
         embeds = embeds.view(B, max_len, H)
         new_labels = labels
         if labels is not None:

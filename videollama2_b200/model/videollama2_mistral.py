@@ -34,10 +34,14 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
 
     # ---- construction -----------------------------------------------------------------------------------------
     @classmethod
-    def from_state_dict(cls, config, state_dict: Dict[str, torch.Tensor], device="cuda", tp_group=None):
+    def from_state_dict(cls, config, state_dict: Dict[str, torch.Tensor], device="cuda", tp_group=None, dtype=None):
         """Build from HF-named weights (the reference's checkpoint format) and repack for the kernels.
         `tp_group` (a process group, or True for the default one): shard the decoder tensor-parallel over its ranks
-        (model/tp_decoder.py); every rank passes the same full state dict and keeps its slices."""
+        (model/tp_decoder.py); every rank passes the same full state dict and keeps its slices.
+        `dtype`: torch.bfloat16 (default) or torch.float16 - the storage type of weights and activations; float16 runs the
+        fp16 build of the kernel library (libvl2_f16.so), matching the reference's `torch_dtype=float16` loading."""
+        if dtype is not None:          # torch.float16 (the reference's inference dtype) or torch.bfloat16
+            config.torch_dtype = str(dtype).replace("torch.", "")
         self = cls(config, tp_group=tp_group)
         self.load_state_dict(state_dict, device)
         return self
@@ -61,7 +65,7 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
 
     @property
     def dtype(self):
-        return torch.bfloat16
+        return self.config.storage_dtype
 
     def eval(self):
         return self
@@ -104,7 +108,7 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
             n = S if new_len is None else new_len[b]
             if attention_mask is not None and new_len is None:
                 n = int(attention_mask[b].sum().item())            # right padding only (reference convention)
-            lg, hx = dec.prefill(inputs_embeds[b, :n].to(torch.bfloat16).contiguous(), all_logits=True)
+            lg, hx = dec.prefill(inputs_embeds[b, :n].to(dec.dtype).contiguous(), all_logits=True)
             logits[b, :n] = lg
             if hidden is not None:
                 hidden.append(hx)
@@ -148,7 +152,7 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         else:
             inputs_embeds = self.get_model().embed_tokens(inputs)
         dec = self.get_model().decoder
-        x = inputs_embeds[0].to(torch.bfloat16).contiguous()
+        x = inputs_embeds[0].to(dec.dtype).contiguous()
         new_ids: List[int] = []
         # prefill once (keeps per-layer K/V), then one weight-streaming decode step per new token
         use_cache = kwargs.get("use_cache", True)

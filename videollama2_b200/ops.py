@@ -44,19 +44,38 @@ def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
                                 f"`torch.cuda.device({t.device.index})` (kernels launch on the current device's stream)")
 
 
+_STORAGE = (torch.bfloat16, torch.float16)
+
+
 def _bf16(*ts: Optional[torch.Tensor]) -> None:
+    """All given tensors hold the library's 16-bit storage type: bfloat16 (libvl2.so) or float16 (libvl2_f16.so), and the
+    same one - the two builds are separate libraries and a call runs entirely in one of them."""
+    dt = None
     for t in ts:
-        if t is not None and t.dtype != torch.bfloat16:
-            raise TypeError(f"expected bfloat16 tensor, got {t.dtype}")
+        if t is None:
+            continue
+        if t.dtype not in _STORAGE:
+            raise TypeError(f"expected a bfloat16 / float16 tensor, got {t.dtype}")
+        if dt is None:
+            dt = t.dtype
+        elif t.dtype != dt:
+            raise TypeError(f"mixed storage types in one call: {dt} and {t.dtype}")
+
+
+def _L(t: torch.Tensor):
+    """The build of the library that matches tensor t's storage type."""
+    return _lib.load(t.dtype)
 
 
 def launch_count() -> int:
-    return int(_lib.load().vl2_launch_count())
+    """Kernel launches issued by the library (both storage-type builds) in this process."""
+    _lib.load()
+    return sum(int(l.vl2_launch_count()) for l in _lib._libs.values())
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bn: int = 0,
+         out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, bn: int = 0,
          bcast_ptrs: Optional[list] = None, mc_ptr: int = 0, rms_in: Optional[torch.Tensor] = None,
          rms_eps: float = 0.0, sumsq_out: Optional[torch.Tensor] = None, trace: bool = False,
          splitk=True, ln_in=None, ln_colsum: Optional[torch.Tensor] = None,
@@ -81,7 +100,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         raise ValueError(f"gemm: K mismatch {K} vs {Kw}")
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
-        out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
+        out = torch.empty((M, n_out), device=a.device, dtype=out_dtype or a.dtype)
     assert out.shape == (M, n_out) and out.stride(1) == 1
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
@@ -93,8 +112,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
                     row_scale=_ptr(row_scale), lda=a.stride(0), ldw=w.stride(0), ldc=out.stride(0),
                     ldr=residual.stride(0) if residual is not None else 0, M=M, N=N, K=K, act=act,
                     out_f32=1 if out.dtype == torch.float32 else 0, reserved=bn)
-    if out.dtype not in (torch.float32, torch.bfloat16):
-        raise TypeError("gemm: out must be bf16 or fp32")
+    if out.dtype not in (torch.float32, a.dtype):
+        raise TypeError("gemm: out must have the operands' storage type or be fp32")
     if rms_in is not None:
         assert rms_in.is_cuda and rms_in.dtype == torch.float32 and rms_in.is_contiguous() and rms_in.shape[0] == M
         args.rms_sumsq_in = rms_in.data_ptr()
@@ -130,14 +149,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         assert tuple(rowsum_out.shape) == (M, N // 32)
         args.rowsum_out = rowsum_out.data_ptr()
     if sumsq_out is not None:
-        if out.dtype != torch.bfloat16 or act == ACT_SWIGLU or N % 32:
-            raise NotImplementedError("gemm: sumsq_out supports bf16, non-SwiGLU outputs with N % 32 == 0")
+        if out.dtype == torch.float32 or act == ACT_SWIGLU or N % 32:
+            raise NotImplementedError("gemm: sumsq_out supports 16-bit, non-SwiGLU outputs with N % 32 == 0")
         assert sumsq_out.is_cuda and sumsq_out.dtype == torch.float32 and sumsq_out.is_contiguous()
         assert tuple(sumsq_out.shape) == (M, N // 32)
         args.sumsq_out = sumsq_out.data_ptr()
     if bcast_ptrs or mc_ptr:
-        if out.dtype != torch.bfloat16 or act == ACT_SWIGLU:
-            raise NotImplementedError("gemm: broadcast epilogue supports bf16, non-SwiGLU outputs")
+        if out.dtype == torch.float32 or act == ACT_SWIGLU:
+            raise NotImplementedError("gemm: broadcast epilogue supports 16-bit, non-SwiGLU outputs")
         ptrs = list(bcast_ptrs or [])
         if len(ptrs) > 8:
             raise ValueError("gemm: at most 8 broadcast targets")
@@ -154,7 +173,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         ws = _splitk_workspace(a.device)
         args.splitk_ws = ws.data_ptr()
         args.splitk_ws_bytes = ws.numel()
-    check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
+    check(_L(a).vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16")
     return out
 
 
@@ -190,16 +209,16 @@ def gemm_skinny(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
-    assert a.dtype in (torch.float32, torch.bfloat16)
+    assert a.dtype in (torch.float32, w.dtype)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=out_dtype)
-    assert out.is_contiguous() and out.numel() == M * n_out and out.dtype in (torch.float32, torch.bfloat16)
+    assert out.is_contiguous() and out.numel() == M * n_out and out.dtype in (torch.float32, w.dtype)
     if residual is not None:
         assert residual.is_contiguous() and residual.numel() == M * n_out
-    check(_lib.load().vl2_gemm_skinny(a.data_ptr(), 1 if a.dtype == torch.float32 else 0, w.data_ptr(), _ptr(bias),
+    check(_L(w).vl2_gemm_skinny(a.data_ptr(), 1 if a.dtype == torch.float32 else 0, w.data_ptr(), _ptr(bias),
                                       _ptr(residual), out.data_ptr(), 1 if out.dtype == torch.float32 else 0, M, N, K,
                                       act, _stream()), "vl2_gemm_skinny")
     return out
@@ -212,11 +231,14 @@ class pdl:
         self.on = on
 
     def __enter__(self):
-        check(_lib.load().vl2_set_pdl(1 if self.on else 0), "vl2_set_pdl")
+        _lib.load()
+        for lib in _lib._libs.values():
+            check(lib.vl2_set_pdl(1 if self.on else 0), "vl2_set_pdl")
         return self
 
     def __exit__(self, *exc):
-        check(_lib.load().vl2_set_pdl(-1), "vl2_set_pdl")
+        for lib in _lib._libs.values():
+            check(lib.vl2_set_pdl(-1), "vl2_set_pdl")
         return False
 
 
@@ -225,7 +247,7 @@ def l2_prefetch(t: torch.Tensor, nbytes: Optional[int] = None) -> None:
     _need_cuda(t)
     total = t.numel() * t.element_size()
     n = total if nbytes is None else min(int(nbytes), total)
-    check(_lib.load().vl2_l2_prefetch(t.data_ptr(), n, _stream()), "vl2_l2_prefetch")
+    check(_L(t).vl2_l2_prefetch(t.data_ptr(), n, _stream()), "vl2_l2_prefetch")
 
 
 _decode_ws = {}
@@ -244,7 +266,7 @@ def decode_workspace(device, Hq: int, Hkv: int, D: int) -> torch.Tensor:
 
 def gemv(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, rms_eps: float = 0.0,
-         out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+         out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """y[1,Nout] = act(s * w[N,K] x + bias) (+ residual); rms_eps > 0 fuses the RMSNorm in front (gain folded into w)."""
     _need_cuda(x, w, bias, residual, out)
     _bf16(x, w, residual)
@@ -254,11 +276,11 @@ def gemv(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         assert bias.dtype == torch.float32 and bias.numel() == N
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
-        out = torch.empty((1, n_out), device=x.device, dtype=out_dtype)
-    assert out.is_contiguous() and out.numel() == n_out and out.dtype in (torch.float32, torch.bfloat16)
+        out = torch.empty((1, n_out), device=x.device, dtype=out_dtype or x.dtype)
+    assert out.is_contiguous() and out.numel() == n_out and out.dtype in (torch.float32, w.dtype)
     if residual is not None:
         assert residual.is_contiguous() and residual.numel() == n_out
-    check(_lib.load().vl2_gemv_bf16(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
+    check(_L(w).vl2_gemv_bf16(x.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
                                     1 if out.dtype == torch.float32 else 0, N, K, act, float(rms_eps), _stream()),
           "vl2_gemv_bf16")
     return out
@@ -272,9 +294,9 @@ def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
     assert q.is_contiguous() and q.numel() == Hq * D and k_cache.stride(1) == 1 and v_cache.stride(1) == 1
     assert k_cache.stride(0) == v_cache.stride(0) and k_cache.shape[0] >= n_pos
     if out is None:
-        out = torch.empty((1, Hq * D), device=q.device, dtype=torch.bfloat16)
+        out = torch.empty((1, Hq * D), device=q.device, dtype=q.dtype)
     ws = decode_workspace(q.device, Hq, Hkv, D)
-    check(_lib.load().vl2_attention_decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+    check(_L(k_cache).vl2_attention_decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
                                            k_cache.stride(0), n_pos, Hq, Hkv, D, float(scale), ws.data_ptr(), _stream()),
           "vl2_attention_decode")
     return out
@@ -288,11 +310,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, B: int, S: i
     for t, h in ((q, Hq), (k, Hkv), (v, Hkv)):
         assert t.dim() == 2 and t.shape == (B * S, h * D) and t.stride(1) == 1
     if out is None:
-        out = torch.empty((B * S, Hq * D), device=q.device, dtype=torch.bfloat16)
+        out = torch.empty((B * S, Hq * D), device=q.device, dtype=q.dtype)
     args = AttnArgs(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(), ldq=q.stride(0),
                     ldk=k.stride(0), ldv=v.stride(0), ldo=out.stride(0), B=B, S=S, Hq=Hq, Hkv=Hkv, D=D,
                     causal=1 if causal else 0, scale=float(scale), reserved=0)
-    check(_lib.load().vl2_attention(C.byref(args), _stream()), "vl2_attention")
+    check(_L(q).vl2_attention(C.byref(args), _stream()), "vl2_attention")
     return out
 
 
@@ -303,7 +325,7 @@ def decode_rope_append(qkv_row: torch.Tensor, cache: torch.Tensor, pos_dev: torc
     _bf16(qkv_row, cache)
     assert qkv_row.is_contiguous() and qkv_row.numel() == (Hq + 2 * Hkv) * D and cache.stride(1) == 1
     assert pos_dev.dtype == torch.int32 and pos_dev.numel() == 1
-    check(_lib.load().vl2_decode_rope_append(qkv_row.data_ptr(), cache.data_ptr(), cache.stride(0), pos_dev.data_ptr(),
+    check(_L(qkv_row).vl2_decode_rope_append(qkv_row.data_ptr(), cache.data_ptr(), cache.stride(0), pos_dev.data_ptr(),
                                              Hq, Hkv, D, inv_freq.data_ptr(), 1 if interleaved else 0, _stream()),
           "vl2_decode_rope_append")
 
@@ -315,7 +337,7 @@ def attention_decode_dyn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.
     _bf16(q, k_cache, v_cache, out)
     assert k_cache.stride(0) == v_cache.stride(0) and pos_dev.dtype == torch.int32
     ws = workspace if workspace is not None else decode_workspace(q.device, Hq, Hkv, D)
-    check(_lib.load().vl2_attention_decode_dyn(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
+    check(_L(q).vl2_attention_decode_dyn(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(),
                                                k_cache.stride(0), pos_dev.data_ptr(), Hq, Hkv, D, float(scale),
                                                ws.data_ptr(), _stream()), "vl2_attention_decode_dyn")
     return out
@@ -332,7 +354,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         out = torch.empty_like(x)
     if residual is not None:
         assert residual.is_contiguous() and residual.shape == x.shape
-    check(_lib.load().vl2_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(residual), out.data_ptr(),
+    check(_L(x).vl2_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(residual), out.data_ptr(),
                                     rows, Cc, float(eps), act, _stream()), "vl2_layernorm")
     return out
 
@@ -344,7 +366,7 @@ def rmsnorm(x: torch.Tensor, gamma: torch.Tensor, eps: float, out: Optional[torc
     Cc = x.shape[-1]
     if out is None:
         out = torch.empty_like(x)
-    check(_lib.load().vl2_rmsnorm(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), x.numel() // Cc, Cc, float(eps),
+    check(_L(x).vl2_rmsnorm(x.data_ptr(), gamma.data_ptr(), out.data_ptr(), x.numel() // Cc, Cc, float(eps),
                                   _stream()), "vl2_rmsnorm")
     return out
 
@@ -357,7 +379,7 @@ def row_stats(x: torch.Tensor):
     assert x.is_contiguous() and x.dim() == 2
     s = torch.empty((x.shape[0], 1), device=x.device, dtype=torch.float32)
     q = torch.empty((x.shape[0], 1), device=x.device, dtype=torch.float32)
-    check(_lib.load().vl2_row_stats(x.data_ptr(), s.data_ptr(), q.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_stats")
+    check(_L(x).vl2_row_stats(x.data_ptr(), s.data_ptr(), q.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_stats")
     return s, q
 
 
@@ -366,7 +388,7 @@ def row_sumsq(x: torch.Tensor) -> torch.Tensor:
     _bf16(x)
     assert x.is_contiguous() and x.dim() == 2
     out = torch.empty((x.shape[0], 1), device=x.device, dtype=torch.float32)
-    check(_lib.load().vl2_row_sumsq(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_sumsq")
+    check(_L(x).vl2_row_sumsq(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()), "vl2_row_sumsq")
     return out
 
 
@@ -375,8 +397,8 @@ def patch_im2col(pixels: torch.Tensor, P: int, Kpad: int) -> torch.Tensor:
     _bf16(pixels)
     assert pixels.is_contiguous() and pixels.dim() == 4 and pixels.shape[1] == 3
     F, _, H, W = pixels.shape
-    out = torch.empty((F * (H // P) * (W // P), Kpad), device=pixels.device, dtype=torch.bfloat16)
-    check(_lib.load().vl2_patch_im2col(pixels.data_ptr(), out.data_ptr(), F, H, W, P, Kpad, _stream()),
+    out = torch.empty((F * (H // P) * (W // P), Kpad), device=pixels.device, dtype=pixels.dtype)
+    check(_L(pixels).vl2_patch_im2col(pixels.data_ptr(), out.data_ptr(), F, H, W, P, Kpad, _stream()),
           "vl2_patch_im2col")
     return out
 
@@ -397,12 +419,12 @@ def patch_embed(pixels: torch.Tensor, weight: torch.Tensor, pos: torch.Tensor, P
     assert pos.shape == (npatch + (1 if clip else 0), Cc)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cc
-    out = torch.empty((F * (npatch + (1 if clip else 0)), Cc), device=pixels.device, dtype=torch.bfloat16)
+    out = torch.empty((F * (npatch + (1 if clip else 0)), Cc), device=pixels.device, dtype=pixels.dtype)
     scratch = torch.empty((F * npatch, Cc), device=pixels.device, dtype=torch.float32) if clip else None
     a = _lib.PatchEmbedArgs(pixels=pixels.data_ptr(), weight=weight.data_ptr(), pos=pos.data_ptr(), cls=_ptr(cls),
                             gamma=_ptr(gamma), beta=_ptr(beta), bias=_ptr(bias), out=out.data_ptr(), scratch=_ptr(scratch),
                             F=F, H=H, W=W, P=P, C=Cc, Kpad=Kpad, eps=float(eps))
-    check(_lib.load().vl2_patch_embed(C.byref(a), _stream()), "vl2_patch_embed")
+    check(_L(pixels).vl2_patch_embed(C.byref(a), _stream()), "vl2_patch_embed")
     return out
 
 
@@ -414,8 +436,8 @@ def clip_embed_finish(patch: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor,
     Cc = patch.shape[-1]
     np_ = patch.shape[0] // F
     assert pos.shape == (np_ + 1, Cc)
-    out = torch.empty((F * (np_ + 1), Cc), device=patch.device, dtype=torch.bfloat16)
-    check(_lib.load().vl2_clip_embed_finish(patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), gamma.data_ptr(),
+    out = torch.empty((F * (np_ + 1), Cc), device=patch.device, dtype=patch.dtype)
+    check(_L(patch).vl2_clip_embed_finish(patch.data_ptr(), cls.data_ptr(), pos.data_ptr(), gamma.data_ptr(),
                                             beta.data_ptr(), out.data_ptr(), F, np_, Cc, float(eps), _stream()),
           "vl2_clip_embed_finish")
     return out
@@ -430,7 +452,7 @@ def dwconv3x3_ln_silu(x: torch.Tensor, w9c: torch.Tensor, gamma: torch.Tensor, b
     F, H, W, Cc = x.shape
     y = torch.empty_like(x)
     pool = torch.empty((F * Cc + F * H * Cc,), device=x.device, dtype=torch.float32) if with_pool else None
-    check(_lib.load().vl2_dwconv3x3_ln_silu(x.data_ptr(), w9c.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+    check(_L(x).vl2_dwconv3x3_ln_silu(x.data_ptr(), w9c.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                             y.data_ptr(), _ptr(pool), F, H, W, Cc, float(eps), _stream()),
           "vl2_dwconv3x3_ln_silu")
     return y, (pool[: F * Cc].view(F, Cc) if with_pool else None)
@@ -443,7 +465,7 @@ def se_scale(y: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     assert y.is_contiguous() and s.dtype == torch.float32 and s.is_contiguous()
     F, Cc = s.shape
     HW = y.numel() // (F * Cc)
-    check(_lib.load().vl2_se_scale(y.data_ptr(), s.data_ptr(), F, HW, Cc, _stream()), "vl2_se_scale")
+    check(_L(y).vl2_se_scale(y.data_ptr(), s.data_ptr(), F, HW, Cc, _stream()), "vl2_se_scale")
     return y
 
 
@@ -463,14 +485,14 @@ def conv3d_k2s2(x: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor
     To, Ho, Wo = (T + 2 * pad - 2) // 2 + 1, (H + 2 * pad - 2) // 2 + 1, (W + 2 * pad - 2) // 2 + 1
     M = To * Ho * Wo
     if out is None:
-        out = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
-    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == torch.bfloat16
+        out = torch.empty((M, N), device=x.device, dtype=x.dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == x.dtype
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     args = GemmArgs(A=x.data_ptr(), W=w.data_ptr(), C=out.data_ptr(), bias=_ptr(bias), lda=K, ldw=w.stride(0),
                     ldc=out.stride(0), ldr=0, M=M, N=N, K=K, act=act, out_f32=0, reserved=bn, conv_C=Cc, conv_T=T, conv_H=H,
                     conv_W=W, conv_pad=pad)
-    check(_lib.load().vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16(conv3d)")
+    check(_L(x).vl2_gemm_bf16(C.byref(args), _stream()), "vl2_gemm_bf16(conv3d)")
     return out
 
 
@@ -481,8 +503,8 @@ def conv3d_im2col(x: torch.Tensor, pad: int) -> torch.Tensor:
     assert x.is_contiguous() and x.dim() == 4
     T, H, W, Cc = x.shape
     To, Ho, Wo = (T + 2 * pad - 2) // 2 + 1, (H + 2 * pad - 2) // 2 + 1, (W + 2 * pad - 2) // 2 + 1
-    out = torch.empty((To * Ho * Wo, 8 * Cc), device=x.device, dtype=torch.bfloat16)
-    check(_lib.load().vl2_conv3d_im2col(x.data_ptr(), out.data_ptr(), T, H, W, Cc, pad, To, Ho, Wo, _stream()),
+    out = torch.empty((To * Ho * Wo, 8 * Cc), device=x.device, dtype=x.dtype)
+    check(_L(x).vl2_conv3d_im2col(x.data_ptr(), out.data_ptr(), T, H, W, Cc, pad, To, Ho, Wo, _stream()),
           "vl2_conv3d_im2col")
     return out
 
@@ -492,7 +514,7 @@ def rope_inplace(qkv: torch.Tensor, S: int, Hq: int, Hkv: int, D: int, q_off: in
     _need_cuda(qkv, inv_freq)
     _bf16(qkv)
     assert qkv.dim() == 2 and qkv.stride(1) == 1 and inv_freq.dtype == torch.float32 and inv_freq.numel() == D // 2
-    check(_lib.load().vl2_rope_inplace(qkv.data_ptr(), qkv.stride(0), S, Hq, Hkv, D, q_off, k_off, pos0,
+    check(_L(qkv).vl2_rope_inplace(qkv.data_ptr(), qkv.stride(0), S, Hq, Hkv, D, q_off, k_off, pos0,
                                        inv_freq.data_ptr(), 1 if interleaved else 0, _stream()), "vl2_rope_inplace")
     return qkv
 
@@ -505,13 +527,14 @@ def rope_interleave_rows(n_heads: int, D: int) -> torch.Tensor:
     return (torch.arange(n_heads)[:, None] * D + per_head[None, :]).reshape(-1)
 
 
-def rope_table(n_pos: int, D: int, theta: float, device) -> torch.Tensor:
-    """[n_pos, D/2] int32: bf16 cos (low half) | bf16 sin (high half) of angle pos * theta^(-2i/D), computed in fp32 and
-    rounded to bf16 as HF does before applying them (HF:mistral/modeling_mistral.py:311-324).  Built once per engine."""
+def rope_table(n_pos: int, D: int, theta: float, device, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """[n_pos, D/2] int32: cos (low half) | sin (high half) of angle pos * theta^(-2i/D) as 16-bit values of the storage
+    type, computed in fp32 and rounded as HF does before applying them (HF:mistral/modeling_mistral.py:311-324).  Built once
+    per engine."""
     inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
     ang = torch.outer(torch.arange(n_pos, dtype=torch.float32), inv)
-    c = ang.cos().to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF
-    sn = ang.sin().to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF
+    c = ang.cos().to(dtype).view(torch.int16).to(torch.int32) & 0xFFFF
+    sn = ang.sin().to(dtype).view(torch.int16).to(torch.int32) & 0xFFFF
     return (c | (sn << 16)).to(torch.int32).contiguous().to(device)
 
 
@@ -520,6 +543,6 @@ def embed_splice(ids: torch.Tensor, dst_row: torch.Tensor, table: torch.Tensor, 
     _bf16(table, out)
     assert ids.dtype == torch.int64 and dst_row.dtype == torch.int32 and ids.numel() == dst_row.numel()
     assert table.is_contiguous() and out.is_contiguous() and table.shape[1] == out.shape[1]
-    check(_lib.load().vl2_embed_splice(ids.data_ptr(), dst_row.data_ptr(), ids.numel(), table.data_ptr(),
+    check(_L(table).vl2_embed_splice(ids.data_ptr(), dst_row.data_ptr(), ids.numel(), table.data_ptr(),
                                        table.shape[0], out.data_ptr(), out.shape[1], _stream()), "vl2_embed_splice")
     return out

@@ -115,7 +115,7 @@ class NvlsAllReduce:
     allocation has no multicast mapping."""
 
     def __init__(self, max_rows: int, hidden: int, device, group=None, use_multicast: bool = True,
-                 inswitch_reduce: bool = False):
+                 inswitch_reduce: bool = False, dtype: torch.dtype = torch.bfloat16):
         import torch.distributed._symmetric_memory as symm_mem
         self.inswitch_reduce = inswitch_reduce
         self.group = group if group is not None else dist.group.WORLD
@@ -131,13 +131,14 @@ class NvlsAllReduce:
             t.zero_()
             return t, symm_mem.rendezvous(t, self.group)
 
-        self.part, self._h_part = sym((max_rows, hidden), torch.bfloat16)
+        self.dtype = dtype
+        self.part, self._h_part = sym((max_rows, hidden), dtype)
         self.out = []
         self._h_out = []
         self.stats = []
         self._h_stats = []
         for _ in range(2):
-            t, h = sym((max_rows, hidden), torch.bfloat16)
+            t, h = sym((max_rows, hidden), dtype)
             self.out.append(t)
             self._h_out.append(h)
             t, h = sym((max_rows,), torch.float32)
@@ -176,6 +177,6 @@ class NvlsAllReduce:
             a.xout_mc = int(self._h_out[i].multicast_ptr)
             a.stats_mc = int(self._h_stats[i].multicast_ptr)
             a.inswitch_reduce = 1 if self.inswitch_reduce else 0
-        _lib.check(_lib.load().vl2_tp_allreduce_stats(C.byref(a), torch.cuda.current_stream().cuda_stream),
+        _lib.check(_lib.load(self.dtype).vl2_tp_allreduce_stats(C.byref(a), torch.cuda.current_stream().cuda_stream),
                    "vl2_tp_allreduce_stats")
         return self.out[i][:rows], self.stats[i][:rows].view(rows, 1)

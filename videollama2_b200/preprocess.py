@@ -108,7 +108,8 @@ def _tables_on(device, in_size: int, out_size: int):
 
 
 def preprocess_frames(frames: torch.Tensor, size: int, mean: Sequence[float], std: Sequence[float], *,
-                      kind: str = "clip", aspect_ratio: str = "pad", return_u8: bool = False):
+                      kind: str = "clip", aspect_ratio: str = "pad", return_u8: bool = False,
+                      dtype: torch.dtype = torch.bfloat16):
     """frames: uint8 CUDA tensor [T,H,W,3] (RGB, HWC — what decord / PIL hand out) -> bf16 [T,3,size,size]
     (+ the resized uint8 window [T,size,size,3] when return_u8)."""
     if not frames.is_cuda:
@@ -122,7 +123,7 @@ def preprocess_frames(frames: torch.Tensor, size: int, mean: Sequence[float], st
     bh, kh, ksh = _tables_on(dev, cw, out_w)
     bv, kv, ksv = _tables_on(dev, ch, out_h)
     lut = torch.from_numpy(normalise_lut(mean, std)).to(dev)
-    out = torch.empty((T, 3, size, size), device=dev, dtype=torch.bfloat16)
+    out = torch.empty((T, 3, size, size), device=dev, dtype=dtype)
     u8 = torch.empty((T, size, size, 3), device=dev, dtype=torch.uint8) if return_u8 else None
     a = PreprocessArgs()
     a.frames, a.T, a.H, a.W = frames.data_ptr(), T, H, W
@@ -133,7 +134,7 @@ def preprocess_frames(frames: torch.Tensor, size: int, mean: Sequence[float], st
     a.bounds_h, a.kk_h, a.ksize_h = bh.data_ptr(), kh.data_ptr(), ksh
     a.bounds_v, a.kk_v, a.ksize_v = bv.data_ptr(), kv.data_ptr(), ksv
     a.lut = lut.data_ptr()
-    lib = _lib.load()
+    lib = _lib.load(dtype)
     tmp = torch.empty((int(lib.vl2_preprocess_workspace(C.byref(a))),), device=dev, dtype=torch.uint8)
     a.tmp, a.out_bf16, a.out_u8 = tmp.data_ptr(), out.data_ptr(), (u8.data_ptr() if u8 is not None else None)
     check(lib.vl2_preprocess_frames(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
