@@ -357,6 +357,8 @@ def main():
     ap.add_argument("--impl", default="vl2", choices=["vl2", "reference"])
     ap.add_argument("--model", default="mistral7b", choices=["mistral7b", "qwen2_7b", "qwen2_7b_v21", "qwen2_72b"],
                     help="qwen2_7b_v21 = the released VideoLLaMA2.1 geometry: SigLIP-so400m@384 tower + stc_connector_v35")
+    ap.add_argument("--dtype", default="bfloat16", choices=["bfloat16", "float16"],
+                    help="16-bit storage type: bfloat16 (headline) or float16 (the reference's inference dtype; libvl2_f16.so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true",
                     help="skip the untimed full-depth parity pass against tests/golden/full_cfg*.pt (on by default)")
@@ -412,6 +414,7 @@ def main():
         cfg = presets.make_config(llm, FRAMES, "stc_connector_v35", presets.SIGLIP_SO400M_384)
     else:
         cfg = presets.make_config(llm, FRAMES)
+    cfg.torch_dtype = args.dtype
     IMG = cfg.vision_config.image_size
     fl = presets.flops(cfg, FRAMES, PROMPT)
     S = fl["S"]
@@ -434,7 +437,7 @@ def main():
     if rank > 0:
         g = torch.Generator(device="cpu").manual_seed(1234 + rank)
         px0 = torch.randn((FRAMES, 3, IMG, IMG), generator=g).to(torch.bfloat16)
-    px_host = px0.pin_memory()
+    px_host = px0.to(cfg.storage_dtype).pin_memory()
     px_dev = px_host.to(dev)
     mask = torch.ones_like(ids_host, dtype=torch.bool)
 
@@ -694,7 +697,7 @@ def main():
         line = {
             "metric": METRIC, "value": world * S / (ms_step * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.dtype == "bfloat16" else "fp16", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(model=args.model, img=IMG, S=S), "frames": FRAMES, "prompt": PROMPT, "seq": S,
                        "global_batch": world, "weights": "device RNG" if args.gpu_rng_weights else
                        f"deterministic synthetic checkpoint (host RNG, seed {presets.SYNTH_SEED}; {weights_s:.0f}s to generate + load)",
