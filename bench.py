@@ -515,7 +515,7 @@ def main():
             torch.cuda.synchronize()
             return (time.perf_counter() - t_a) * 1e3, int(out.shape[1])
 
-        gen(3)                                  # captures the single-token decode graph
+        gen(n_new)                              # sizes the KV cache for the long run and captures the single-token decode graph
         t_short, _ = gen(2)                     # prefill (with cache) + 1 decode step
         t_long, got = gen(n_new)
         if got > 2:

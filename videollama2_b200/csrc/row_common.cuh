@@ -38,6 +38,31 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
   return make_float2(ra, rb);
 }
 
+// Block-wide sum of four floats in one round (blockDim.x multiple of 32, <= 1024).  `red` is 128 floats of shared memory.
+__device__ __forceinline__ float4 block_sum4(float a, float b, float c, float d, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();  // protect `red` against the previous use
+  if (lane == 0) { red[warp] = a; red[32 + warp] = b; red[64 + warp] = c; red[96 + warp] = d; }
+  __syncthreads();
+  float ra = (lane < nw) ? red[lane] : 0.f, rb = (lane < nw) ? red[32 + lane] : 0.f;
+  float rc = (lane < nw) ? red[64 + lane] : 0.f, rd = (lane < nw) ? red[96 + lane] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ra += __shfl_xor_sync(0xffffffffu, ra, o);
+    rb += __shfl_xor_sync(0xffffffffu, rb, o);
+    rc += __shfl_xor_sync(0xffffffffu, rc, o);
+    rd += __shfl_xor_sync(0xffffffffu, rd, o);
+  }
+  return make_float4(ra, rb, rc, rd);
+}
+
 static inline int row_threads(int C) {
   int t = (C / 8 + 31) / 32 * 32;
   if (t > 512) t = 512;
