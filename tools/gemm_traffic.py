@@ -1,5 +1,5 @@
 """ncu csv (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum for the GEMM launches of one step)
--> profiles/r01_gemm_dram_traffic.json: mean DRAM traffic per launch of the dominant kernel."""
+-> profiles/r02_gemm_dram_traffic.json (stamped with the digest of the kernel sources it was taken from): mean DRAM traffic per launch of the dominant kernel."""
 import collections
 import csv
 import json
@@ -21,7 +21,10 @@ def main(path, out):
     rd = sum(d.get("dram__bytes_read.sum", 0) for d in rows)
     wr = sum(d.get("dram__bytes_write.sum", 0) for d in rows)
     t = sum(d.get("gpu__time_duration.sum", 0) for d in rows)
-    res = {"kernel": "gemm_bf16_tcgen05_kernel", "launches": n, "dram_read_bytes_total": rd, "dram_write_bytes_total": wr,
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from videollama2_b200 import build as vl2_build
+    res = {"kernel": "gemm_bf16_tcgen05_kernel", "launches": n, "source_digest": vl2_build._digest(), "dram_read_bytes_total": rd, "dram_write_bytes_total": wr,
            "traffic_bytes_per_launch": (rd + wr) / max(1, n), "time_s_total_under_ncu": t, "source": path}
     json.dump(res, open(out, "w"), indent=1)
     print(res)
