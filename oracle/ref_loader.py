@@ -75,20 +75,26 @@ def load():
     return model
 
 
+def _write_json_atomic(path: str, obj) -> None:
+    """Concurrent test processes share these temp directories: never expose a half-written file."""
+    tmp = f"{path}.{os.getpid()}.tmp"
+    with open(tmp, "w") as fh:
+        json.dump(obj, fh)
+    os.replace(tmp, path)
+
+
 def clip_dir(vcfg) -> str:
     """A local directory whose path contains 'clip' (encoder.py:157) holding the tower + processor configs."""
     d = os.path.join(tempfile.gettempdir(), f"vl2_oracle_clip_{vcfg.hidden}_{vcfg.layers}_{vcfg.image}")
     os.makedirs(d, exist_ok=True)
-    with open(os.path.join(d, "config.json"), "w") as fh:
-        json.dump({"model_type": "clip_vision_model", "hidden_size": vcfg.hidden, "intermediate_size": vcfg.inter,
+    _write_json_atomic(os.path.join(d, "config.json"), {"model_type": "clip_vision_model", "hidden_size": vcfg.hidden, "intermediate_size": vcfg.inter,
                    "num_hidden_layers": vcfg.layers, "num_attention_heads": vcfg.heads, "image_size": vcfg.image,
                    "patch_size": vcfg.patch, "hidden_act": "quick_gelu", "layer_norm_eps": vcfg.eps,
-                   "projection_dim": 768, "num_channels": 3}, fh)
-    with open(os.path.join(d, "preprocessor_config.json"), "w") as fh:
-        json.dump({"crop_size": vcfg.image, "do_center_crop": True, "do_normalize": True, "do_resize": True,
+                   "projection_dim": 768, "num_channels": 3})
+    _write_json_atomic(os.path.join(d, "preprocessor_config.json"), {"crop_size": vcfg.image, "do_center_crop": True, "do_normalize": True, "do_resize": True,
                    "feature_extractor_type": "CLIPFeatureExtractor", "image_processor_type": "CLIPImageProcessor",
                    "image_mean": [0.48145466, 0.4578275, 0.40821073], "image_std": [0.26862954, 0.26130258, 0.27577711],
-                   "resample": 3, "size": vcfg.image}, fh)
+                   "resample": 3, "size": vcfg.image})
     return d
 
 
@@ -96,15 +102,13 @@ def siglip_dir(vcfg) -> str:
     """A local directory whose path contains 'siglip' (encoder.py:159) holding the tower + processor configs."""
     d = os.path.join(tempfile.gettempdir(), f"vl2_oracle_siglip_{vcfg.hidden}_{vcfg.layers}_{vcfg.image}")
     os.makedirs(d, exist_ok=True)
-    with open(os.path.join(d, "config.json"), "w") as fh:
-        json.dump({"model_type": "siglip_vision_model", "hidden_size": vcfg.hidden, "intermediate_size": vcfg.inter,
+    _write_json_atomic(os.path.join(d, "config.json"), {"model_type": "siglip_vision_model", "hidden_size": vcfg.hidden, "intermediate_size": vcfg.inter,
                    "num_hidden_layers": vcfg.layers, "num_attention_heads": vcfg.heads, "image_size": vcfg.image,
                    "patch_size": vcfg.patch, "hidden_act": "gelu_pytorch_tanh", "layer_norm_eps": vcfg.eps,
-                   "num_channels": 3}, fh)
-    with open(os.path.join(d, "preprocessor_config.json"), "w") as fh:
-        json.dump({"do_resize": True, "do_rescale": True, "do_normalize": True, "image_processor_type": "SiglipImageProcessor",
+                   "num_channels": 3})
+    _write_json_atomic(os.path.join(d, "preprocessor_config.json"), {"do_resize": True, "do_rescale": True, "do_normalize": True, "image_processor_type": "SiglipImageProcessor",
                    "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5], "resample": 3, "rescale_factor": 1 / 255,
-                   "size": {"height": vcfg.image, "width": vcfg.image}}, fh)
+                   "size": {"height": vcfg.image, "width": vcfg.image}})
     return d
 
 

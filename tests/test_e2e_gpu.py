@@ -331,3 +331,46 @@ def test_batch_of_two_videos_and_ragged_prompts(setup, cuda):
     assert float(out.logits[1, S_short:].abs().max()) == 0.0
     text_only = model(inputs_embeds=model.get_model().embed_tokens(ids_b[1:2]))
     assert torch.equal(out.logits[1, :S_short], text_only.logits[0])
+
+
+def test_generate_batch_of_two(setup, cuda):
+    """generate() on a right-padded batch of two prompts (one with a video, one text-only that still consumes its image
+    slot): every row equals its own batch-1 generate, shorter outputs are padded with pad_token_id."""
+    cfg, sd, px, ids, gold, model = setup
+    px2 = (px * 0.7).to(cuda)
+    short = ids[0, :8].clone()
+    short[4] = 9                                                    # no placeholder in the short prompt
+    P = ids.shape[1]
+    ids_b = torch.zeros((2, P), dtype=torch.long)
+    ids_b[0] = ids[0]
+    ids_b[1, :8] = short
+    mask_b = torch.zeros((2, P), dtype=torch.bool)
+    mask_b[0] = True
+    mask_b[1, :8] = True
+    images = [(px.to(cuda), "video"), (px2, "video")]
+    out = model.generate(ids_b, images=images, attention_mask=mask_b, max_new_tokens=4, do_sample=False, pad_token_id=0)
+    a = model.generate(ids, images=images[:1], max_new_tokens=4, do_sample=False)
+    b = model.generate(short[None], images=images[1:], max_new_tokens=4, do_sample=False)
+    assert out.shape[0] == 2 and torch.equal(out[0, : a.shape[1]], a[0]) and torch.equal(out[1, : b.shape[1]], b[0])
+    assert int(out[0, a.shape[1]:].abs().sum()) == 0 and int(out[1, b.shape[1]:].abs().sum()) == 0
+
+
+def test_forward_with_past_key_values(setup, cuda):
+    """HF generation-loop call pattern through forward(): prefill with use_cache=True, then one token at a time with the
+    returned past_key_values handle; the greedy tokens equal generate()'s, stale handles are refused."""
+    cfg, sd, px, ids, gold, model = setup
+    images = [(px.to(cuda), "video")]
+    want = model.generate(ids, images=images, max_new_tokens=4, do_sample=False)
+    out = model(input_ids=ids, attention_mask=torch.ones_like(ids), images=images, use_cache=True)
+    assert out.past_key_values is not None and out.past_key_values.get_seq_length() == cfg.seq
+    toks = [int(out.logits[0, -1].argmax())]
+    pkv = out.past_key_values
+    for _ in range(3):
+        step = model(input_ids=torch.tensor([[toks[-1]]]), past_key_values=pkv)
+        assert step.logits.shape == (1, 1, cfg.llm.vocab)
+        toks.append(int(step.logits[0, -1].argmax()))
+        pkv = step.past_key_values
+    assert toks == want[0].tolist()
+    model.generate(ids, images=images, max_new_tokens=2, do_sample=False)        # a new prefill invalidates the handle
+    with pytest.raises(ValueError):
+        model(input_ids=torch.tensor([[toks[-1]]]), past_key_values=pkv)

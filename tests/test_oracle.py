@@ -21,9 +21,10 @@ def test_oracle_matches_reference_goldens(name):
     px, ids = synth.inputs(cfg)
     mine = torch_ref.full_forward(sd, cfg, px, ids, torch.float32)
     g = gold["g32"]
-    assert mine["vit"].shape == g["vit"].shape and rel(mine["vit"], g["vit"]) < 1e-5
-    assert mine["mm"].shape == g["mm"].shape == (cfg.vis_tokens, cfg.llm.hidden) and rel(mine["mm"], g["mm"]) < 1e-5
-    assert mine["logits"].shape == (cfg.seq, cfg.llm.vocab) and rel(mine["logits"], g["logits"]) < 1e-5
+    # fp32 on both sides; the bar leaves room for thread-count-dependent summation orders (a few 1e-6 here), nothing more
+    assert mine["vit"].shape == g["vit"].shape and rel(mine["vit"], g["vit"]) < 3e-5
+    assert mine["mm"].shape == g["mm"].shape == (cfg.vis_tokens, cfg.llm.hidden) and rel(mine["mm"], g["mm"]) < 3e-5
+    assert mine["logits"].shape == (cfg.seq, cfg.llm.vocab) and rel(mine["logits"], g["logits"]) < 3e-5
     # the reference's greedy continuation starts with the argmax of the last prefill position
     assert int(mine["logits"][-1].argmax()) == int(gold["generate_greedy"][0, 0])
     # the bf16 run of the reference differs from its own fp32 run by the noise floor the GPU tests allow for

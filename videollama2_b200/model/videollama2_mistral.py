@@ -23,6 +23,19 @@ class CausalLMOutput(SimpleNamespace):
         return (self.loss, self.logits)[i] if self.loss is not None else (self.logits,)[i]
 
 
+class EngineKVCache:
+    """What `forward(use_cache=True)` returns as `past_key_values`: a handle to the K/V rows the decoder engine holds for
+    the ONE sequence it is decoding (the engine owns a single per-layer cache; a handle is valid until the next prefill).
+    Passing it back with one new token runs a single-token decode step - the call pattern of HF's generation loop
+    (videollama2_mistral.py:63-108 forwards `past_key_values` to the HF decoder)."""
+
+    def __init__(self, engine, serial):
+        self.engine, self.serial = engine, serial
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self.engine.kv_len
+
+
 class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
     config_class = Videollama2MistralConfig
 
@@ -86,8 +99,20 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
                 return_dict=None, **kwargs):
         if output_attentions:
             raise NotImplementedError("output_attentions is not supported by the fused attention kernel")
+        dec = self.get_model().decoder
         if past_key_values is not None:
-            raise NotImplementedError("forward() with past_key_values is not supported; use generate()")
+            # single-token continuation on the engine's cache (HF generation-loop call pattern)
+            if not isinstance(past_key_values, EngineKVCache) or past_key_values.engine is not dec or \
+                    past_key_values.serial != getattr(self, "_cache_serial", None):
+                raise ValueError("past_key_values must be the handle returned by this model's last forward(use_cache=True)")
+            x = inputs_embeds if inputs_embeds is not None else self.get_model().embed_tokens(input_ids)
+            if x.dim() == 3:
+                x = x[0]
+            if x.shape[0] != 1:
+                raise NotImplementedError("forward(past_key_values=...) takes exactly one new token")
+            logits = dec.decode_step(x.to(dec.dtype).contiguous())
+            return CausalLMOutput(loss=None, logits=logits.view(1, 1, -1), past_key_values=past_key_values,
+                                  hidden_states=None, attentions=None)
         if inputs_embeds is None and input_ids is not None and input_ids.shape[1] != 1 and self._vision_only_rank(images):
             return None
         new_len = None
@@ -101,14 +126,15 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         if inputs_embeds.dim() == 2:
             inputs_embeds = inputs_embeds.unsqueeze(0)
         B, S, _ = inputs_embeds.shape
-        dec = self.get_model().decoder
         logits = torch.zeros((B, S, self.vocab_size), device=inputs_embeds.device, dtype=torch.float32)
         hidden = [] if output_hidden_states else None
+        keep = bool(use_cache) and B == 1                           # the engine caches one sequence
         for b in range(B):
             n = S if new_len is None else new_len[b]
             if attention_mask is not None and new_len is None:
                 n = int(attention_mask[b].sum().item())            # right padding only (reference convention)
-            lg, hx = dec.prefill(inputs_embeds[b, :n].to(dec.dtype).contiguous(), all_logits=True)
+            lg, hx = dec.prefill(inputs_embeds[b, :n].to(dec.dtype).contiguous(), all_logits=True, keep_cache=keep,
+                                 max_len=n + int(kwargs.get("cache_extra_positions", 1024)) if keep else None)
             logits[b, :n] = lg
             if hidden is not None:
                 hidden.append(hx)
@@ -117,7 +143,11 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
             shift_logits = logits[:, :-1].reshape(-1, self.vocab_size)
             shift_labels = labels[:, 1:].reshape(-1).to(shift_logits.device)
             loss = torch.nn.functional.cross_entropy(shift_logits, shift_labels, ignore_index=-100)
-        out = CausalLMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden, attentions=None)
+        pkv = None
+        if keep:
+            self._cache_serial = getattr(self, "_cache_serial", 0) + 1
+            pkv = EngineKVCache(dec, self._cache_serial)
+        out = CausalLMOutput(loss=loss, logits=logits, past_key_values=pkv, hidden_states=hidden, attentions=None)
         out.labels = labels
         return out
 
@@ -137,7 +167,7 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         top_p, top_k = float(kwargs.get("top_p", 1.0) or 1.0), int(kwargs.get("top_k", 50) or 0)
         rng = kwargs.get("generator")
         if inputs.shape[0] != 1:
-            raise NotImplementedError("generate supports batch size 1 (as the reference's inference scripts)")
+            return self._generate_batch(inputs, images, attention_mask, kwargs)
         max_new = int(kwargs.get("max_new_tokens", 20))
         eos = kwargs.get("eos_token_id", getattr(self.config, "eos_token_id", None))
         eos_ids = set(eos if isinstance(eos, (list, tuple)) else [eos]) if eos is not None else set()
@@ -157,6 +187,7 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         # prefill once (keeps per-layer K/V), then one weight-streaming decode step per new token
         use_cache = kwargs.get("use_cache", True)
         S = x.shape[0]
+        self._cache_serial = getattr(self, "_cache_serial", 0) + 1        # handles of earlier forward(use_cache=True) calls die here
         logits, _ = dec.prefill(x, all_logits=False, keep_cache=use_cache and max_new > 1, max_len=S + max_new)
         graphed = use_cache and max_new > 1 and dec.graph_decode
         from ..sampling import sample_token
@@ -186,6 +217,38 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
                 x = torch.cat([x, e], 0)
                 logits, _ = dec.prefill(x, all_logits=False)
         return torch.tensor([new_ids], dtype=torch.long, device=self.device)
+
+    def _generate_batch(self, inputs, images, attention_mask, kwargs):
+        """Batch > 1 (HF `generate` semantics of videollama2_mistral.py:110-144 for a padded batch): the rows are decoded
+        one after the other through the batch-1 path - each row keeps its own real tokens (`attention_mask`), takes the
+        images its placeholders consume in order (a row without a placeholder consumes one slot, videollama2_arch.py:181-191)
+        - and the new ids are right-padded with `pad_token_id` to the longest row, as HF pads finished sequences."""
+        from ..mm_utils import splice_plan
+        if kwargs.get("stopping_criteria"):
+            raise NotImplementedError("stopping_criteria with batch > 1 (the criteria objects are built for one prompt)")
+        B = inputs.shape[0]
+        pad = kwargs.get("pad_token_id", getattr(self.config, "pad_token_id", None))
+        if pad is None:
+            eos = kwargs.get("eos_token_id", getattr(self.config, "eos_token_id", None))
+            pad = (eos[0] if isinstance(eos, (list, tuple)) else eos) if eos is not None else 0
+        rows, mm = [], 0
+        for b in range(B):
+            ids = inputs[b]
+            if attention_mask is not None:
+                ids = ids[attention_mask[b].to(torch.bool).to(ids.device)]
+            used = splice_plan(ids.tolist(), [0] * (len(images) if images is not None else 0) + [0], 0)[2] if images is not None else 0
+            imgs = images[mm:mm + used] if images is not None else None
+            mm += used
+            out = self.generate(ids.unsqueeze(0), images=imgs, attention_mask=torch.ones((1, ids.numel()), dtype=torch.bool),
+                                **kwargs)
+            rows.append(None if out is None else out[0])
+        if any(r is None for r in rows):       # a frame-parallel rank that does not decode
+            return None
+        n = max(int(r.numel()) for r in rows)
+        res = torch.full((B, n), int(pad), dtype=torch.long, device=self.device)
+        for b, r in enumerate(rows):
+            res[b, : r.numel()] = r
+        return res
 
     def _generate_greedy_graphed(self, dec, logits, max_new: int, eos_ids, stopping, chunk: int):
         """Greedy decoding with the host off the critical path: the captured single-token graph feeds itself (token and
