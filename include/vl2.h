@@ -309,9 +309,10 @@ int vl2_preprocess_frames(const vl2_preprocess_args* args, void* stream);
  *   CLIP   (gamma != NULL): out[f, 0] = LN(cls + pos[0]);  out[f, 1+p] = LN(conv(pixels[f])[p] + pos[1+p])
  *   SigLIP (gamma == NULL): out[f, p] = conv(pixels[f])[p] + bias + pos[p]
  * pixels bf16 [F,3,H,W]; weight bf16 [C, Kpad] = patch_embedding.weight flattened (c, i, j)-major and zero-padded from
- * 3*P*P to Kpad (multiple of 64, <= 640); pos bf16 [np (+1), C]; out bf16 [F*(np (+1)), C]; scratch fp32 [F*np, C] (CLIP
- * only: the un-normalised rows between the two epilogue passes).  The A operand is gathered from the frames by the kernel
- * (LDG -> 128B-swizzled shared memory); no im2col matrix exists.
+ * 3*P*P to Kpad (multiple of 64, <= 640); pos bf16 [np (+1), C]; out bf16 [F*(np (+1)), C].  The A operand is gathered
+ * from the frames by the kernel (LDG -> 128B-swizzled shared memory); no im2col matrix exists.  A 128-patch row block is
+ * split along C over a thread-block cluster of up to 4 CTAs that keep their accumulators in TMEM and exchange the
+ * LayerNorm statistics through distributed shared memory: nothing un-normalised leaves the SM (`scratch` is unused).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct vl2_patch_embed_args {
   const void* pixels;
@@ -322,7 +323,7 @@ typedef struct vl2_patch_embed_args {
   const void* beta;
   const float* bias;   /* conv bias fp32 [C] (SigLIP) or NULL */
   void* out;
-  float* scratch;
+  float* scratch;      /* unused (kept for ABI stability) */
   int32_t F, H, W, P, C, Kpad;
   float eps;
   int32_t reserved;

@@ -103,4 +103,23 @@ if "--conv" in sys.argv:
         conv[f"implicit bn={bn}"] = round(timed(lambda: ops.conv3d_k2s2(x, wk, bias=b, act=ops.ACT_SILU, pad=1, bn=bn), 10) * 1e3, 1)
     conv["explicit im2col+gemm"] = round(timed(lambda: ops.gemm(ops.conv3d_im2col(x, 1), wk, bias=b, act=ops.ACT_SILU), 10) * 1e3, 1)
     out["conv3d_us"] = conv
+if "--embed" in sys.argv:
+    # ViT embeddings: the fused implicit-GEMM kernel against im2col + GEMM + finish (graph replays, per launch of the chain)
+    emb = {}
+    tw = CLIPVisionTower("synthetic-clip", cfg, vision_config=cfg.vision_config).load_state_dict(sd, dev, prefix=PFX)
+    for frames in (2, 16):
+        px = torch.randn((frames, 3, 336, 336), device=dev).bfloat16()
+        w = tw.w
+        fused = lambda: ops.patch_embed(px, w["patch"], w["pos"], 14, cls=w["cls"], gamma=w["pre_g"], beta=w["pre_b"], eps=1e-5)
+        explicit = lambda: ops.clip_embed_finish(ops.gemm(ops.patch_im2col(px, 14, 640), w["patch"]), w["cls"], w["pos"],
+                                                 w["pre_g"], w["pre_b"], frames, 1e-5)
+        for name, fn in (("fused", fused), ("explicit", explicit)):
+            g = torch.cuda.CUDAGraph()
+            fn(); fn()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                for _ in range(4):
+                    fn()
+            emb[f"{name} frames={frames}"] = round(timed(g.replay, 10) / 4 * 1e3, 1)
+    out["patch_embed_us"] = emb
 print(json.dumps(out))

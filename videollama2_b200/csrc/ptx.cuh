@@ -97,6 +97,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// wait whose acquire has CLUSTER scope: for barriers other CTAs of the cluster arrive on (release.cluster) after writing
+// this CTA's shared memory through DSMEM
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > VL2_MBAR_SPIN_LIMIT) { asm volatile("trap;"); }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Proxy / tcgen05 fences
 // ----------------------------------------------------------------------------------------------

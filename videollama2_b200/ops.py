@@ -420,9 +420,8 @@ def patch_embed(pixels: torch.Tensor, weight: torch.Tensor, pos: torch.Tensor, P
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == Cc
     out = torch.empty((F * (npatch + (1 if clip else 0)), Cc), device=pixels.device, dtype=pixels.dtype)
-    scratch = torch.empty((F * npatch, Cc), device=pixels.device, dtype=torch.float32) if clip else None
     a = _lib.PatchEmbedArgs(pixels=pixels.data_ptr(), weight=weight.data_ptr(), pos=pos.data_ptr(), cls=_ptr(cls),
-                            gamma=_ptr(gamma), beta=_ptr(beta), bias=_ptr(bias), out=out.data_ptr(), scratch=_ptr(scratch),
+                            gamma=_ptr(gamma), beta=_ptr(beta), bias=_ptr(bias), out=out.data_ptr(), scratch=None,
                             F=F, H=H, W=W, P=P, C=Cc, Kpad=Kpad, eps=float(eps))
     check(_L(pixels).vl2_patch_embed(C.byref(a), _stream()), "vl2_patch_embed")
     return out
