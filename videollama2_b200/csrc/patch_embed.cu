@@ -28,8 +28,9 @@ static constexpr int kPeStagesB = 3;
 static constexpr int kPeThreads = 320;                        // warps 0-3 gather; 4 TMA; 5 MMA; 6-9 gather, then epilogue
 static constexpr int kPeStageB = kPeBN * kPeBK * 2;           // 16 KB
 static constexpr int kPeOffB = kPeMaxKB * kPeBM * kPeBK * 2;  // 160 KB of A
-static constexpr int kPeOffStats = kPeOffB + kPeStagesB * kPeStageB;       // [4 ranks][128 rows] float2
-static constexpr int kPeOffBar = kPeOffStats + 4 * 128 * 8;
+static constexpr int kPeMaxStatTiles = 16;                    // 128-column tiles of a whole row (C <= 2048 in the LayerNorm form)
+static constexpr int kPeOffStats = kPeOffB + kPeStagesB * kPeStageB;       // [16 tiles][128 rows] float2
+static constexpr int kPeOffBar = kPeOffStats + kPeMaxStatTiles * 128 * 8;
 static constexpr int kPeSmem = kPeOffBar + 256;
 
 struct PatchEmbedParams {
@@ -60,7 +61,7 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchEmbedP
   if ((smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
   uint8_t* sA = smem;                                              // [nkb][128 rows][128 B], swizzled
   uint8_t* sB = smem + kPeOffB;                                    // [3][128 rows][128 B]
-  float2* sStats = reinterpret_cast<float2*>(smem + kPeOffStats);  // [rank][row] partial (sum, sum of squares)
+  float2* sStats = reinterpret_cast<float2*>(smem + kPeOffStats);  // [global 128-column tile][row] partial (sum, sum of squares)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPeOffBar);
   uint64_t* a_full = bars;            // [10]  gather -> MMA (128 arrivals each)
   uint64_t* b_full = bars + 10;       // [3]   TMA -> MMA
@@ -216,29 +217,37 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const PatchEmbedP
 
     float mean = 0.f, rstd = 1.f;
     if (clip) {
-      // ---- pass 1: this CTA's part of the row statistics
-      float s = 0.f, sq = 0.f;
-      for (int ck = 0; ck < n_chunks; ++ck) {
-        if ((ck & 3) == 0) { mbar_wait(&t_full[ck >> 2], 0); tc_fence_after_sync(); }
-        float x[32];
-        load_chunk(ck, x);
+      // ---- pass 1: the row statistics of this CTA's columns, ONE partial per 128-column tile.  The tiles are the same
+      // whatever the cluster size (column ranges are multiples of 128 whenever the split can vary), and the final sum below
+      // runs over the row's tiles in global order: the result does not depend on how many CTAs shared the row, which keeps
+      // the tower bit-identical for any number of frames per launch (frame sharding).
+      const int tile0 = n_begin / kPeBN;
+      for (int jn = 0; jn < p.n_tiles; ++jn) {
+        mbar_wait(&t_full[jn], 0);
+        tc_fence_after_sync();
+        float s = 0.f, sq = 0.f;
+        for (int ck = jn * 4; ck < min(n_chunks, jn * 4 + 4); ++ck) {
+          float x[32];
+          load_chunk(ck, x);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) { s += x[e]; sq = fmaf(x[e], x[e], sq); }
-      }
-      // ---- exchange over the cluster: every CTA receives every CTA's partial, sums them in rank order
-      const uint32_t slot = smem_u32(sStats + rank * 128 + r);
-      for (uint32_t rr = 0; rr < (uint32_t)p.ns; ++rr) {
-        if (p.ns > 1) {
-          st_cluster_f32x2(slot, rr, s, sq);
-          mbar_arrive_cluster(stat_bar, rr);          // release.cluster: the store above is visible to whoever acquires
-        } else {
-          sStats[r] = make_float2(s, sq);
-          mbar_arrive(stat_bar);
+          for (int e = 0; e < 32; ++e) { s += x[e]; sq = fmaf(x[e], x[e], sq); }
         }
+        // ---- hand the partial to every CTA of the cluster (distributed shared memory)
+        const uint32_t slot = smem_u32(sStats + (tile0 + jn) * 128 + r);
+        if (p.ns > 1) {
+          for (uint32_t rr = 0; rr < (uint32_t)p.ns; ++rr) st_cluster_f32x2(slot, rr, s, sq);
+        } else {
+          sStats[(tile0 + jn) * 128 + r] = make_float2(s, sq);
+        }
+      }
+      for (uint32_t rr = 0; rr < (uint32_t)p.ns; ++rr) {
+        if (p.ns > 1) mbar_arrive_cluster(stat_bar, rr);   // release.cluster: the stores above are visible to whoever acquires
+        else mbar_arrive(stat_bar);
       }
       mbar_wait_cluster(stat_bar, 0);                // acquire.cluster: pairs with the peers' release arrivals
       float ts = 0.f, tq = 0.f;
-      for (int rr = 0; rr < p.ns; ++rr) { const float2 t = sStats[rr * 128 + r]; ts += t.x; tq += t.y; }
+      const int row_tiles = (p.C + kPeBN - 1) / kPeBN;
+      for (int t = 0; t < row_tiles; ++t) { const float2 v2 = sStats[t * 128 + r]; ts += v2.x; tq += v2.y; }
       mean = ts / (float)p.C;
       rstd = rsqrtf(fmaxf(tq / (float)p.C - mean * mean, 0.f) + p.eps);
     }
@@ -331,9 +340,12 @@ extern "C" int vl2_patch_embed(const vl2_patch_embed_args* a, void* stream) {
   for (int i = 0; i < ncand; ++i) {
     const int s = cands[i];
     if (a->C % s != 0 || (a->C / s) % 32 != 0 || a->C / s > kPeMaxTiles * kPeBN) continue;
+    if (clip && s > 1 && (a->C / s) % kPeBN != 0) continue;            // statistics tiles must line up with global 128-column tiles
     if (ns == 0) ns = s;
     else if (blocks_m * s <= sm_count() && a->C / s >= 128) ns = s;      // a finer split only while it still is one wave
   }
+  VL2_REQUIRE(!clip || (a->C + kPeBN - 1) / kPeBN <= kPeMaxStatTiles, VL2_E_UNSUPPORTED, "vl2_patch_embed: C <= %d with a LayerNorm",
+              kPeMaxStatTiles * kPeBN);
   VL2_REQUIRE(ns > 0, VL2_E_UNSUPPORTED, "vl2_patch_embed: C = %d cannot be split into <= 4 column ranges of <= 512", a->C);
   p.ns = ns; p.cols = a->C / ns; p.n_tiles = (p.cols + kPeBN - 1) / kPeBN;
   CUtensorMap tw;
