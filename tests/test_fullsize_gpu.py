@@ -99,6 +99,26 @@ def test_stc_block_real_dims(cuda):
     assert rel(out2, r2) < 1e-2
 
 
+def test_stc_connector_8192_wide(cuda):
+    """The connector of BASELINE config 5 (VideoLLaMA2-72B: hidden 8192): one RegStage block per stage at the real width,
+    Conv3d front end with K = 65536, depthwise kernel split over a 2-CTA cluster (LayerNorm statistics exchanged through
+    DSMEM) - against the fp32 oracle."""
+    from oracle import synth, torch_ref
+    from videollama2_b200.model.projector import STCConnector
+    C = 8192
+    sd = dict(synth.iter_state(synth.stc_specs(1024, C, depth=1, prefix="")))
+    x = torch.randn((1, 4, 36, 1024), generator=torch.Generator().manual_seed(19)).to(torch.bfloat16)      # T = 4, 6 x 6 patches
+    ref = torch_ref.stc_stages({"model.mm_projector." + k: v for k, v in sd.items()}, x.float(), 1, 1, torch.float32)
+    nb = torch_ref.stc_stages({"model.mm_projector." + k: v for k, v in sd.items()}, x, 1, 1, torch.bfloat16)
+    cfg = type("C", (), {"mm_hidden_size": 1024, "hidden_size": C})()
+    stc = STCConnector(cfg, depth=1).load_state_dict(sd, cuda)
+    out = stc(x.to(cuda))
+    assert out.shape == ref["out"].shape
+    assert rel(out, ref["out"]) < max(1e-2, 1.25 * rel(nb["out"], ref["out"]))
+    s1 = stc.run_s1(x[0].to(cuda).view(4, 6, 6, 1024))
+    assert rel(s1, ref["s1"]) < max(1e-2, 1.25 * rel(nb["s1"], ref["s1"]))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE config-2 sizes (no CPU oracle needed: bit-exact identities)
 # ---------------------------------------------------------------------------------------------------------------

@@ -255,7 +255,8 @@ def test_patch_embed_path(cuda, F, H, P, C):
     assert relerr(tok, ref_tok) < 4e-3
 
 
-@pytest.mark.parametrize("F,H,W,C", [(2, 24, 24, 4096), (3, 13, 13, 512), (1, 4, 5, 64)])
+@pytest.mark.parametrize("F,H,W,C", [(2, 24, 24, 4096), (3, 13, 13, 512), (1, 4, 5, 64), (2, 13, 13, 8192), (1, 6, 7, 8192),
+                                     (1, 24, 24, 6144)])
 def test_dwconv_ln_silu_pool_scale(cuda, F, H, W, C):
     from videollama2_b200 import ops
     x = rnd((F, H, W, C), cuda, seed=22)

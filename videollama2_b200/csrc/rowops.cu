@@ -326,25 +326,41 @@ __global__ void __launch_bounds__(512)
 dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w9c,
                          const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                          __nv_bfloat16* __restrict__ y, float* __restrict__ pool_partial, int H, int W, int C,
-                         float eps) {
+                         float eps, int Cl) {
+  // Cl = channels this CTA owns (C, or C / 2 when the row is split over a 2-CTA cluster: 8192-wide connector of the 72B
+  // model).  The LayerNorm runs over all C channels: with a split the two CTAs exchange their partial (sum, sum of squares)
+  // of every pixel pair through distributed shared memory and add them in rank order.
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ __align__(16) uint8_t dw_smem[];   // [9][C] bf16 weights (registers are spent on the pixel window)
+  extern __shared__ __align__(16) uint8_t dw_smem[];   // [9][Cl] bf16 weights (registers are spent on the pixel window)
   __shared__ float red[128];
-  const int h = blockIdx.x % H;
-  const int f = blockIdx.x / H;
-  const int c0 = threadIdx.x * 8;
-  const bool active = c0 < C;
+  __shared__ float4 xchg[2][2];                        // [pair parity][source rank] partial statistics of a pixel pair
+  __shared__ uint64_t xbar[2];                         // [pair parity] both ranks' partials have landed (2 arrivals)
+  const int split = C / Cl;
+  const uint32_t crank = split > 1 ? cluster_ctarank() : 0u;
+  const int row_id = split > 1 ? (int)(blockIdx.x / split) : (int)blockIdx.x;
+  const int h = row_id % H;
+  const int f = row_id / H;
+  const int cb = (int)crank * Cl;                      // first channel of this CTA
+  const int c0 = cb + threadIdx.x * 8;
+  const bool active = (int)threadIdx.x * 8 < Cl;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 9 * (C / 8); i += blockDim.x)
-    reinterpret_cast<uint4*>(dw_smem)[i] = __ldg(reinterpret_cast<const uint4*>(w9c) + i);
+  for (int i = threadIdx.x; i < 9 * (Cl / 8); i += blockDim.x) {
+    const int tap = i / (Cl / 8), v = i - tap * (Cl / 8);
+    reinterpret_cast<uint4*>(dw_smem)[i] = __ldg(reinterpret_cast<const uint4*>(w9c + (int64_t)tap * C + cb) + v);
+  }
   uint4 gp = zero4, bp = zero4;
   if (active) {
     gp = __ldg(reinterpret_cast<const uint4*>(gamma + c0));
     bp = __ldg(reinterpret_cast<const uint4*>(beta + c0));
   }
-  __syncthreads();
-  const uint32_t wbase = smem_u32(dw_smem) + c0 * 2;
+  if (split > 1 && threadIdx.x == 0) {
+    mbar_init(&xbar[0], 2);
+    mbar_init(&xbar[1], 2);
+    fence_barrier_init();
+  }
+  if (split > 1) cluster_sync_all(); else __syncthreads();
+  const uint32_t wbase = smem_u32(dw_smem) + threadIdx.x * 16;
   const __nv_bfloat16* xf = x + (int64_t)f * H * W * C;
   auto load_col = [&](int wcol, uint4 (&col)[3]) {
 #pragma unroll
@@ -381,7 +397,7 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
 #pragma unroll
       for (int dh = 0; dh < 3; ++dh) {
         float x0[8], x1[8], wv[8];
-        unpack8(active ? lds128(wbase + (dh * 3 + dw) * C * 2) : zero4, wv);
+        unpack8(active ? lds128(wbase + (dh * 3 + dw) * Cl * 2) : zero4, wv);
         unpack8(win[dw][dh], x0);
         unpack8(win[dw + 1][dh], x1);
 #pragma unroll
@@ -395,7 +411,29 @@ dwconv3x3_ln_silu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
       s0 += acc0[j]; q0 = fmaf(acc0[j], acc0[j], q0);
       s1 += acc1[j]; q1 = fmaf(acc1[j], acc1[j], q1);
     }
-    const float4 sq = block_sum4(s0, q0, s1, q1, red);
+    float4 sq = block_sum4(s0, q0, s1, q1, red);
+    if (split > 1) {
+      // exchange the pair's partial statistics with the other half of the channels; parity-indexed slots and barriers, so
+      // the next pair's exchange can start before everybody has read this one (a slot is rewritten two pairs later, after a
+      // full cluster-wide barrier phase in between)
+      const int par = (wc >> 1) & 1;
+      const uint32_t phase = (uint32_t)((wc >> 2) & 1);
+      if (threadIdx.x == 0) {
+        for (uint32_t rr = 0; rr < 2; ++rr) {
+          const uint32_t slot = smem_u32(&xchg[par][crank]);
+          asm volatile(
+              "{\n\t.reg .b32 ra;\n\t"
+              "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+              "st.shared::cluster.v4.f32 [ra], {%2, %3, %4, %5};\n\t}"
+              ::"r"(slot), "r"(rr), "f"(sq.x), "f"(sq.y), "f"(sq.z), "f"(sq.w)
+              : "memory");
+          mbar_arrive_cluster(&xbar[par], rr);
+        }
+      }
+      mbar_wait_cluster(&xbar[par], phase);
+      const float4 a = xchg[par][0], b = xchg[par][1];
+      sq = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
     const bool second = wc + 1 < W;
     if (active) {
 #pragma unroll
@@ -770,19 +808,21 @@ extern "C" int vl2_clip_embed_finish(const void* patch, const void* cls, const v
 
 extern "C" int vl2_dwconv3x3_ln_silu(const void* x, const void* w9c, const void* gamma, const void* beta, void* y,
                                      float* pooled, int F, int H, int W, int C, float eps, void* stream) {
-  VL2_REQUIRE(F > 0 && H > 0 && W > 0 && C % 8 == 0 && C <= 8 * 512, VL2_E_BADSHAPE,
-              "vl2_dwconv3x3_ln_silu: C %% 8 == 0 and C <= 4096 required (C=%d)", C);
+  VL2_REQUIRE(F > 0 && H > 0 && W > 0 && C % 8 == 0 && (C <= 8 * 512 || (C <= 16 * 512 && C % 16 == 0)), VL2_E_BADSHAPE,
+              "vl2_dwconv3x3_ln_silu: C %% 8 == 0 and C <= 4096, or C %% 16 == 0 and C <= 8192 (C=%d)", C);
   VL2_REQUIRE(aligned16(x) && aligned16(w9c) && aligned16(y) && aligned16(gamma) && aligned16(beta) && aligned16(pooled),
               VL2_E_BADALIGN, "vl2_dwconv3x3_ln_silu: 16-byte alignment");
   // `pooled` layout: [F*C] pooled means followed by [F*H*C] per-row partial sums (workspace); see vl2.h.
-  int threads = (C / 8 + 31) / 32 * 32;
+  const int split = C > 8 * 512 ? 2 : 1;       // wide rows: two CTAs (a cluster) share a pixel row, half the channels each
+  const int Cl = C / split;
+  int threads = (Cl / 8 + 31) / 32 * 32;
   float* partial = pooled ? pooled + (int64_t)F * C : nullptr;
-  const size_t dw_smem = (size_t)9 * C * sizeof(bf16);
+  const size_t dw_smem = (size_t)9 * Cl * sizeof(bf16);
   if (dw_smem > 48 * 1024) {
     VL2_SMEM_OPT_IN(dwconv3x3_ln_silu_kernel, 9 * 4096 * 2);
   }
-  launch_kernel(dwconv3x3_ln_silu_kernel, dim3((unsigned)(F * H)), dim3(threads), dw_smem, (cudaStream_t)stream, 1, 
-      (const bf16*)x, (const bf16*)w9c, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, partial, H, W, C, eps);
+  launch_kernel(dwconv3x3_ln_silu_kernel, dim3((unsigned)(F * H * split)), dim3(threads), dw_smem, (cudaStream_t)stream, split,
+      (const bf16*)x, (const bf16*)w9c, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, partial, H, W, C, eps, Cl);
   VL2_CHECK_LAUNCH("dwconv3x3_ln_silu_kernel");
   if (pooled) {
     dim3 grid((C + 255) / 256, F);

@@ -59,10 +59,15 @@ class Videollama2MistralForCausalLM(Videollama2MetaForCausalLM):
         self.load_state_dict(state_dict, device)
         return self
 
-    def load_state_dict(self, sd: Dict[str, torch.Tensor], device="cuda"):
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], device="cuda", presharded: bool = False):
+        """`presharded` (tensor-parallel decoder only): the decoder tensors in `sd` are already this rank's slices
+        (tp_decoder.shard_state_dict layout) - how a 72B checkpoint is loaded without any rank holding all of it."""
         dev = torch.device(device)
         m = self.model
-        m.decoder.load_state_dict(sd, dev)
+        if presharded:
+            m.decoder.load_state_dict(sd, dev, presharded=True)
+        else:
+            m.decoder.load_state_dict(sd, dev)
         if m.vision_tower is not None:
             m.vision_tower.load_state_dict(sd, dev, prefix="model.vision_tower.vision_tower.vision_model.")
             m.mm_projector.load_state_dict(sd, dev, prefix="model.mm_projector.")

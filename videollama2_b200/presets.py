@@ -62,6 +62,30 @@ def random_tp_shard(cfg: Videollama2Config, rank: int, world: int, device, seed:
     return sd
 
 
+def random_vision_state(cfg: Videollama2Config, device, seed: int = 20240603):
+    """Random vision tower + connector weights of `cfg` (HF names), the same on every rank (rank-independent generator)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed + 7)
+    sd = {}
+    for name, shape, kind in state_dict_specs(cfg):
+        if not (name.startswith("model.vision_tower.") or name.startswith("model.mm_projector.")):
+            continue
+        x = torch.randn(shape, generator=g, device=device, dtype=torch.float32)
+        if kind == "w":
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            x *= fan_in ** -0.5
+        elif kind == "gain":
+            x = 1.0 + 0.1 * x
+        elif kind == "bias":
+            x *= 0.02
+        else:
+            x *= 0.05
+        sd[name] = x.to(torch.bfloat16)
+    return sd
+
+
 def make_config(llm: dict, frames: int, projector: str = "stc_connector", vision: dict = CLIP_L_336) -> Videollama2Config:
     vc = VisionConfig(**vision)
     siglip = "siglip" in vc.model_type
