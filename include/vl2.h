@@ -131,7 +131,8 @@ typedef struct vl2_gemm_args {
    * The TMA producer gathers each k-block (one tap x 64 channels) of 8 output lines straight from x with ONE box of a 5-D
    * tensor map over x viewed as [T, H/2, 2, W/2, 2C] (out-of-bounds = the zero padding): no im2col matrix exists.
    * Up to 16 x 16 output positions per time step; odd H / W only with conv_pad = 0.  lda is ignored.  bias + activation
-   * epilogues only. */
+   * epilogues only.  reserved4: 0; test hook 1 = use the general epilogue where the lean (TMA-store) one would be
+   * picked (both are parity-tested against each other). */
   int32_t conv_C, conv_T, conv_H, conv_W, conv_pad, reserved4;
   /* RoPE in the epilogue of the fused QKV projection (HF:mistral/modeling_mistral.py:51-82 apply_rotary_pos_emb): output
    * columns [0, rope_cols) are q and k heads of width rope_D whose weight rows were permuted at load so that the rotation
@@ -146,8 +147,10 @@ typedef struct vl2_gemm_args {
 int vl2_gemm_bf16(const vl2_gemm_args* args, void* stream);
 /* Debug aid: with args->reserved2 == 777 CTA 0 records clock64() at its tile boundaries: out[0] = tiles traced (<= 7), and
  * for tile t at out[8t+1..8t+6]: MMA role waits for the accumulator stage / starts issuing / issued its last commit;
- * epilogue warp starts the tile / sees the accumulator complete / stored its last span.  Synchronises the device. */
-int vl2_debug_gemm_trace(long long* host_out64);
+ * epilogue warp starts the tile / sees the accumulator complete / stored its last span; out[64+8t .. 64+8t+5]: phases of that
+ * warp's first 64-column span (start, residual staged, accumulator chunk loaded, first / second half computed, stored).
+ * host_out128: 128 values.  Synchronises the device. */
+int vl2_debug_gemm_trace(long long* host_out128);
 /* Planning only, no device work: out6 = {tile width BN, 1 if the 256-row cta_group::2 tile is used, number of tiles,
  * CTAs (or CTA pairs) the persistent grid runs, rounds = ceil(tiles / that), SM count assumed (148 without a device)}. */
 int vl2_gemm_plan(int M, int N, int K, int with_splitk_ws, int32_t* out6);

@@ -64,5 +64,7 @@ for name, M, N, K, has_bias, has_res, act in SHAPES:
             v = t[8 * i + 1: 8 * i + 7]
             rows.append({"mma_wait_acc": v[1] - v[0], "mma_issue": v[2] - v[1], "epi_wait_acc": v[4] - v[3],
                          "epi_work": v[5] - v[4], "mma_start_at": v[0] - base, "epi_start_at": v[3] - base})
+            ph = t[64 + 8 * i: 64 + 8 * i + 6]   # first span of epilogue warp 4: residual staged / chunk loaded / half 0 / half 1 / stored
+            rows[-1]["span0"] = [ph[j + 1] - ph[j] for j in range(5)]
         res[name]["trace_cycles"] = rows
 print(json.dumps(res))

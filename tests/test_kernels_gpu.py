@@ -591,3 +591,58 @@ def test_patch_embed_fused_siglip(cuda, F, H, P, C):
     patch = torch.nn.functional.conv2d(px.float(), wconv.float(), bias, stride=P).flatten(2).transpose(1, 2)
     ref = (patch + pos.float()).reshape(-1, C)
     assert tok.shape == ref.shape and relerr(tok, ref) < 4e-3
+
+
+@pytest.mark.parametrize("bn", [0, 64, 160, 224, 1128, 1224, 1256])
+@pytest.mark.parametrize("kind", ["bias_act_res", "rms_stats", "swiglu", "plain_tail", "inplace_strided"])
+def test_gemm_lean_and_general_epilogues_agree(cuda, bn, kind):
+    """The lean epilogue (32-column units, TMA stores, residual blocks by TMA load one unit ahead) against the general one
+    (smem transpose + st.global) on the same launch: same arithmetic, so the outputs must agree to the last bf16 bit up to
+    FMA contraction (<= 1 ulp on a handful of elements), and both against the fp32 restatement.  M / N tails, several
+    tiles per CTA (the cross-tile residual prefetch), every tile family."""
+    from videollama2_b200 import ops
+    if kind == "swiglu" and bn in (160, 224, 1224):
+        pytest.skip("SwiGLU with a tile width that is not a multiple of 64 always takes the general epilogue")
+    M, N, K = (9232, 1048, 192) if kind == "plain_tail" else (2100, 2080, 328)
+    a = rnd((M, K), cuda, seed=70)
+    w = rnd((N, K), cuda, 0.06, seed=71)
+    kw, ref = {}, a.float() @ w.float().t()
+    stats = None
+    if kind == "bias_act_res":
+        bias = torch.randn(N, device=cuda)
+        res = rnd((M, N), cuda, seed=72)
+        kw = dict(bias=bias, act=ops.ACT_QUICK_GELU, residual=res)
+        ref = ACTS[1](ref + bias) + res.float()
+    elif kind == "rms_stats":
+        rms_in = (a.float() ** 2).view(M, 8, K // 8).sum(-1).contiguous()
+        res = rnd((M, N), cuda, seed=73)
+        stats = [(torch.empty((M, N // 32), device=cuda), torch.empty((M, N // 32), device=cuda)) for _ in range(2)]
+        kw = dict(rms_in=rms_in, rms_eps=1e-5, residual=res)
+        ref = ref * torch.rsqrt((a.float() ** 2).mean(-1, keepdim=True) + 1e-5) + res.float()
+    elif kind == "swiglu":
+        ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
+        kw = dict(act=ops.ACT_SWIGLU)
+    outs = []
+    for i, general in enumerate((False, True)):
+        k2 = dict(kw)
+        if stats is not None:
+            k2.update(sumsq_out=stats[i][0], rowsum_out=stats[i][1])
+        if kind == "inplace_strided":
+            # out aliases the residual (the residual stream updated in place) and both are column slices of a wider buffer
+            buf = rnd((M, N + 64), cuda, seed=74)
+            view = buf[:, 32:32 + N]
+            if i == 0:
+                ref = ref + view.float()
+            outs.append(ops.gemm(a, w, residual=view, out=view, bn=bn, general_epilogue=general).clone())
+            assert torch.equal(buf[:, :32], rnd((M, N + 64), cuda, seed=74)[:, :32]), "store outside the output slice"
+            assert torch.equal(buf[:, 32 + N:], rnd((M, N + 64), cuda, seed=74)[:, 32 + N:]), "store outside the output slice"
+        else:
+            outs.append(ops.gemm(a, w, bn=bn, general_epilogue=general, **k2))
+    assert relerr(outs[0], ref) < 6e-3 and relerr(outs[1], ref) < 6e-3, (kind, bn)
+    diff = (outs[0].float() - outs[1].float()).abs()
+    assert (diff > 0).float().mean().item() < 1e-3 and relerr(outs[0], outs[1]) < 1e-4, (kind, bn, diff.max().item())
+    if stats is not None:
+        o = outs[0].float()
+        for (sq, sm) in stats:
+            assert torch.allclose(sq.sum(1), (o ** 2).sum(1), rtol=2e-3, atol=1e-2)
+            assert torch.allclose(sm.sum(1), o.sum(1), rtol=2e-3, atol=0.5)

@@ -36,7 +36,7 @@ struct GemmCfg {
   static constexpr int kStageBytesB = kRowsB * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
-  static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias (+ colsum) staging*/ + 256 /*barriers*/;
+  static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias (+ colsum) staging*/ + 512 /*barriers*/;
   static constexpr int kMaxStages = (227 * 1024 - kExtraBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kAccStride = BN > 128 ? 256 : (BN > 64 ? 128 : 64);  // TMEM columns between accumulator stages
@@ -85,7 +85,7 @@ struct GemmParams {
 
 // [0] tiles traced; per tile t (<= 7), at 8*t + 1: MMA waits for the accumulator stage, MMA starts issuing, MMA issued
 // the last commit, epilogue warp 4 starts the tile, its accumulator is complete, its last span is stored.
-__device__ long long g_gemm_trace[64];
+__device__ long long g_gemm_trace[128];   // [64 + 8 t ..]: phases of warp 4's first span of tile t (see the epilogue)
 
 // one 16-byte store replicated by the NVSwitch to every GPU of the multicast group
 __device__ __forceinline__ void multimem_st128(void* mc_addr, const uint4& v) {
@@ -139,9 +139,261 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   return v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Lean epilogue (LEAN = true instantiations): everything the hot launches of the path use - row scale / folded RMSNorm,
+// bias, activation, SwiGLU, RoPE, residual, row statistics, bf16 output - and nothing else (the Conv3d front end, peer /
+// multicast stores, split-K, folded LayerNorm and fp32 output stay in the general epilogue below).  Differences that
+// matter for speed (profiles/r02_gemm_epilogue_trace.txt: the general epilogue spends 2.2 k cycles per 64-column span in
+// its smem -> global store loop and 2.7-3 k staging the residual, against ~1.3 k per 32-column half of arithmetic):
+//   * the unit of work is 32 OUTPUT columns: thread = accumulator row writes its 64 bytes into a [32 rows x 64 B]
+//     staging block (64-byte swizzle, conflict-free), ONE lane issues a TMA store of the block (cp.async.bulk.tensor
+//     shared -> global, clipped at the matrix edge by the tensor map) - no per-thread address arithmetic or stores;
+//   * the residual block of a unit arrives by TMA load into the same staging block (the sum is formed in place), issued
+//     one unit ahead - also across tiles - into the other of the warp's two blocks, so its latency is never exposed;
+//   * feature tests read one register of flags instead of the kernel parameters in constant memory.
+// ---------------------------------------------------------------------------------------------------------------------
+enum : uint32_t { kFBias = 1, kFRes = 2, kFSwiglu = 4, kFScale = 8, kFSumsq = 16, kFRowsum = 32, kFRope = 64, kFTrace = 128 };
+
 template <int BN, bool PAIR>
+__device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const CUtensorMap* tmap_r, const GemmParams& p,
+                                              uint8_t* smem_stage, float* sbias, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                              uint64_t* res_bars, uint32_t tmem_base, uint32_t rank, int tile0,
+                                              int tile_stride) {
+  using Cfg = GemmCfg<BN, PAIR>;
+  constexpr int kTileM = PAIR ? 2 * BM : BM;
+  constexpr uint32_t kUnitBytes = 32 * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ew = warp & 3, grp = (warp - 4) >> 2, etid = threadIdx.x - 128;
+  const int row_in_tile = ew * 32 + lane;
+  uint32_t feat = (p.bias != nullptr ? kFBias : 0u) | (p.residual != nullptr ? kFRes : 0u) |
+                  (p.act == VL2_ACT_SWIGLU ? kFSwiglu : 0u) |
+                  ((p.row_scale != nullptr || p.rms_sumsq_in != nullptr) ? kFScale : 0u) |
+                  (p.sumsq_out != nullptr ? kFSumsq : 0u) | (p.rowsum_out != nullptr ? kFRowsum : 0u) |
+                  (p.rope_tab != nullptr ? kFRope : 0u) | ((p.trace && blockIdx.x == 0 && etid == 0) ? kFTrace : 0u);
+  asm volatile("" : "+r"(feat));   // keep the flags in a register (do not re-derive them from constant memory)
+  int act = p.act;
+  asm volatile("" : "+r"(act));
+  uint8_t* stg = smem_stage + (warp - 4) * 4096;                 // two [32 x 64 B] blocks
+  const uint32_t my_row = smem_u32(stg) + lane * 64;
+  const uint32_t swz = (uint32_t)(lane >> 1) & 3u;               // 64-byte swizzle key of this thread's row
+  uint64_t* rbar = res_bars + (warp - 4) * 2;
+  uint32_t uc = 0;          // units this warp has processed: staging block uc & 1, residual barrier phase (uc >> 1) & 1
+  bool res_ahead = false;   // (lane 0) the first residual block of the coming tile is already in flight
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int it = 0;
+  for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    const bool etr = (feat & kFTrace) && it < 7;
+    if (etr) g_gemm_trace[8 * it + 4] = clock64();
+    const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
+    const int n0 = (tile / p.num_m_tiles) * BN;
+    const int row = m0 + row_in_tile;
+    const bool row_ok = row < p.M;
+    const int rbase = m0 + ew * 32;
+    const bool first_ok = grp * 64 < BN && n0 + grp * 64 < p.N;   // this warp has work in the tile
+    if ((feat & kFRes) && lane == 0 && first_ok && !res_ahead) {
+      bulk_wait_read_all();
+      mbar_arrive_expect_tx(&rbar[uc & 1], kUnitBytes);
+      tma_load_2d(stg + (uc & 1) * kUnitBytes, tmap_r, &rbar[uc & 1], n0 + grp * 64, rbase);
+    }
+    res_ahead = false;
+    if (feat & kFBias) {   // stage this tile's bias slice once (double buffered by accumulator stage)
+      for (int i = etid; i < BN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    }
+    float rs = 1.f;
+    if (feat & kFScale) {
+      if (p.row_scale != nullptr && row_ok) rs = p.row_scale[row];
+      if (p.rms_sumsq_in != nullptr && row_ok) {
+        // sum the producer's per-32-column partials in a fixed order (deterministic: no atomics anywhere)
+        const float* pp = p.rms_sumsq_in + (int64_t)row * p.rms_nparts;
+        const int nvec = (p.rms_nparts % 4 == 0) ? p.rms_nparts : 0;   // rows are 16-byte aligned only then
+        float q = 0.f;
+        int i = 0;
+        for (; i + 4 <= nvec; i += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(pp + i);
+          q += (t4.x + t4.y) + (t4.z + t4.w);
+        }
+        for (; i < p.rms_nparts; ++i) q += pp[i];
+        rs *= rsqrtf(q * p.rms_inv_dim + p.rms_eps);
+      }
+    }
+    if (feat & kFBias) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    const uint32_t sb = smem_u32(sbias + as * 256);
+    mbar_wait(&tmem_full[as], aphase);
+    tc_fence_after_sync();
+    if (etr) g_gemm_trace[8 * it + 5] = clock64();
+    const uint32_t taddr = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
+    uint32_t v[32];
+    if (first_ok) tmem_ld_32x32(taddr + grp * 64, v);
+
+#pragma unroll 1
+    for (int sp = grp; sp * 64 < BN; sp += 2) {
+      const int c0 = sp * 64;                       // first accumulator column of the span inside the tile
+      const int col0 = n0 + c0;
+      if (col0 >= p.N) break;                       // warp-uniform
+      const int span = min(min(64, BN - c0), p.N - col0);   // valid accumulator columns (multiple of 8)
+      const bool next_span_ok = c0 + 128 < BN && col0 + 128 < p.N;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {              // 32 accumulator columns at a time
+        if (hf * 32 >= span) break;                 // warp-uniform
+        const bool ptr_ = etr && sp == grp && hf == 0;
+        if (ptr_) g_gemm_trace[64 + 8 * it] = clock64();
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        // next 32 columns of this warp: second half of the span, else the first half of its next span
+        if (hf == 0 && span > 32) tmem_ld_32x32(taddr + c0 + 32, v);
+        else if (next_span_ok) tmem_ld_32x32(taddr + c0 + 128, v);
+        if (ptr_) g_gemm_trace[64 + 8 * it + 1] = clock64();
+        if (feat & kFScale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] *= rs;
+        }
+        if (feat & kFBias) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bq = lds_f4(sb + (c0 + hf * 32 + g * 4) * 4);
+            x[g * 4 + 0] += bq.x; x[g * 4 + 1] += bq.y; x[g * 4 + 2] += bq.z; x[g * 4 + 3] += bq.w;
+          }
+        }
+        if (!(feat & kFSwiglu)) {
+          // one branch per activation (warp-uniform), each with a fully unrolled body
+          if (act == VL2_ACT_QUICK_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fast_sigmoid_mul(x[j], 1.702f * 1.4426950408889634f);
+          } else if (act == VL2_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fast_sigmoid_mul(x[j], 1.4426950408889634f);
+          } else if (act == VL2_ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752f));
+          } else if (act == VL2_ACT_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
+          }
+          if ((feat & kFRope) && col0 + hf * 32 < p.rope_cols && row_ok) {
+            // 32 accumulator columns = 16 rotation pairs of one head, frequencies i0 .. i0 + 15, angle of this row's position
+            const int i0 = ((col0 + hf * 32) % p.rope_D) >> 1;
+            const uint4* tr = reinterpret_cast<const uint4*>(p.rope_tab + (int64_t)(p.rope_pos0 + row) * (p.rope_D >> 1) + i0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 cs = __ldg(tr + g);
+              const uint32_t e[4] = {cs.x, cs.y, cs.z, cs.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float c = bf16_lo(e[j]), sn = bf16_hi(e[j]);
+                const float a = x[g * 8 + 2 * j], b = x[g * 8 + 2 * j + 1];
+                x[g * 8 + 2 * j] = a * c - b * sn;
+                x[g * 8 + 2 * j + 1] = b * c + a * sn;
+              }
+            }
+          }
+        }
+        if (ptr_) g_gemm_trace[64 + 8 * it + 2] = clock64();
+        // ---- staging block of this output unit.  SwiGLU: 64 accumulator columns (both halves) make one 32-column unit
+        const bool unit_begins = !((feat & kFSwiglu) && hf == 1);
+        const uint32_t blk = my_row + (uc & 1) * kUnitBytes;
+        if (unit_begins) {
+          if (lane == 0) {
+            bulk_wait_read_all();     // the stores issued so far have read their blocks (the last one >= half a unit ago)
+            if (feat & kFRes) {
+              // residual of this warp's NEXT unit -> the other block: rest of the span, next span, or the next tile
+              int nc = -1, nr = rbase;
+              if (hf == 0 && span > 32) nc = col0 + 32;
+              else if (next_span_ok) nc = col0 + 128;
+              else if (tile + tile_stride < num_tiles) {
+                const int tn = tile + tile_stride;
+                const int n0n = (tn / p.num_m_tiles) * BN;
+                if (grp * 64 < BN && n0n + grp * 64 < p.N) {
+                  nc = n0n + grp * 64;
+                  nr = (tn % p.num_m_tiles) * kTileM + (int)rank * BM + ew * 32;
+                  res_ahead = true;
+                }
+              }
+              if (nc >= 0) {
+                mbar_arrive_expect_tx(&rbar[(uc + 1) & 1], kUnitBytes);
+                tma_load_2d(stg + ((uc + 1) & 1) * kUnitBytes, tmap_r, &rbar[(uc + 1) & 1], nc, nr);
+              }
+            }
+          }
+          if (feat & kFRes) mbar_wait(&rbar[uc & 1], (uc >> 1) & 1);
+          else __syncwarp();
+        }
+        if (ptr_) g_gemm_trace[64 + 8 * it + 3] = clock64();
+        bool unit_ends = true;
+        if (feat & kFSwiglu) {
+          // accumulator columns interleave (gate, up): 32 columns -> 16 outputs = chunks 2*hf, 2*hf+1 of the unit
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float g0 = x[g * 16 + 4 * j + 0], u0 = x[g * 16 + 4 * j + 1];
+              const float g1 = x[g * 16 + 4 * j + 2], u1 = x[g * 16 + 4 * j + 3];
+              o[j] = pack_bf16(fast_sigmoid_mul(g0, 1.4426950408889634f) * u0, fast_sigmoid_mul(g1, 1.4426950408889634f) * u1);
+            }
+            sts128(blk + ((uint32_t)((hf * 2 + g) ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+          }
+          unit_ends = (hf == 1) || (span <= 32);
+        } else {
+          float ssq = 0.f, ssum = 0.f;
+          if (feat & kFRes) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 r = lds128(blk + ((uint32_t)(g ^ swz) << 4));
+              x[g * 8 + 0] += bf16_lo(r.x); x[g * 8 + 1] += bf16_hi(r.x);
+              x[g * 8 + 2] += bf16_lo(r.y); x[g * 8 + 3] += bf16_hi(r.y);
+              x[g * 8 + 4] += bf16_lo(r.z); x[g * 8 + 5] += bf16_hi(r.z);
+              x[g * 8 + 6] += bf16_lo(r.w); x[g * 8 + 7] += bf16_hi(r.w);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 pk = make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
+                                        pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+            sts128(blk + ((uint32_t)(g ^ swz) << 4), pk);
+            if ((feat & kFSumsq) && hf * 32 + g * 8 < span) {   // statistics of what the consumer will read
+              const float a0 = bf16_lo(pk.x), a1 = bf16_hi(pk.x), a2 = bf16_lo(pk.y), a3 = bf16_hi(pk.y);
+              const float a4 = bf16_lo(pk.z), a5 = bf16_hi(pk.z), a6 = bf16_lo(pk.w), a7 = bf16_hi(pk.w);
+              ssq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+              if (feat & kFRowsum) ssum += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+            }
+          }
+          if ((feat & kFSumsq) && row_ok) {   // one slot per 32 output columns
+            const int64_t slot = (int64_t)row * (p.N >> 5) + ((col0 + hf * 32) >> 5);
+            p.sumsq_out[slot] = ssq;
+            if (feat & kFRowsum) p.rowsum_out[slot] = ssum;
+          }
+        }
+        if (ptr_) g_gemm_trace[64 + 8 * it + 4] = clock64();
+        if (unit_ends) {
+          fence_proxy_async_smem();   // this thread's smem writes -> visible to the TMA unit
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmap_c, stg + (uc & 1) * kUnitBytes, (feat & kFSwiglu) ? (col0 >> 1) : (col0 + hf * 32), rbase);
+            bulk_commit_group();
+          }
+          ++uc;
+        }
+        if (ptr_) g_gemm_trace[64 + 8 * it + 5] = clock64();
+      }
+    }
+    if (etr) g_gemm_trace[8 * it + 6] = clock64();
+    // all tcgen05.ld of this thread have completed (wait::ld above) -> hand the accumulator stage back
+    tmem_ld_wait();
+    tc_fence_before_sync();
+    if (PAIR) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]);
+  }
+  if (lane == 0) bulk_wait_read_all();   // the staging blocks must outlive the last stores' reads
+}
+
+template <int BN, bool PAIR, bool LEAN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
                          const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs), 1 = peer
@@ -162,16 +414,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;    // [2]        MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;             // [2]        epilogue -> MMA
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bars = tmem_empty + 3;              // [kEpiWarps][2]  lean epilogue: residual block landed (TMA)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_k_blocks = (p.K + BK - 1) / BK;
 
   pdl_launch_dependents();   // let the next kernel's CTAs take the SMs this kernel's last wave leaves idle
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (LEAN) {
+      tma_prefetch_desc(&tmap_c);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmap_r);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -181,6 +437,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues arrive on the leader's
+    }
+    if (LEAN) {
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bars[i], 1);
     }
     fence_barrier_init();
   }
@@ -199,7 +458,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      const bool conv = p.conv_C > 0;
+      const bool conv = !LEAN && p.conv_C > 0;
       const int slabs = conv ? p.conv_C / BK : 1;
       for (int item = tile0; item < p.num_items; item += tile_stride) {
         const WorkItem w = decode_item(item, p, num_k_blocks);
@@ -275,8 +534,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (tr) { g_gemm_trace[8 * it + 3] = clock64(); g_gemm_trace[0] = it + 1; }
       }
     }
+  } else if (warp >= 4 && LEAN) {
+    epilogue_lean<BN, PAIR>(&tmap_c, &tmap_r, p, smem_stage, sbias, tmem_full, tmem_empty, res_bars, tmem_base, rank, tile0,
+                            tile_stride);
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== general epilogue (8 warps) =====================
     // warp w: TMEM lane quarter (w & 3); the two warps of a quarter take alternate 64-column spans of the tile.
     // Accumulator rows live one per thread (TMEM lane == row), which is the wrong shape for global memory, so every
     // 32-row x 64-column block goes through a per-warp swizzled smem buffer: residual rows come in and output rows go
@@ -397,6 +659,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int span = min(min(64, BN - c0), p.N - col0);   // 8..64 valid accumulator columns (multiple of 8)
         uint32_t v[32];
         float ssq = 0.f, ssum = 0.f;                  // sum of squares / sum of this thread's (row's) outputs in the span
+        const bool ptr_ = etr && sp == 0;             // phase trace of this warp's first span
+        if (ptr_) g_gemm_trace[64 + 8 * it] = clock64();
         tmem_ld_32x32(taddr + c0, v);
         // residual block -> smem (coalesced: 8 lanes x 16 B per row)
         if (res != nullptr) {
@@ -410,10 +674,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           __syncwarp();
         }
+        if (ptr_) g_gemm_trace[64 + 8 * it + 1] = clock64();
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {              // two 32-column halves of the span
           if (hf * 32 >= span) break;                 // warp-uniform
           tmem_ld_wait();
+          if (ptr_ && hf == 0) g_gemm_trace[64 + 8 * it + 2] = clock64();
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
@@ -525,6 +791,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
           }
+          if (ptr_) g_gemm_trace[64 + 8 * it + 3 + hf] = clock64();
         }
         if (p.sumsq_out != nullptr && row_ok && !swiglu && !p.out_f32) {
           // one slot per 32 output columns: this span owns slots col0/32 (its sum) and col0/32 + 1 (zero)
@@ -564,6 +831,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           __syncwarp();  // the buffer is reused by the next span
         }
+        if (ptr_) g_gemm_trace[64 + 8 * it + 5] = clock64();
       }
       if (etr) g_gemm_trace[8 * it + 6] = clock64();
       if (w.part == 0) {   // every thread has consumed the partials: re-arm the counter for the next launch
@@ -586,6 +854,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 static bool splitk_enabled();
+static bool lean_enabled();
 
 template <int BN, bool PAIR>
 static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
@@ -641,7 +910,6 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   const int m_rows = conv ? conv_To * kConvLine * kConvLine : a->M;     // rows of the (padded) A enumeration
   p.num_m_tiles = (m_rows + tile_m - 1) / tile_m;
   p.num_n_tiles = (a->N + BN - 1) / BN;
-  VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR>), Cfg::kSmemBytes);
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
   // Split-K of the last, partial round (wave quantisation): the `rem` tiles left for `slots` CTAs (pairs) are cut into s
@@ -683,8 +951,32 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   }
   p.num_items = p.split_first + (tiles - p.split_first) * p.split_s;
   const int units = p.num_items < slots ? p.num_items : slots;
-  VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
-                               Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, p));
+  // The lean epilogue (TMA stores / TMA residual loads, see epilogue_lean) serves every launch that does not need the
+  // general one; reserved4 == 1 forces the general kernel (test hook: both must agree).
+  const bool swiglu = a->act == VL2_ACT_SWIGLU;
+  const bool lean = lean_enabled() && a->reserved4 != 1 && !conv && a->n_bcast == 0 && a->mc_out == nullptr && !a->out_f32 &&
+                    a->ln_sum_in == nullptr && p.split_s == 1 && !(swiglu && BN % 64 != 0);
+  CUtensorMap tc = ta, tr = ta;   // placeholders when unused (never dereferenced)
+  if (lean) {
+    // output / residual as [32 rows x 32 columns] boxes, 64-byte swizzle: one box = one staging block of an epilogue warp
+    uint64_t dims[2] = {(uint64_t)(swiglu ? a->N / 2 : a->N), (uint64_t)a->M};
+    uint64_t str[1] = {(uint64_t)a->ldc * 2};
+    uint32_t box[2] = {32, 32};
+    int rc = make_tmap_bf16(&tc, a->C, 2, dims, str, box, 64);
+    if (rc) return rc;
+    if (a->residual != nullptr) {
+      uint64_t strr[1] = {(uint64_t)a->ldr * 2};
+      rc = make_tmap_bf16(&tr, a->residual, 2, dims, strr, box, 64);
+      if (rc) return rc;
+    }
+    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, true>), Cfg::kSmemBytes);
+    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, true>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
+                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tc, tr, p));
+  } else {
+    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, false>), Cfg::kSmemBytes);
+    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, false>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
+                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tc, tr, p));
+  }
   VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return VL2_OK;
 }
@@ -700,7 +992,7 @@ struct TileChoice { int bn; bool pair; };
 static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair, bool allow_split) {
   const int kb = (K + BK - 1) / BK;
   const double L = 3000.0;
-  const int extra = 8 * 4096 + 2048 + 256;
+  const int extra = 8 * 4096 + 2048 + 512;
   static const int cands[7] = {256, 224, 192, 160, 128, 96, 64};
   TileChoice best = {256, false};
   double best_cost = -1;
@@ -751,6 +1043,16 @@ static bool splitk_enabled() {
   return v == 1;
 }
 
+// VL2_GEMM_LEAN=0 routes every launch through the general epilogue (A/B measurements; both are parity-tested).
+static bool lean_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VL2_GEMM_LEAN");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -782,10 +1084,10 @@ extern "C" int vl2_gemm_plan(int M, int N, int K, int with_splitk_ws, int32_t* o
 }
 
 // Debug: copy the tile-boundary cycle trace of the last traced launch (args->reserved2 == 777) to host memory.
-extern "C" int vl2_debug_gemm_trace(long long* host_out64) {
-  VL2_REQUIRE(host_out64 != nullptr, VL2_E_BADSHAPE, "vl2_debug_gemm_trace: null output");
+extern "C" int vl2_debug_gemm_trace(long long* host_out128) {
+  VL2_REQUIRE(host_out128 != nullptr, VL2_E_BADSHAPE, "vl2_debug_gemm_trace: null output");
   VL2_CHECK_CUDA(cudaDeviceSynchronize());
-  VL2_CHECK_CUDA(cudaMemcpyFromSymbol(host_out64, vl2::g_gemm_trace, 64 * sizeof(long long)));
+  VL2_CHECK_CUDA(cudaMemcpyFromSymbol(host_out128, vl2::g_gemm_trace, 128 * sizeof(long long)));
   return VL2_OK;
 }
 

@@ -71,7 +71,7 @@ static encode_tiled_fn get_encode() {
 }
 
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, int swizzle_bytes) {
   encode_tiled_fn enc = get_encode();
   if (!enc) return set_error(VL2_E_CUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -90,7 +90,8 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   const CUtensorMapDataType elem_type = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 #endif
   CUresult r = enc(map, elem_type, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(VL2_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu, box0 %u)", (int)r,
