@@ -125,9 +125,12 @@ def test_gemm_plan_for_the_path_shapes(lib):
     for M, N, K in [(1776, 6144, 4096), (1776, 4096, 4096), (1776, 4096, 14336), (9232, 3072, 1024), (9232, 4096, 1024),
                     (9232, 1024, 4096), (11664, 1152, 1152)]:
         p = plan(M, N, K)
-        assert p["pair"] == 1 and p["bn"] in (224, 256) and p["sms"] == 148
+        assert p["pair"] == 1 and p["bn"] in (224, 256, 416) and p["sms"] == 148   # 416 = the wide 224 + 192 tile
         tile_m = 256
         assert p["tiles"] == -(-M // tile_m) * -(-N // p["bn"]) and p["rounds"] == -(-p["tiles"] // p["slots"])
+    o_proj, down = plan(1776, 4096, 4096), plan(1776, 4096, 14336)   # one round of wide tiles instead of two narrow ones
+    assert (o_proj["bn"], o_proj["rounds"], down["bn"], down["rounds"]) == (416, 1, 416, 1)
+    assert plan(1776, 6144, 4096)["bn"] == 224 and plan(9232, 1024, 1024)["bn"] == 256
     small = plan(300, 520, 256)                  # a matrix narrower than a wide tile gets a narrow single-CTA tile
     assert small["pair"] == 0 and small["bn"] <= 128 and small["rounds"] == 1
     out = (ctypes.c_int32 * 6)()

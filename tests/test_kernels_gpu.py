@@ -593,7 +593,7 @@ def test_patch_embed_fused_siglip(cuda, F, H, P, C):
     assert tok.shape == ref.shape and relerr(tok, ref) < 4e-3
 
 
-@pytest.mark.parametrize("bn", [0, 64, 160, 224, 1128, 1224, 1256])
+@pytest.mark.parametrize("bn", [0, 64, 160, 224, 1128, 1224, 1256, 2416])
 @pytest.mark.parametrize("kind", ["bias_act_res", "rms_stats", "swiglu", "plain_tail", "inplace_strided"])
 def test_gemm_lean_and_general_epilogues_agree(cuda, bn, kind):
     """The lean epilogue (32-column units, TMA stores, residual blocks by TMA load one unit ahead) against the general one
@@ -601,8 +601,8 @@ def test_gemm_lean_and_general_epilogues_agree(cuda, bn, kind):
     FMA contraction (<= 1 ulp on a handful of elements), and both against the fp32 restatement.  M / N tails, several
     tiles per CTA (the cross-tile residual prefetch), every tile family."""
     from videollama2_b200 import ops
-    if kind == "swiglu" and bn in (160, 224, 1224):
-        pytest.skip("SwiGLU with a tile width that is not a multiple of 64 always takes the general epilogue")
+    if kind == "swiglu" and bn in (160, 224, 1224, 2416):
+        pytest.skip("SwiGLU with a tile width that is not a multiple of 64 always takes the general epilogue (no wide SwiGLU tile)")
     M, N, K = (9232, 1048, 192) if kind == "plain_tail" else (2100, 2080, 328)
     a = rnd((M, K), cuda, seed=70)
     w = rnd((N, K), cuda, 0.06, seed=71)
@@ -625,6 +625,8 @@ def test_gemm_lean_and_general_epilogues_agree(cuda, bn, kind):
     outs = []
     for i, general in enumerate((False, True)):
         k2 = dict(kw)
+        if general and bn == 2416:
+            bn = 1224          # the wide (224 + 192, two accumulators) tile exists for the lean epilogue only
         if stats is not None:
             k2.update(sumsq_out=stats[i][0], rowsum_out=stats[i][1])
         if kind == "inplace_strided":
@@ -646,3 +648,49 @@ def test_gemm_lean_and_general_epilogues_agree(cuda, bn, kind):
         for (sq, sm) in stats:
             assert torch.allclose(sq.sum(1), (o ** 2).sum(1), rtol=2e-3, atol=1e-2)
             assert torch.allclose(sm.sum(1), o.sum(1), rtol=2e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("M,N,K", [(1776, 4096, 512), (600, 1000, 192), (9232, 4096, 128), (100, 424, 64), (257, 8, 72)])
+def test_gemm_wide_two_accumulator_tile(cuda, M, N, K):
+    """The 256 x 416 cta_group::2 tile (two TMEM accumulators of 224 and 192 columns sharing every A k-block, one accumulator
+    stage): forced through the test hook, against fp32 and against the narrow pair tile.  Several rounds per CTA
+    (9232 x 4096: 370 tiles on 74 pairs) exercise the un-overlapped accumulator hand-over; N tails end inside the first
+    or the second accumulator, or (N = 8) leave the second one entirely out of bounds."""
+    from videollama2_b200 import ops
+    a = rnd((M, K), cuda, seed=80)
+    w = rnd((N, K), cuda, 0.06, seed=81)
+    bias = torch.randn(N, device=cuda)
+    res = rnd((M, N), cuda, seed=82)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    stats = N % 32 == 0
+    outs = []
+    for bn in (2416, 1224):
+        kw = {}
+        if stats:
+            kw = dict(sumsq_out=torch.empty((M, N // 32), device=cuda), rowsum_out=torch.empty((M, N // 32), device=cuda))
+        out = ops.gemm(a, w, bias=bias, residual=res, bn=bn, **kw)
+        assert relerr(out, ref) < 6e-3, (bn, M, N, K)
+        if stats:
+            o = out.float()
+            assert torch.allclose(kw["sumsq_out"].sum(1), (o ** 2).sum(1), rtol=2e-3, atol=1e-2)
+            assert torch.allclose(kw["rowsum_out"].sum(1), o.sum(1), rtol=2e-3, atol=0.5)
+        outs.append(out)
+    assert relerr(outs[0], outs[1]) < 1e-4
+    out2 = ops.gemm(a, w, bias=bias, residual=res, bn=2416)
+    assert torch.equal(out2, outs[0]), "the wide tile must be bit-reproducible"
+
+
+def test_gemm_wide_tile_is_chosen_for_single_round_launches(cuda):
+    """The decoder's o_proj / down_proj at S = 1776 (7 x 10 wide tiles = one round of the 74 CTA pairs) go to the wide tile
+    by the cost model; the result equals the forced narrow tile's up to accumulation order."""
+    import ctypes
+    from videollama2_b200 import _lib, ops
+    out6 = (ctypes.c_int32 * 6)()
+    assert _lib.load().vl2_gemm_plan(1776, 4096, 4096, 0, out6) == 0
+    if out6[5] != 148:
+        pytest.skip("plan pinned for 148 SMs")
+    assert (out6[0], out6[1], out6[2], out6[4]) == (416, 1, 70, 1)
+    a = rnd((1776, 4096), cuda, seed=83)
+    w = rnd((4096, 4096), cuda, 0.02, seed=84)
+    res = rnd((1776, 4096), cuda, seed=85)
+    assert relerr(ops.gemm(a, w, residual=res), ops.gemm(a, w, residual=res, bn=1224)) < 1e-4

@@ -28,21 +28,33 @@ static constexpr int kConvLine = 16;                      // Conv3d front end: o
 // PAIR = true: two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 on a 256 x BN tile; each CTA stages its own
 // 128 rows of A and HALF of the B tile, so a k-block costs 16 KB + BN*64 B of smem/L2 traffic per CTA instead of
 // 16 KB + BN*128 B, and the ring is deep enough (6 stages at BN=256) to cover the L2/HBM latency at the full MMA rate.
-template <int BN, bool PAIR>
+// BN2 > 0 (the "wide" tile, lean pair kernel only): the tile is BN + BN2 columns wide, held as TWO accumulators (TMEM columns
+// [0, BN) and [256, 256 + BN2)) that share every A k-block: a k-block then costs 16 KB of A for 416 columns instead of
+// 224 or 256 - the narrow pair tiles are bound by operand ingest (~58 B/clk/SM), not by the tensor pipe.  All 512
+// TMEM columns hold ONE accumulator stage, so the epilogue is not overlapped with the next tile: the tile choice uses it
+// only where a launch then needs a single round of the persistent grid (o_proj / down_proj at S = 1776).
+template <int BN, bool PAIR, int BN2 = 0>
 struct GemmCfg {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 32 in [64,256]");
+  static_assert(BN2 == 0 || (PAIR && BN2 % 32 == 0 && BN2 >= 64 && BN2 <= 256), "a wide tile is a cta_group::2 tile");
+  static constexpr int kTileN = BN + BN2;
   static constexpr int kRowsB = PAIR ? BN / 2 : BN;   // B rows staged by one CTA
+  static constexpr int kRowsB2 = BN2 / 2;             // ... of the second accumulator
   static constexpr int kStageBytesA = BM * BK * 2;
-  static constexpr int kStageBytesB = kRowsB * BK * 2;
+  static constexpr int kStageBytesB1 = kRowsB * BK * 2;
+  static constexpr int kStageBytesB = (kRowsB + kRowsB2) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStagingBytes = kEpiWarps * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
   static constexpr int kExtraBytes = kStagingBytes + 2 * 256 * 4 /*bias (+ colsum) staging*/ + 512 /*barriers*/;
   static constexpr int kMaxStages = (227 * 1024 - kExtraBytes) / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kAccStages = BN2 > 0 ? 1 : 2;
   static constexpr int kAccStride = BN > 128 ? 256 : (BN > 64 ? 128 : 64);  // TMEM columns between accumulator stages
-  static constexpr int kTmemCols = 2 * kAccStride;                           // power of two >= 32
+  static constexpr int kTmemCols = 2 * kAccStride;                           // power of two >= 32 (wide: 512 = both accumulators)
   static constexpr int kSmemBytes = kStages * kStageBytes + kExtraBytes;
   static constexpr int kChunks = BN / 32;
+  static_assert(BN2 == 0 || kAccStride == 256, "wide tile: the second accumulator lives at TMEM column 256");
+  static_assert(kStageBytesB1 % 1024 == 0 || BN2 == 0, "second B box must start on a swizzle-atom boundary");
 };
 
 struct GemmParams {
@@ -155,13 +167,14 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // ---------------------------------------------------------------------------------------------------------------------
 enum : uint32_t { kFBias = 1, kFRes = 2, kFSwiglu = 4, kFScale = 8, kFSumsq = 16, kFRowsum = 32, kFRope = 64, kFTrace = 128 };
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int BN2>
 __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const CUtensorMap* tmap_r, const GemmParams& p,
                                               uint8_t* smem_stage, float* sbias, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint64_t* res_bars, uint32_t tmem_base, uint32_t rank, int tile0,
                                               int tile_stride) {
-  using Cfg = GemmCfg<BN, PAIR>;
+  using Cfg = GemmCfg<BN, PAIR, BN2>;
   constexpr int kTileM = PAIR ? 2 * BM : BM;
+  constexpr int kTileN = Cfg::kTileN;
   constexpr uint32_t kUnitBytes = 32 * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ew = warp & 3, grp = (warp - 4) >> 2, etid = threadIdx.x - 128;
@@ -174,6 +187,9 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
   asm volatile("" : "+r"(feat));   // keep the flags in a register (do not re-derive them from constant memory)
   int act = p.act;
   asm volatile("" : "+r"(act));
+  // accumulator columns per output unit: 32, or 64 for SwiGLU ((gate, up) pairs -> 32 outputs).  The two warps of a TMEM
+  // lane quarter take alternate units.
+  const int ustep = (feat & kFSwiglu) ? 64 : 32;
   uint8_t* stg = smem_stage + (warp - 4) * 4096;                 // two [32 x 64 B] blocks
   const uint32_t my_row = smem_u32(stg) + lane * 64;
   const uint32_t swz = (uint32_t)(lane >> 1) & 3u;               // 64-byte swizzle key of this thread's row
@@ -181,26 +197,32 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
   uint32_t uc = 0;          // units this warp has processed: staging block uc & 1, residual barrier phase (uc >> 1) & 1
   bool res_ahead = false;   // (lane 0) the first residual block of the coming tile is already in flight
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // TMEM column of tile column c: the second accumulator of a wide tile starts at column 256
+  auto tcol = [](int c) { return (BN2 > 0 && c >= BN) ? 256 + (c - BN) : c; };
   int it = 0;
   for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
-    const int as = it & 1;
-    const uint32_t aphase = (it >> 1) & 1;
+    const int as = Cfg::kAccStages == 2 ? (it & 1) : 0;
+    const uint32_t aphase = Cfg::kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
     const bool etr = (feat & kFTrace) && it < 7;
     if (etr) g_gemm_trace[8 * it + 4] = clock64();
     const int m0 = (tile % p.num_m_tiles) * kTileM + (int)rank * BM;
-    const int n0 = (tile / p.num_m_tiles) * BN;
+    const int n0 = (tile / p.num_m_tiles) * kTileN;
     const int row = m0 + row_in_tile;
     const bool row_ok = row < p.M;
     const int rbase = m0 + ew * 32;
-    const bool first_ok = grp * 64 < BN && n0 + grp * 64 < p.N;   // this warp has work in the tile
+    const int c_first = grp * ustep;
+    const bool first_ok = c_first < kTileN && n0 + c_first < p.N;   // this warp has work in the tile
     if ((feat & kFRes) && lane == 0 && first_ok && !res_ahead) {
       bulk_wait_read_all();
       mbar_arrive_expect_tx(&rbar[uc & 1], kUnitBytes);
-      tma_load_2d(stg + (uc & 1) * kUnitBytes, tmap_r, &rbar[uc & 1], n0 + grp * 64, rbase);
+      tma_load_2d(stg + (uc & 1) * kUnitBytes, tmap_r, &rbar[uc & 1], n0 + c_first, rbase);
     }
     res_ahead = false;
-    if (feat & kFBias) {   // stage this tile's bias slice once (double buffered by accumulator stage)
-      for (int i = etid; i < BN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    if (feat & kFBias) {
+      // stage this tile's bias slice once; double buffered by accumulator stage (a wide tile has one stage and uses the
+      // whole area: one more barrier keeps its writes behind the previous tile's reads)
+      if (Cfg::kAccStages == 1) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      for (int i = etid; i < kTileN; i += kEpiThreads) sbias[as * 256 + i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
     }
     float rs = 1.f;
     if (feat & kFScale) {
@@ -226,27 +248,27 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
     if (etr) g_gemm_trace[8 * it + 5] = clock64();
     const uint32_t taddr = tmem_base + as * Cfg::kAccStride + ((uint32_t)(ew * 32) << 16);
     uint32_t v[32];
-    if (first_ok) tmem_ld_32x32(taddr + grp * 64, v);
+    if (first_ok) tmem_ld_32x32(taddr + tcol(c_first), v);
 
 #pragma unroll 1
-    for (int sp = grp; sp * 64 < BN; sp += 2) {
-      const int c0 = sp * 64;                       // first accumulator column of the span inside the tile
-      const int col0 = n0 + c0;
+    for (int c0 = c_first; c0 < kTileN; c0 += 2 * ustep) {
+      const int col0 = n0 + c0;                     // first accumulator column of the unit
       if (col0 >= p.N) break;                       // warp-uniform
-      const int span = min(min(64, BN - c0), p.N - col0);   // valid accumulator columns (multiple of 8)
-      const bool next_span_ok = c0 + 128 < BN && col0 + 128 < p.N;
+      const int ucols = min(min(ustep, kTileN - c0), p.N - col0);   // its valid accumulator columns (multiple of 8)
+      const bool next_unit_ok = c0 + 2 * ustep < kTileN && col0 + 2 * ustep < p.N;
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {              // 32 accumulator columns at a time
-        if (hf * 32 >= span) break;                 // warp-uniform
-        const bool ptr_ = etr && sp == grp && hf == 0;
+      for (int hf = 0; hf < 2; ++hf) {              // 32 accumulator columns at a time (two passes only for SwiGLU)
+        if (hf * 32 >= ucols) break;                // warp-uniform
+        const int cc = c0 + hf * 32;                // tile column of these 32 accumulator columns
+        const bool ptr_ = etr && c0 == c_first && hf == 0;
         if (ptr_) g_gemm_trace[64 + 8 * it] = clock64();
         tmem_ld_wait();
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        // next 32 columns of this warp: second half of the span, else the first half of its next span
-        if (hf == 0 && span > 32) tmem_ld_32x32(taddr + c0 + 32, v);
-        else if (next_span_ok) tmem_ld_32x32(taddr + c0 + 128, v);
+        // this warp's next 32 accumulator columns: second half of a SwiGLU unit, else the first of its next unit
+        if (hf == 0 && ucols > 32) tmem_ld_32x32(taddr + tcol(cc + 32), v);
+        else if (next_unit_ok) tmem_ld_32x32(taddr + tcol(c0 + 2 * ustep), v);
         if (ptr_) g_gemm_trace[64 + 8 * it + 1] = clock64();
         if (feat & kFScale) {
 #pragma unroll
@@ -255,7 +277,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
         if (feat & kFBias) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const float4 bq = lds_f4(sb + (c0 + hf * 32 + g * 4) * 4);
+            const float4 bq = lds_f4(sb + (cc + g * 4) * 4);
             x[g * 4 + 0] += bq.x; x[g * 4 + 1] += bq.y; x[g * 4 + 2] += bq.z; x[g * 4 + 3] += bq.w;
           }
         }
@@ -274,9 +296,9 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
           }
-          if ((feat & kFRope) && col0 + hf * 32 < p.rope_cols && row_ok) {
+          if ((feat & kFRope) && col0 < p.rope_cols && row_ok) {
             // 32 accumulator columns = 16 rotation pairs of one head, frequencies i0 .. i0 + 15, angle of this row's position
-            const int i0 = ((col0 + hf * 32) % p.rope_D) >> 1;
+            const int i0 = (col0 % p.rope_D) >> 1;
             const uint4* tr = reinterpret_cast<const uint4*>(p.rope_tab + (int64_t)(p.rope_pos0 + row) * (p.rope_D >> 1) + i0);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -293,22 +315,20 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
           }
         }
         if (ptr_) g_gemm_trace[64 + 8 * it + 2] = clock64();
-        // ---- staging block of this output unit.  SwiGLU: 64 accumulator columns (both halves) make one 32-column unit
-        const bool unit_begins = !((feat & kFSwiglu) && hf == 1);
+        // ---- staging block of this output unit
         const uint32_t blk = my_row + (uc & 1) * kUnitBytes;
-        if (unit_begins) {
+        if (hf == 0) {
           if (lane == 0) {
             bulk_wait_read_all();     // the stores issued so far have read their blocks (the last one >= half a unit ago)
             if (feat & kFRes) {
-              // residual of this warp's NEXT unit -> the other block: rest of the span, next span, or the next tile
+              // residual of this warp's NEXT unit -> the other block: the next unit of the tile, or the next tile's first
               int nc = -1, nr = rbase;
-              if (hf == 0 && span > 32) nc = col0 + 32;
-              else if (next_span_ok) nc = col0 + 128;
+              if (next_unit_ok) nc = col0 + 2 * ustep;
               else if (tile + tile_stride < num_tiles) {
                 const int tn = tile + tile_stride;
-                const int n0n = (tn / p.num_m_tiles) * BN;
-                if (grp * 64 < BN && n0n + grp * 64 < p.N) {
-                  nc = n0n + grp * 64;
+                const int n0n = (tn / p.num_m_tiles) * kTileN;
+                if (c_first < kTileN && n0n + c_first < p.N) {
+                  nc = n0n + c_first;
                   nr = (tn % p.num_m_tiles) * kTileM + (int)rank * BM + ew * 32;
                   res_ahead = true;
                 }
@@ -323,7 +343,6 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
           else __syncwarp();
         }
         if (ptr_) g_gemm_trace[64 + 8 * it + 3] = clock64();
-        bool unit_ends = true;
         if (feat & kFSwiglu) {
           // accumulator columns interleave (gate, up): 32 columns -> 16 outputs = chunks 2*hf, 2*hf+1 of the unit
 #pragma unroll
@@ -337,7 +356,6 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
             }
             sts128(blk + ((uint32_t)((hf * 2 + g) ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
           }
-          unit_ends = (hf == 1) || (span <= 32);
         } else {
           float ssq = 0.f, ssum = 0.f;
           if (feat & kFRes) {
@@ -355,7 +373,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
             const uint4 pk = make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
                                         pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
             sts128(blk + ((uint32_t)(g ^ swz) << 4), pk);
-            if ((feat & kFSumsq) && hf * 32 + g * 8 < span) {   // statistics of what the consumer will read
+            if ((feat & kFSumsq) && g * 8 < ucols) {   // statistics of what the consumer will read
               const float a0 = bf16_lo(pk.x), a1 = bf16_hi(pk.x), a2 = bf16_lo(pk.y), a3 = bf16_hi(pk.y);
               const float a4 = bf16_lo(pk.z), a5 = bf16_hi(pk.z), a6 = bf16_lo(pk.w), a7 = bf16_hi(pk.w);
               ssq += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
@@ -363,17 +381,17 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
             }
           }
           if ((feat & kFSumsq) && row_ok) {   // one slot per 32 output columns
-            const int64_t slot = (int64_t)row * (p.N >> 5) + ((col0 + hf * 32) >> 5);
+            const int64_t slot = (int64_t)row * (p.N >> 5) + (col0 >> 5);
             p.sumsq_out[slot] = ssq;
             if (feat & kFRowsum) p.rowsum_out[slot] = ssum;
           }
         }
         if (ptr_) g_gemm_trace[64 + 8 * it + 4] = clock64();
-        if (unit_ends) {
+        if (hf * 32 + 32 >= ucols) {   // the unit is complete
           fence_proxy_async_smem();   // this thread's smem writes -> visible to the TMA unit
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(tmap_c, stg + (uc & 1) * kUnitBytes, (feat & kFSwiglu) ? (col0 >> 1) : (col0 + hf * 32), rbase);
+            tma_store_2d(tmap_c, stg + (uc & 1) * kUnitBytes, (feat & kFSwiglu) ? (col0 >> 1) : col0, rbase);
             bulk_commit_group();
           }
           ++uc;
@@ -390,12 +408,14 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
   if (lane == 0) bulk_wait_read_all();   // the staging blocks must outlive the last stores' reads
 }
 
-template <int BN, bool PAIR, bool LEAN>
+template <int BN, bool PAIR, bool LEAN, int BN2 = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                         const GemmParams p) {
-  using Cfg = GemmCfg<BN, PAIR>;
+                         const __grid_constant__ CUtensorMap tmap_b2, const __grid_constant__ CUtensorMap tmap_c,
+                         const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+  static_assert(BN2 == 0 || LEAN, "the wide tile exists for the lean epilogue only");
+  using Cfg = GemmCfg<BN, PAIR, BN2>;
+  constexpr int kTileN = Cfg::kTileN;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs), 1 = peer
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // persistent tile loop start / stride
   const int tile_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -424,6 +444,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (BN2 > 0) tma_prefetch_desc(&tmap_b2);
     if (LEAN) {
       tma_prefetch_desc(&tmap_c);
       if (p.residual != nullptr) tma_prefetch_desc(&tmap_r);
@@ -463,7 +484,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int item = tile0; item < p.num_items; item += tile_stride) {
         const WorkItem w = decode_item(item, p, num_k_blocks);
         const int m0 = (w.tile % p.num_m_tiles) * kTileM + (int)rank * BM;
-        const int n0 = (w.tile / p.num_m_tiles) * BN + (int)rank * (PAIR ? BN / 2 : 0);
+        const int nt0 = (w.tile / p.num_m_tiles) * kTileN;                    // first column of the tile
+        const int n0 = nt0 + (int)rank * (PAIR ? BN / 2 : 0);                 // first B row this CTA stages
         // conv: this 128-row tile = output lines ho_base .. ho_base + 7 of time step `to`
         const int line0 = m0 / kConvLine, to = line0 / kConvLine, ho_base = line0 % kConvLine;
         int tap = w.kb0 / slabs, slab = w.kb0 - tap * slabs;
@@ -492,6 +514,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (PAIR) tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
           else tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage], kb * BK, n0);
+          if (BN2 > 0)   // second accumulator's half of B (wide tile: always a pair)
+            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB + Cfg::kStageBytesB1, &tmap_b2, &full_bar[stage], kb * BK,
+                             nt0 + BN + (int)rank * (BN2 / 2));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -500,13 +525,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0 && rank == 0) {
       // ===================== MMA issuer (leader CTA only for a pair) =====================
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(kTileM, BN2 > 0 ? BN2 : BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int item = tile0; item < p.num_items; item += tile_stride, ++it) {
         const WorkItem w = decode_item(item, p, num_k_blocks);
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = Cfg::kAccStages == 2 ? (it & 1) : 0;
+        const uint32_t aphase = Cfg::kAccStages == 2 ? ((it >> 1) & 1) : (it & 1);
         const bool tr = p.trace && blockIdx.x == 0 && it < 7;
         if (tr) g_gemm_trace[8 * it + 1] = clock64();
         mbar_wait(&tmem_empty[as], aphase ^ 1);  // epilogue drained this accumulator stage
@@ -524,6 +550,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
             if (PAIR) umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0) || (k != 0));
             else umma_bf16_ss(d_tmem, da, db, idesc, (kb != w.kb0) || (k != 0));
+            if (BN2 > 0) {   // the same A k-slice into the second accumulator (TMEM column 256)
+              const uint64_t db2 = umma_desc_sw128(b_addr + Cfg::kStageBytesB1 + k * 32, 16, 1024);
+              umma_bf16_ss_pair(d_tmem + 256, da, db2, idesc2, (kb != w.kb0) || (k != 0));
+            }
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -535,8 +565,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp >= 4 && LEAN) {
-    epilogue_lean<BN, PAIR>(&tmap_c, &tmap_r, p, smem_stage, sbias, tmem_full, tmem_empty, res_bars, tmem_base, rank, tile0,
-                            tile_stride);
+    epilogue_lean<BN, PAIR, BN2>(&tmap_c, &tmap_r, p, smem_stage, sbias, tmem_full, tmem_empty, res_bars, tmem_base, rank,
+                                 tile0, tile_stride);
   } else if (warp >= 4) {
     // ===================== general epilogue (8 warps) =====================
     // warp w: TMEM lane quarter (w & 3); the two warps of a quarter take alternate 64-column spans of the tile.
@@ -855,11 +885,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
 static bool splitk_enabled();
 static bool lean_enabled();
+static bool wide_enabled();
 
-template <int BN, bool PAIR>
+static bool lean_eligible(const vl2_gemm_args* a) {   // launches the lean epilogue can serve (modulo split-K / SwiGLU tile width)
+  return lean_enabled() && a->reserved4 != 1 && a->conv_C == 0 && a->n_bcast == 0 && a->mc_out == nullptr && !a->out_f32 &&
+         a->ln_sum_in == nullptr;
+}
+
+template <int BN, bool PAIR, int BN2 = 0>
 static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, PAIR>;
-  CUtensorMap ta, tb;
+  using Cfg = GemmCfg<BN, PAIR, BN2>;
+  CUtensorMap ta, tb, tb2;
   const bool conv = a->conv_C > 0;
   int conv_To = 0, conv_Ho = 0, conv_Wo = 0;
   if (conv) {
@@ -893,6 +929,12 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
     uint32_t box[2] = {BK, (uint32_t)Cfg::kRowsB};
     int rc = make_tmap_bf16(&tb, a->W, 2, dims, str, box);
     if (rc) return rc;
+    tb2 = tb;
+    if (BN2 > 0) {
+      uint32_t box2[2] = {BK, (uint32_t)Cfg::kRowsB2};
+      rc = make_tmap_bf16(&tb2, a->W, 2, dims, str, box2);
+      if (rc) return rc;
+    }
   }
   GemmParams p;
   p.C = a->C; p.bias = a->bias; p.residual = a->residual; p.row_scale = a->row_scale;
@@ -909,7 +951,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   p.conv_C = conv ? a->conv_C : 0; p.conv_pad = a->conv_pad; p.conv_Ho = conv_Ho; p.conv_Wo = conv_Wo; p.conv_To = conv_To;
   const int m_rows = conv ? conv_To * kConvLine * kConvLine : a->M;     // rows of the (padded) A enumeration
   p.num_m_tiles = (m_rows + tile_m - 1) / tile_m;
-  p.num_n_tiles = (a->N + BN - 1) / BN;
+  p.num_n_tiles = (a->N + Cfg::kTileN - 1) / Cfg::kTileN;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
   // Split-K of the last, partial round (wave quantisation): the `rem` tiles left for `slots` CTAs (pairs) are cut into s
@@ -941,7 +983,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
     const bool forced = rem > 0 && a->reserved3 >= 2 && a->reserved3 <= 4 && num_kb >= a->reserved3;   // test hook
     if (forced) s = a->reserved3;
     const size_t need = kSplitFlagBytes + (size_t)rem * (s > 1 ? s - 1 : 0) * tile_m * BN * sizeof(float);
-    if (s > 1 && (splitk_enabled() || forced) && a->splitk_ws != nullptr && (size_t)a->splitk_ws_bytes >= need && (size_t)2 * rem * kSplitFlagStride * 4 <= kSplitFlagBytes &&
+    if (BN2 == 0 && s > 1 && (splitk_enabled() || forced) && a->splitk_ws != nullptr && (size_t)a->splitk_ws_bytes >= need && (size_t)2 * rem * kSplitFlagStride * 4 <= kSplitFlagBytes &&
         aligned16(a->splitk_ws)) {
       p.split_first = tiles - rem;
       p.split_s = s;
@@ -954,8 +996,7 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
   // The lean epilogue (TMA stores / TMA residual loads, see epilogue_lean) serves every launch that does not need the
   // general one; reserved4 == 1 forces the general kernel (test hook: both must agree).
   const bool swiglu = a->act == VL2_ACT_SWIGLU;
-  const bool lean = lean_enabled() && a->reserved4 != 1 && !conv && a->n_bcast == 0 && a->mc_out == nullptr && !a->out_f32 &&
-                    a->ln_sum_in == nullptr && p.split_s == 1 && !(swiglu && BN % 64 != 0);
+  const bool lean = lean_eligible(a) && p.split_s == 1 && !(swiglu && BN % 64 != 0);
   CUtensorMap tc = ta, tr = ta;   // placeholders when unused (never dereferenced)
   if (lean) {
     // output / residual as [32 rows x 32 columns] boxes, 64-byte swizzle: one box = one staging block of an epilogue warp
@@ -969,13 +1010,20 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
       rc = make_tmap_bf16(&tr, a->residual, 2, dims, strr, box, 64);
       if (rc) return rc;
     }
+  }
+  if constexpr (BN2 > 0) {
+    VL2_REQUIRE(lean && !swiglu, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: the wide tile serves lean, non-SwiGLU launches only");
+    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, true, BN2>), Cfg::kSmemBytes);
+    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, true, BN2>, dim3(2 * units), dim3(kGemmThreads),
+                                 Cfg::kSmemBytes, stream, 2, ta, tb, tb2, tc, tr, p));
+  } else if (lean) {
     VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, true>), Cfg::kSmemBytes);
     VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, true>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
-                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tc, tr, p));
+                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tb2, tc, tr, p));
   } else {
     VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, false>), Cfg::kSmemBytes);
     VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, false>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
-                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tc, tr, p));
+                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tb2, tc, tr, p));
   }
   VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return VL2_OK;
@@ -987,14 +1035,16 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
 //   * the smem ring must cover the L2/HBM latency (~3000 cycles): a k-block cannot retire faster than L / stages
 //     (this is what holds the 4-stage 128x256 single-CTA tile at ~750 cycles per k-block = 83 % tensor-active);
 //   * a launch costs waves x tile time + one un-overlapped epilogue.
-struct TileChoice { int bn; bool pair; };
+struct TileChoice { int bn; bool pair; int bn2; };
+static constexpr int kWideBN = 224, kWideBN2 = 192;   // the wide tile: 416 columns in two accumulators
+static constexpr double kIngestBytesPerClk = 58.0;    // L2 -> smem per SM, measured (scripts/vit_shard_probe.py --sweep)
 
-static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair, bool allow_split) {
+static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair, bool allow_split, bool allow_wide) {
   const int kb = (K + BK - 1) / BK;
   const double L = 3000.0;
   const int extra = 8 * 4096 + 2048 + 512;
   static const int cands[7] = {256, 224, 192, 160, 128, 96, 64};
-  TileChoice best = {256, false};
+  TileChoice best = {256, false, 0};
   double best_cost = -1;
   for (int pair = (allow_pair ? 1 : 0); pair >= 0; --pair) {
     for (int i = 0; i < 7; ++i) {
@@ -1025,6 +1075,24 @@ static TileChoice choose_tile(int M, int N, int K, int sms, bool allow_pair, boo
       if (best_cost < 0 || cost < best_cost * 0.98) { best_cost = cost; best.bn = bn; best.pair = pair != 0; }
     }
   }
+  // The wide tile against the winner.  Both sides are costed with the operand-ingest bound here (a k-block cannot retire
+  // faster than its bytes arrive: 16 KB of A + the CTA's share of B at ~58 B/clk - what holds the 256 x 224 / 256 x 256
+  // pair tiles at 530 / 565 cycles per k-block although their MMAs need 448 / 512), which is the whole point of the wide
+  // tile: 832 cycles of MMA per k-block for 416 columns on the same 16 KB of A.  Its epilogue is exposed on every tile.
+  if (allow_wide && allow_pair && best.pair && N >= kWideBN + kWideBN2 / 2) {
+    const long slots = sms / 2;
+    const long mt = (M + 255) / 256;
+    const long tiles_n = mt * ((N + best.bn - 1) / best.bn);
+    const double ing_n = (16384.0 + best.bn * 64.0) / kIngestBytesPerClk;
+    const double per_n = ing_n > 2.0 * best.bn ? ing_n : 2.0 * best.bn;
+    const double cost_n = (double)((tiles_n + slots - 1) / slots) * (kb * per_n + 600.0) + 2000.0 + best.bn * 16.0;
+    const int wn = kWideBN + kWideBN2;
+    const long tiles_w = mt * ((N + wn - 1) / wn);
+    const double per_w = 2.0 * wn;                       // MMA-bound (ingest: (16384 + 64 * 416) / 58 = 741)
+    const double epi_w = 12000.0;                        // 13 units of 32 columns over two warps per lane quarter
+    const double cost_w = (double)((tiles_w + slots - 1) / slots) * (kb * per_w + 600.0 + epi_w) + 2000.0;
+    if (cost_w < 0.97 * cost_n) { best.bn = kWideBN; best.bn2 = kWideBN2; best.pair = true; }
+  }
   return best;
 }
 
@@ -1053,6 +1121,16 @@ static bool lean_enabled() {
   return v == 1;
 }
 
+// VL2_GEMM_WIDE=0 keeps the cost model away from the wide (two-accumulator) tile (A/B measurements)
+static bool wide_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VL2_GEMM_WIDE");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1070,11 +1148,12 @@ extern "C" int vl2_gemm_plan(int M, int N, int K, int with_splitk_ws, int32_t* o
   using namespace vl2;
   VL2_REQUIRE(M > 0 && N > 0 && K > 0 && out6 != nullptr, VL2_E_BADSHAPE, "vl2_gemm_plan: bad arguments");
   const int sms = sm_count();
-  const TileChoice t = choose_tile(M, N, K, sms, pair_enabled(), splitk_enabled() && with_splitk_ws != 0);
+  // (planned for a launch the lean epilogue can serve: bias / activation / residual / statistics, bf16 output)
+  const TileChoice t = choose_tile(M, N, K, sms, pair_enabled(), splitk_enabled() && with_splitk_ws != 0, wide_enabled());
   const int tile_m = t.pair ? 2 * BM : BM;
-  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + t.bn - 1) / t.bn);
+  const int tiles = ((M + tile_m - 1) / tile_m) * ((N + t.bn + t.bn2 - 1) / (t.bn + t.bn2));
   const int slots = t.pair ? sms / 2 : sms;
-  out6[0] = t.bn;
+  out6[0] = t.bn + t.bn2;
   out6[1] = t.pair ? 1 : 0;
   out6[2] = tiles;
   out6[3] = slots;
@@ -1150,11 +1229,19 @@ extern "C" int vl2_gemm_bf16(const vl2_gemm_args* a, void* stream) {
                 VL2_E_UNSUPPORTED, "vl2_gemm_bf16: the conv front end supports bias + activation epilogues, bf16 output");
     m_plan = To * kConvLine * kConvLine;
   }
-  TileChoice t = choose_tile(m_plan, a->N, a->K, sm_count(), pair_enabled(),
-                             splitk_enabled() && a->splitk_ws != nullptr && a->conv_C == 0);
+  const bool split_ok = splitk_enabled() && a->splitk_ws != nullptr && a->conv_C == 0;
+  const bool wide_ok = wide_enabled() && lean_eligible(a) && a->act != VL2_ACT_SWIGLU && !split_ok && a->reserved3 == 0;
+  TileChoice t = choose_tile(m_plan, a->N, a->K, sm_count(), pair_enabled(), split_ok, wide_ok);
   // test hook: reserved = BN forces a single-CTA tile width, 1000 + BN forces the cta_group::2 pair kernel
-  if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) { t.bn = a->reserved; t.pair = false; }
-  if (a->reserved >= 1128 && a->reserved <= 1256 && (a->reserved - 1000) % 32 == 0) { t.bn = a->reserved - 1000; t.pair = true; }
+  // (2416 forces the wide 224 + 192 pair tile)
+  if (a->reserved >= 64 && a->reserved <= 256 && a->reserved % 32 == 0) { t.bn = a->reserved; t.pair = false; t.bn2 = 0; }
+  if (a->reserved >= 1128 && a->reserved <= 1256 && (a->reserved - 1000) % 32 == 0) { t.bn = a->reserved - 1000; t.pair = true; t.bn2 = 0; }
+  if (a->reserved == 2000 + kWideBN + kWideBN2) {
+    VL2_REQUIRE(lean_eligible(a) && a->act != VL2_ACT_SWIGLU && pair_enabled(), VL2_E_UNSUPPORTED,
+                "vl2_gemm_bf16: the wide tile serves lean, non-SwiGLU launches only");
+    t.bn = kWideBN; t.bn2 = kWideBN2; t.pair = true;
+  }
+  if (t.bn2 > 0) return launch_gemm<kWideBN, true, kWideBN2>(a, st);
   if (t.pair) {
     switch (t.bn) {
       case 256: return launch_gemm<256, true>(a, st);
