@@ -13,7 +13,7 @@ namespace vl2 {
 
 
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NV >= 16 ? 2 : 1))
 layernorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                       const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ residual,
                       __nv_bfloat16* __restrict__ y, int64_t rows, int C, float eps, int act) {
@@ -614,6 +614,7 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int32
 // permuted consistently for A and B so that one 16-byte load supplies two k16 steps (lane quad q holds physical
 // k = 32*kb + 8q .. 8q+7).  HBM-bound on W; this is the SE excitation MLP and every linear layer of a decode step.
 static constexpr int kSkinnyNT8 = 2;  // n8 tiles per CTA
+static constexpr int kSkinnyBatch = 4;  // k-blocks whose loads are in flight together (per warp)
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
@@ -622,15 +623,37 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// raw 16 (fp32 A: 32) bytes of A row `row`, elements k .. k+7; the caller guarantees a valid address (indices are clamped,
+// results of clamped loads are discarded) so that the loads of several k-blocks can be in flight together
+// (volatile: ptxas otherwise sinks each load next to the mma that consumes it, i.e. one DRAM round trip per k-block; volatile
+// asm statements keep their source order, and the mma wrapper is volatile too, so a batch's loads all precede its mmas)
+__device__ __forceinline__ uint4 ldg_nc_v4_ordered(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 template <bool A_F32>
-__device__ __forceinline__ uint4 skinny_load_a(const void* A, int row, int M, int64_t K, int k) {
-  if (row >= M) return make_uint4(0, 0, 0, 0);
+struct SkinnyA { uint4 lo, hi; };
+template <bool A_F32>
+__device__ __forceinline__ SkinnyA<A_F32> skinny_load_a(const void* A, int row, int64_t K, int k) {
+  SkinnyA<A_F32> r;
   if (A_F32) {
-    const float* ar = reinterpret_cast<const float*>(A) + (int64_t)row * K + k;
-    const float4 x = *reinterpret_cast<const float4*>(ar), y = *reinterpret_cast<const float4*>(ar + 4);
-    return make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+    const uint4* ar = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(A) + (int64_t)row * K + k);
+    r.lo = ldg_nc_v4_ordered(ar);
+    r.hi = ldg_nc_v4_ordered(ar + 1);
+  } else {
+    r.lo = ldg_nc_v4_ordered(reinterpret_cast<const __nv_bfloat16*>(A) + (int64_t)row * K + k);
+    r.hi = make_uint4(0, 0, 0, 0);
   }
-  return *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(A) + (int64_t)row * K + k);
+  return r;
+}
+template <bool A_F32>
+__device__ __forceinline__ uint4 skinny_pack_a(const SkinnyA<A_F32>& r, bool keep) {
+  if (!keep) return make_uint4(0, 0, 0, 0);
+  if (A_F32)
+    return make_uint4(pack_bf16(__uint_as_float(r.lo.x), __uint_as_float(r.lo.y)), pack_bf16(__uint_as_float(r.lo.z), __uint_as_float(r.lo.w)),
+                      pack_bf16(__uint_as_float(r.hi.x), __uint_as_float(r.hi.y)), pack_bf16(__uint_as_float(r.hi.z), __uint_as_float(r.hi.w)));
+  return r.lo;
 }
 
 template <bool A_F32>
@@ -651,19 +674,52 @@ gemm_skinny_kernel(const void* __restrict__ Av, const __nv_bfloat16* __restrict_
     for (int t = 0; t < kSkinnyNT8; ++t)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
-#pragma unroll 4
-    for (int kb = warp; kb < nkb; kb += 8) {
-      const int k = kb * 32 + q * 8;
-      const bool k_ok = k < K;
-      const uint4 a_lo = k_ok ? skinny_load_a<A_F32>(Av, m0 + g, M, K, k) : make_uint4(0, 0, 0, 0);
-      const uint4 a_hi = k_ok ? skinny_load_a<A_F32>(Av, m0 + g + 8, M, K, k) : make_uint4(0, 0, 0, 0);
+    // kSkinnyBatch k-blocks per trip: ALL their loads (branch-free: out-of-range indices are clamped to a valid address and
+    // the values dropped) are issued before the first mma, so a warp keeps kSkinnyBatch x 1.5 KB in flight instead of one
+    // dependent DRAM round trip per k-block (38 -> us per 8 MB weight matrix at M = 16; profiles/r02_skinny_gemm.txt)
+    const int row_lo = min(m0 + g, M - 1), row_hi = min(m0 + g + 8, M - 1);
+    const bool lo_ok = m0 + g < M, hi_ok = m0 + g + 8 < M;
+    const uint32_t zero = (act == 0x7fffffff) ? 0xffffffffu : 0u;   // no such activation: 0, but only at run time
+    for (int kb0 = warp; kb0 < nkb; kb0 += 8 * kSkinnyBatch) {
+      SkinnyA<A_F32> ra_lo[kSkinnyBatch], ra_hi[kSkinnyBatch];
+      uint4 rw[kSkinnyBatch][kSkinnyNT8];
+      bool okk[kSkinnyBatch];
 #pragma unroll
-      for (int t = 0; t < kSkinnyNT8; ++t) {
-        const int n = n_base + t * 8 + g;
-        uint4 bw = make_uint4(0, 0, 0, 0);
-        if (k_ok && n < N) bw = __ldg(reinterpret_cast<const uint4*>(Wt + (int64_t)n * K + k));
-        mma_bf16_16816(acc[t], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bw.x, bw.y);
-        mma_bf16_16816(acc[t], a_lo.z, a_hi.z, a_lo.w, a_hi.w, bw.z, bw.w);
+      for (int u = 0; u < kSkinnyBatch; ++u) {
+        const int k = (kb0 + 8 * u) * 32 + q * 8;
+        okk[u] = k < K;
+        const int kc = okk[u] ? k : 0;
+        ra_lo[u] = skinny_load_a<A_F32>(Av, row_lo, K, kc);
+        ra_hi[u] = skinny_load_a<A_F32>(Av, row_hi, K, kc);
+#pragma unroll
+        for (int t = 0; t < kSkinnyNT8; ++t) {
+          const int n = min(n_base + t * 8 + g, N - 1);
+          rw[u][t] = ldg_nc_v4_ordered(Wt + (int64_t)n * K + kc);
+        }
+      }
+      // ptxas sinks each load next to the mma that consumes it (one DRAM round trip per k-block, whatever the source order);
+      // making the FIRST mma depend on every load of the batch keeps them all in flight together.  `zero` is 0 at run time
+      // but not at compile time.
+      uint32_t dep = 0;
+#pragma unroll
+      for (int u = 0; u < kSkinnyBatch; ++u) {
+        dep ^= ra_lo[u].lo.x ^ ra_hi[u].lo.x ^ (A_F32 ? (ra_lo[u].hi.x ^ ra_hi[u].hi.x) : 0u);
+#pragma unroll
+        for (int t = 0; t < kSkinnyNT8; ++t) dep ^= rw[u][t].x;
+      }
+      dep &= zero;
+#pragma unroll
+      for (int u = 0; u < kSkinnyBatch; ++u) {
+        uint4 a_lo = skinny_pack_a<A_F32>(ra_lo[u], okk[u] && lo_ok);
+        if (u == 0) a_lo.x ^= dep;
+        const uint4 a_hi = skinny_pack_a<A_F32>(ra_hi[u], okk[u] && hi_ok);
+#pragma unroll
+        for (int t = 0; t < kSkinnyNT8; ++t) {
+          // (columns n >= N read row N-1: they are never stored; a k block past K has zero A)
+          const uint4 bw = rw[u][t];
+          mma_bf16_16816(acc[t], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bw.x, bw.y);
+          mma_bf16_16816(acc[t], a_lo.z, a_hi.z, a_lo.w, a_hi.w, bw.z, bw.w);
+        }
       }
     }
     __syncthreads();  // red[] is reused across m0 passes
@@ -738,6 +794,9 @@ extern "C" int vl2_layernorm(const void* x, const void* gamma, const void* beta,
   else if (nv <= 2) VL2_LN_WARP(2);
   else if (nv <= 4) VL2_LN_WARP(4);
   else if (nv <= 6) VL2_LN_WARP(6);     // C <= 1536: SigLIP-so400m rows (1152) stay in registers
+  else if (nv <= 16) VL2_LN_WARP(16);   // C <= 4096 (the connector's RegStage rows): 64 registers of packed row per lane, ONE
+                                        // pass over global memory with all 16 loads in flight (the two-pass stream kernel took
+                                        // 55-64 us on 9216 x 4096 and 23-26 us on 1521 x 4096: latency, not bandwidth)
   else
     launch_kernel(layernorm_stream_kernel, dim3(wgrid), dim3(256), 0, (cudaStream_t)stream, 1, (const bf16*)x, (const bf16*)gamma, (const bf16*)beta,
                                                                    (const bf16*)residual, (bf16*)y, rows, C, eps, act);
