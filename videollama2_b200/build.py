@@ -91,11 +91,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed on {src}")
     for name, out, obj_dir, defs, stamp in todo:
         objs = [os.path.join(obj_dir, os.path.basename(s)[:-3] + ".o") for s in srcs]
-        link = [nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        tmp = out + ".tmp"   # link next to the target, then rename: a reader (or a gpurun snapshot) never sees a partial library
+        link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(link, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"link of {os.path.basename(out)} failed")
+        os.replace(tmp, out)
         with open(stamp, "w") as fh:
             fh.write(dig)
     return OUT

@@ -167,7 +167,13 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 // ---------------------------------------------------------------------------------------------------------------------
 enum : uint32_t { kFBias = 1, kFRes = 2, kFSwiglu = 4, kFScale = 8, kFSumsq = 16, kFRowsum = 32, kFRope = 64, kFTrace = 128 };
 
-template <int BN, bool PAIR, int BN2>
+// PLAIN = true: the instantiation for launches without activation, SwiGLU and RoPE (tower qkv / out_proj / fc2, decoder
+// o_proj / down_proj, most connector convolutions): those bodies are not compiled in.  Not a micro-optimisation of the
+// epilogue alone - with the bodies present the 256-wide pair kernel is 11.3 k SASS instructions, the epilogue warps stream
+// through them while the single MMA-issuing thread and the TMA producer run their short loops, and the k-loop of the K = 1024
+// GEMMs ran 4-8 % slower (instruction-cache misses in the issuing thread; no effect on the wide tile, whose epilogue does not
+// overlap its mainloop): profiles/r02_gemm_epilogue_trace.txt, last part.
+template <int BN, bool PAIR, int BN2, bool PLAIN>
 __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const CUtensorMap* tmap_r, const GemmParams& p,
                                               uint8_t* smem_stage, float* sbias, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint64_t* res_bars, uint32_t tmem_base, uint32_t rank, int tile0,
@@ -176,6 +182,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
   constexpr int kTileM = PAIR ? 2 * BM : BM;
   constexpr int kTileN = Cfg::kTileN;
   constexpr uint32_t kUnitBytes = 32 * 64;
+  constexpr uint32_t kExpFeat = PLAIN ? ~(kFSwiglu | kFRope) : ~0u;   // features compiled into this instantiation
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ew = warp & 3, grp = (warp - 4) >> 2, etid = threadIdx.x - 128;
   const int row_in_tile = ew * 32 + lane;
@@ -185,11 +192,11 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
                   (p.sumsq_out != nullptr ? kFSumsq : 0u) | (p.rowsum_out != nullptr ? kFRowsum : 0u) |
                   (p.rope_tab != nullptr ? kFRope : 0u) | ((p.trace && blockIdx.x == 0 && etid == 0) ? kFTrace : 0u);
   asm volatile("" : "+r"(feat));   // keep the flags in a register (do not re-derive them from constant memory)
-  int act = p.act;
-  asm volatile("" : "+r"(act));
+  int act = PLAIN ? (int)VL2_ACT_NONE : p.act;
+  if (!PLAIN) asm volatile("" : "+r"(act));
   // accumulator columns per output unit: 32, or 64 for SwiGLU ((gate, up) pairs -> 32 outputs).  The two warps of a TMEM
   // lane quarter take alternate units.
-  const int ustep = (feat & kFSwiglu) ? 64 : 32;
+  const int ustep = (kExpFeat & feat & kFSwiglu) ? 64 : 32;
   uint8_t* stg = smem_stage + (warp - 4) * 4096;                 // two [32 x 64 B] blocks
   const uint32_t my_row = smem_u32(stg) + lane * 64;
   const uint32_t swz = (uint32_t)(lane >> 1) & 3u;               // 64-byte swizzle key of this thread's row
@@ -256,7 +263,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
       if (col0 >= p.N) break;                       // warp-uniform
       const int ucols = min(min(ustep, kTileN - c0), p.N - col0);   // its valid accumulator columns (multiple of 8)
       const bool next_unit_ok = c0 + 2 * ustep < kTileN && col0 + 2 * ustep < p.N;
-#pragma unroll
+#pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {              // 32 accumulator columns at a time (two passes only for SwiGLU)
         if (hf * 32 >= ucols) break;                // warp-uniform
         const int cc = c0 + hf * 32;                // tile column of these 32 accumulator columns
@@ -281,9 +288,12 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
             x[g * 4 + 0] += bq.x; x[g * 4 + 1] += bq.y; x[g * 4 + 2] += bq.z; x[g * 4 + 3] += bq.w;
           }
         }
-        if (!(feat & kFSwiglu)) {
-          // one branch per activation (warp-uniform), each with a fully unrolled body
-          if (act == VL2_ACT_QUICK_GELU) {
+        if (!(kExpFeat & feat & kFSwiglu)) {
+          // one branch per activation (warp-uniform), each with a fully unrolled body; a launch without activation takes ONE
+          // jump over all of them (every skipped 200-instruction body is an instruction-cache miss at the landing site:
+          // compiling the bodies out made the unit 300-450 cycles shorter, profiles/r02_gemm_epilogue_trace.txt)
+          if (act == VL2_ACT_NONE) {
+          } else if (act == VL2_ACT_QUICK_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = fast_sigmoid_mul(x[j], 1.702f * 1.4426950408889634f);
           } else if (act == VL2_ACT_SILU) {
@@ -296,7 +306,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = gelu_tanh(x[j]);
           }
-          if ((feat & kFRope) && col0 < p.rope_cols && row_ok) {
+          if ((kExpFeat & feat & kFRope) && col0 < p.rope_cols && row_ok) {
             // 32 accumulator columns = 16 rotation pairs of one head, frequencies i0 .. i0 + 15, angle of this row's position
             const int i0 = (col0 % p.rope_D) >> 1;
             const uint4* tr = reinterpret_cast<const uint4*>(p.rope_tab + (int64_t)(p.rope_pos0 + row) * (p.rope_D >> 1) + i0);
@@ -343,7 +353,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
           else __syncwarp();
         }
         if (ptr_) g_gemm_trace[64 + 8 * it + 3] = clock64();
-        if (feat & kFSwiglu) {
+        if (kExpFeat & feat & kFSwiglu) {
           // accumulator columns interleave (gate, up): 32 columns -> 16 outputs = chunks 2*hf, 2*hf+1 of the unit
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -391,7 +401,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
           fence_proxy_async_smem();   // this thread's smem writes -> visible to the TMA unit
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(tmap_c, stg + (uc & 1) * kUnitBytes, (feat & kFSwiglu) ? (col0 >> 1) : col0, rbase);
+            tma_store_2d(tmap_c, stg + (uc & 1) * kUnitBytes, (kExpFeat & feat & kFSwiglu) ? (col0 >> 1) : col0, rbase);
             bulk_commit_group();
           }
           ++uc;
@@ -408,7 +418,7 @@ __device__ __forceinline__ void epilogue_lean(const CUtensorMap* tmap_c, const C
   if (lane == 0) bulk_wait_read_all();   // the staging blocks must outlive the last stores' reads
 }
 
-template <int BN, bool PAIR, bool LEAN, int BN2 = 0>
+template <int BN, bool PAIR, bool LEAN, int BN2 = 0, bool PLAIN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_b2, const __grid_constant__ CUtensorMap tmap_c,
@@ -565,8 +575,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp >= 4 && LEAN) {
-    epilogue_lean<BN, PAIR, BN2>(&tmap_c, &tmap_r, p, smem_stage, sbias, tmem_full, tmem_empty, res_bars, tmem_base, rank,
-                                 tile0, tile_stride);
+    epilogue_lean<BN, PAIR, BN2, PLAIN>(&tmap_c, &tmap_r, p, smem_stage, sbias, tmem_full, tmem_empty, res_bars, tmem_base, rank,
+                                        tile0, tile_stride);
   } else if (warp >= 4) {
     // ===================== general epilogue (8 warps) =====================
     // warp w: TMEM lane quarter (w & 3); the two warps of a quarter take alternate 64-column spans of the tile.
@@ -1011,20 +1021,26 @@ static int launch_gemm(const vl2_gemm_args* a, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
+  const bool plain = a->act == VL2_ACT_NONE && a->rope_tab == nullptr;   // epilogue without activation / SwiGLU / RoPE bodies
+  const dim3 grid(PAIR ? 2 * units : units), block(kGemmThreads);
+  const int cl = PAIR ? 2 : 1;
+#define VL2_LAUNCH_GEMM(...)                                                                                        \
+  do {                                                                                                              \
+    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<__VA_ARGS__>), Cfg::kSmemBytes);                                      \
+    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<__VA_ARGS__>, grid, block, Cfg::kSmemBytes, stream, cl, ta, tb, tb2, \
+                                 tc, tr, p));                                                                       \
+  } while (0)
   if constexpr (BN2 > 0) {
     VL2_REQUIRE(lean && !swiglu, VL2_E_UNSUPPORTED, "vl2_gemm_bf16: the wide tile serves lean, non-SwiGLU launches only");
-    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, true, BN2>), Cfg::kSmemBytes);
-    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, true, BN2>, dim3(2 * units), dim3(kGemmThreads),
-                                 Cfg::kSmemBytes, stream, 2, ta, tb, tb2, tc, tr, p));
+    if (plain) VL2_LAUNCH_GEMM(BN, PAIR, true, BN2, true);
+    else VL2_LAUNCH_GEMM(BN, PAIR, true, BN2, false);
   } else if (lean) {
-    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, true>), Cfg::kSmemBytes);
-    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, true>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
-                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tb2, tc, tr, p));
+    if (plain) VL2_LAUNCH_GEMM(BN, PAIR, true, 0, true);
+    else VL2_LAUNCH_GEMM(BN, PAIR, true, 0, false);
   } else {
-    VL2_SMEM_OPT_IN((gemm_bf16_tcgen05_kernel<BN, PAIR, false>), Cfg::kSmemBytes);
-    VL2_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN, PAIR, false>, dim3(PAIR ? 2 * units : units), dim3(kGemmThreads),
-                                 Cfg::kSmemBytes, stream, PAIR ? 2 : 1, ta, tb, tb2, tc, tr, p));
+    VL2_LAUNCH_GEMM(BN, PAIR, false, 0, false);
   }
+#undef VL2_LAUNCH_GEMM
   VL2_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
   return VL2_OK;
 }
