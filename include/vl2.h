@@ -194,8 +194,13 @@ int vl2_attention(const vl2_attn_args* args, void* stream);
 /* Debug aid: with args->reserved == 777 one softmax thread of CTA (0,0,0) accumulates the cycles it spends in each
  * phase of the key-tile loop; this call synchronises the device and copies the 16 counters to host memory
  * ([0] wait S, [1] TMEM load, [2] mask+max+exchange, [3] wait PV / rescale, [4] exp2+pack+st.shared, [5] fence+arrive,
- *  [6] number of key tiles). */
+ *  [6] item epilogue, [7] key tiles traced, [8] work items traced, [9] cycles of the CTA's whole item loop);
+ * reserved == 778 traces every work item of the persistent CTA 0 instead of its first (cold) one. */
 int vl2_debug_attn_trace(long long* host_out16);
+/* Debug aid: with args->reserved == 779 the softmax thread, the MMA-issuing thread and the two TMA producer lanes of the
+ * persistent CTA 0 stamp clock64() at every hand-over of its second work item (slot map: csrc/attn_tcgen05.cu,
+ * g_attn_tl); this call synchronises the device and copies the 320 stamps to host memory (tools/attn_trace.py). */
+int vl2_debug_attn_timeline(long long* host_out320);
 
 /* Hint: pull [ptr, ptr + bytes) into L2 (cp.async.bulk.prefetch.L2 in 16 KB pieces; returns immediately).  The decode graph
  * forks this next to the latency-bound attention phase so the o_proj / gate-up GEMVs start from L2-resident weights. */

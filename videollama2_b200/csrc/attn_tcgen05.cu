@@ -47,6 +47,14 @@ struct AttnCfg {
 // Debug cycle trace (vl2_attn_args.reserved == 777): block (0,0,0), softmax thread 0 accumulates the cycles it spends
 // in each phase of the key-tile loop; read back with vl2_debug_attn_trace().
 __device__ long long g_attn_trace[16];
+// Timeline trace (vl2_attn_args.reserved == 779, persistent kernel): clock64 stamps of CTA 0's SECOND work item, per key
+// tile j: softmax thread 0 at [8j + 0..6] (tile start, S arrived, S in registers, maxima exchanged, P buffer / O free,
+// P stored, p_full arrive) and [120..123] (item epilogue: start, l exchanged, last P V complete, O stored);
+// MMA thread at [128 + 8j + 0..5] (before Q K^T(j+1), its K arrived, issued, P(j) arrived, V(j) arrived, P V(j) issued),
+// [250..251] (Q arrived, Q K^T(0) issued); K loader at [256 + j] and V loader at [288 + j] (stage free, load issued).
+__device__ long long g_attn_tl[320];
+#define VL2_TL(cond, slot) do { if (cond) g_attn_tl[slot] = clock64(); } while (0)
+static constexpr int kTlItem = 1;
 
 struct AttnParams {
   int trace;
@@ -149,22 +157,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
+    // ===================== MMA issuer: one ELECTED lane (the compiler then knows the branch is single-threaded and emits
+    // back-to-back UTCHMMAs; `lane == 0` made it wrap every MMA in an elect loop), descriptors as (lo, hi) words with
+    // the low words of every ring stage computed once =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
+    constexpr uint32_t hi_kmaj = umma_desc_sw128_hi(1024);
+    const uint32_t q_lo = umma_desc_sw128_lo(smem_u32(sQ), 16);
+    const uint32_t k_lo0 = umma_desc_sw128_lo(smem_u32(sK), 16);
+    const uint32_t p_lo0 = umma_desc_sw128_lo(smem_u32(sP), 16);
+    const uint32_t v_lo0 = umma_desc_sw128_lo(smem_u32(sV), Cfg::kAtomBytes);   // MN-major: LBO = next 64-wide d atom
+    if (leader) {
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
+        const uint32_t k_lo = k_lo0 + st * (Cfg::kTileBytes >> 4);
         const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32;
-          umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + off, 16, 1024), umma_desc_sw128(k_addr + off, 16, 1024),
-                       idesc_qk, kk != 0);
+          const uint32_t off = ((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4;
+          umma_bf16_ss_lohi(d_tmem, q_lo + off, hi_kmaj, k_lo + off, hi_kmaj, idesc_qk, kk != 0);
         }
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
@@ -177,14 +191,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(&p_full[st], (j >> 1) & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
-        const uint32_t p_addr = smem_u32(sP + st * Cfg::kPBytes);
+        const uint32_t v_lo = v_lo0 + st * (Cfg::kTileBytes >> 4);
+        const uint32_t p_lo = p_lo0 + st * (Cfg::kPBytes >> 4);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
-          // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
-          const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
-          umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
+          // A = P: K-major atoms of 64 keys; B = V, MN-major: 16 keys = 2 groups of 8 rows (1024 B each)
+          umma_bf16_ss_lohi(tmem_base + Cfg::kColO, p_lo + (((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4), hi_kmaj,
+                            v_lo + ((kk * 2048) >> 4), hi_kmaj, idesc_pv, (j | kk) != 0);
         }
         umma_commit(&o_full[st]);
         umma_commit(&v_empty[st]);
@@ -298,7 +311,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     if (tr) {
       for (int i = 0; i < 6; ++i) g_attn_trace[i] = acc_t[i];
-      g_attn_trace[6] = n_kv;
+      g_attn_trace[6] = 0;
+      g_attn_trace[7] = n_kv;
+      g_attn_trace[8] = 1;
+      g_attn_trace[9] = 0;
     }
 #undef VL2_TR
     // combine the two half-row sums, then each thread normalises and stores its half of the output columns
@@ -427,6 +443,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     if (lane == 0) {
       int gk = 0;   // K tiles loaded so far (ring stage / phase)
       for (int it = 0; item_of(it, w); ++it) {
+        const bool tl = p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
         mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
@@ -435,6 +452,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         for (int j = 0; j < w.n_kv; ++j, ++gk) {
           const int st = gk & 1;
           mbar_wait(&k_empty[st], ((gk >> 1) & 1) ^ 1);
+          VL2_TL(tl, 256 + j);
           mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
 #pragma unroll
           for (int a = 0; a < Cfg::kAtoms; ++a)
@@ -444,9 +462,11 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     } else if (lane == 1) {
       int gv = 0;
       for (int it = 0; item_of(it, w); ++it) {
+        const bool tl = p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         for (int j = 0; j < w.n_kv; ++j, ++gv) {
           const int st = gv & 1;
           mbar_wait(&v_empty[st], ((gv >> 1) & 1) ^ 1);
+          VL2_TL(tl, 288 + j);
           mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
 #pragma unroll
           for (int a = 0; a < Cfg::kAtoms; ++a)
@@ -455,23 +475,30 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
+    // ===================== MMA issuer (one elected lane, (lo, hi) descriptor words: see attn_fwd_kernel) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
+    constexpr uint32_t hi_kmaj = umma_desc_sw128_hi(1024);
+    const uint32_t q_lo = umma_desc_sw128_lo(smem_u32(sQ), 16);
+    const uint32_t k_lo0 = umma_desc_sw128_lo(smem_u32(sK), 16);
+    const uint32_t p_lo0 = umma_desc_sw128_lo(smem_u32(sP), 16);
+    const uint32_t v_lo0 = umma_desc_sw128_lo(smem_u32(sV), Cfg::kAtomBytes);   // MN-major: LBO = next 64-wide d atom
+    if (leader) {
+      bool tl = false;
+      int tl_slot = 0;
       int gq = 0, gp = 0;   // S tiles issued / P V tiles issued so far (ring stages and phases run across items)
       auto issue_qk = [&]() {
         const int st = gq & 1;
         mbar_wait(&k_full[st], (gq >> 1) & 1);
+        VL2_TL(tl, tl_slot + 1);
         tc_fence_after_sync();
-        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
+        const uint32_t k_lo = k_lo0 + st * (Cfg::kTileBytes >> 4);
         const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32;
-          umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + off, 16, 1024), umma_desc_sw128(k_addr + off, 16, 1024),
-                       idesc_qk, kk != 0);
+          const uint32_t off = ((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4;
+          umma_bf16_ss_lohi(d_tmem, q_lo + off, hi_kmaj, k_lo + off, hi_kmaj, idesc_qk, kk != 0);
         }
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
@@ -479,30 +506,39 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       };
       Item w;
       for (int it = 0; item_of(it, w); ++it) {
+        tl = p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         mbar_wait(q_full, it & 1);
+        VL2_TL(tl, 250);
+        tl_slot = 240;
         issue_qk();
+        VL2_TL(tl, 251);
         if (w.n_kv == 1) umma_commit(q_empty);
         for (int j = 0; j < w.n_kv; ++j, ++gp) {
           const int st = gp & 1;
+          tl_slot = 128 + 8 * j;
+          VL2_TL(tl, tl_slot + 0);
           if (j + 1 < w.n_kv) {
             issue_qk();
             if (j + 2 == w.n_kv) umma_commit(q_empty);   // last Q K^T of the item issued: Q may be overwritten once they ran
           }
+          VL2_TL(tl, tl_slot + 2);
           mbar_wait(&p_full[st], (gp >> 1) & 1);
+          VL2_TL(tl, tl_slot + 3);
           mbar_wait(&v_full[st], (gp >> 1) & 1);
           if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);   // the previous item's O has left TMEM
+          VL2_TL(tl, tl_slot + 4);
           tc_fence_after_sync();
-          const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
-          const uint32_t p_addr = smem_u32(sP + st * Cfg::kPBytes);
+          const uint32_t v_lo = v_lo0 + st * (Cfg::kTileBytes >> 4);
+          const uint32_t p_lo = p_lo0 + st * (Cfg::kPBytes >> 4);
 #pragma unroll
           for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
-            // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
-            const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
-            umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
+            // A = P: K-major atoms of 64 keys; B = V, MN-major: 16 keys = 2 groups of 8 rows (1024 B each)
+            umma_bf16_ss_lohi(tmem_base + Cfg::kColO, p_lo + (((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4), hi_kmaj,
+                              v_lo + ((kk * 2048) >> 4), hi_kmaj, idesc_pv, (j | kk) != 0);
           }
           umma_commit(&o_full[st]);
           umma_commit(&v_empty[st]);
+          VL2_TL(tl, tl_slot + 5);
         }
       }
     }
@@ -522,27 +558,32 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
 
     const bool tr0 = p.trace && blockIdx.x == 0 && threadIdx.x == 0;
     long long t0 = 0, acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_tiles = 0, tr_items = 0;
+    const long long tr_begin = tr0 ? clock64() : 0;
 #define VL2_TR(i) do { if (tr) { const long long t1 = clock64(); acc_t[i] += t1 - t0; t0 = t1; } } while (0)
     Item w;
     for (int it = 0; item_of(it, w); ++it) {
-    const bool tr = tr0 && it == 0;
+    const bool tr = tr0 && (p.trace == 2 || (p.trace == 1 && it == 0));   // 1: the CTA's first (cold) item; 2: every item
+    const bool tl = tr0 && p.trace == 3 && it == kTlItem;                  // 3: timeline of one item (g_attn_tl)
+#define VL2_TRJ(i) do { VL2_TR(i); VL2_TL(tl, 8 * j + (i) + 1); } while (0)
     const int n_kv = w.n_kv, q0 = w.q0;
     const int qi = q0 + r;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j, ++gt) {
       if (tr) t0 = clock64();
+      VL2_TL(tl, 8 * j);
       const int st = gt & 1;
       const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
       const int kv0 = j * BKV + hf * 64;
       const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
       mbar_wait(&s_full[st], (gt >> 1) & 1);
       tc_fence_after_sync();
-      VL2_TR(0);   // waiting for S_j
+      VL2_TRJ(0);   // waiting for S_j
       uint32_t sv[2][32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
       tmem_ld_wait();
-      VL2_TR(1);   // TMEM load
+      VL2_TRJ(1);   // TMEM load
       if (need_mask) {  // warp-uniform; predicated selects, no per-element branches
         const int lim = p.causal ? min(p.S - 1, qi) : (p.S - 1);   // last visible key index for this row
 #pragma unroll
@@ -561,7 +602,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       float* sm = smax + st * 256;
       sm[hf * 128 + r] = fmaxf(mx0, mx1);
       asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
-      VL2_TR(2);   // mask + max + exchange barrier
+      VL2_TRJ(2);   // mask + max + exchange barrier
       const float m_tile = fmaxf(sm[r], sm[128 + r]) * p.scale_log2;
       // reference maximum for this tile: keep the old one unless it is too stale
       float m_use = m, alpha = 1.f;
@@ -589,7 +630,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           tmem_st_wait();
         }
       }
-      VL2_TR(3);   // waiting for P V(j-2) / rescale
+      VL2_TRJ(3);   // waiting for P V(j-2) / rescale
       // probabilities -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
@@ -610,17 +651,15 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       }
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
-      VL2_TR(4);   // exp2 + pack + st.shared
+      VL2_TRJ(4);   // exp2 + pack + st.shared
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&p_full[st]);
-      VL2_TR(5);   // proxy fence + arrive
+      VL2_TRJ(5);   // proxy fence + arrive
     }
-    if (tr) {
-      for (int i = 0; i < 6; ++i) g_attn_trace[i] = acc_t[i];
-      g_attn_trace[6] = n_kv;
-    }
+    if (tr) { tr_tiles += n_kv; ++tr_items; t0 = clock64(); }
+    VL2_TL(tl, 120);
     // combine the two half-row sums, then each thread normalises and stores its half of the output columns.  The
     // exchange reuses the max buffer of the item's LAST tile: the barrier below orders it after every read of that
     // tile's maxima, the next item's first tile uses the other buffer, and the buffer is only rewritten two tiles later.
@@ -629,8 +668,10 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     sl[hf * 128 + r] = l;
     asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
     const float inv = 1.f / (sl[r] + sl[128 + r]);
+    VL2_TL(tl, 121);
     mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
     tc_fence_after_sync();
+    VL2_TL(tl, 122);
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)w.b * p.S + qi) * p.ldo + w.head * p.d_true + hf * (D / 2);
 #pragma unroll
     for (int c = 0; c < D / 64; ++c) {
@@ -652,7 +693,16 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     // O has left TMEM (tcgen05.wait::ld above): the MMA warp may start the next item's first P V (accumulate = 0)
     tc_fence_before_sync();
     mbar_arrive(o_free);
+    VL2_TR(6);   // item epilogue: l exchange, wait for the last P V, O out of TMEM, normalise, store
+    VL2_TL(tl, 123);
     }   // items
+    if (tr0) {
+      for (int i = 0; i < 7; ++i) g_attn_trace[i] = acc_t[i];
+      g_attn_trace[7] = tr_tiles;
+      g_attn_trace[8] = tr_items;
+      g_attn_trace[9] = clock64() - tr_begin;   // whole item loop of this CTA (all items, traced or not)
+    }
+#undef VL2_TRJ
 #undef VL2_TR
   }
 
@@ -700,7 +750,7 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   AttnParams p;
-  p.trace = (a->reserved == 777) ? 1 : 0;
+  p.trace = (a->reserved == 777) ? 1 : (a->reserved == 778) ? 2 : (a->reserved == 779) ? 3 : 0;
   p.out = a->out; p.ldo = a->ldo; p.d_true = a->D; p.n_batch = a->B; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   VL2_SMEM_OPT_IN(attn_fwd_kernel<D>, Cfg::kSmemBytes);
@@ -735,6 +785,13 @@ extern "C" int vl2_attention(const vl2_attn_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->D <= 64) return launch_attn<64>(a, st);
   return launch_attn<128>(a, st);
+}
+
+// Debug: copy the timeline stamps of the last vl2_attention launch with reserved == 779 (see g_attn_tl) to host memory.
+extern "C" int vl2_debug_attn_timeline(long long* host_out320) {
+  VL2_CHECK_CUDA(cudaDeviceSynchronize());
+  VL2_CHECK_CUDA(cudaMemcpyFromSymbol(host_out320, vl2::g_attn_tl, 320 * sizeof(long long)));
+  return VL2_OK;
 }
 
 // Debug: copy the cycle trace of the last traced vl2_attention launch (see g_attn_trace) to host memory.

@@ -228,6 +228,30 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// The same descriptor as two 32-bit words.  The start address lives in bits [0,14) of the LOW word, so stepping through a
+// tile is `lo + (byte_offset >> 4)` (no carry out of the field while the address stays inside the 228 KB of shared memory)
+// and the high word is a compile-time constant: an issuing thread that keeps (lo, hi) apart needs ONE uniform add per
+// operand per MMA, where rebuilding the 64-bit descriptor from the address costs a dependent shift / mask / or chain of
+// uniform-datapath instructions (~100 cycles per tcgen05.mma, measured in the attention kernel's timeline trace).
+__host__ __device__ constexpr uint32_t umma_desc_sw128_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_sw128_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+// D[tmem] (+)= A[smem] * B[smem] with the descriptors given as (lo, hi) words; issued by ONE (elected) thread.
+__device__ __forceinline__ void umma_bf16_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16 with BF16 A/B and FP32 accumulate.
 //   [4,6) c_format (1 = f32)  [7,10) a_format (1 = bf16)  [10,13) b_format  [15] a_major  [16] b_major
 //   [17,23) N >> 3   [24,29) M >> 4
