@@ -359,10 +359,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // items are balanced by a closed-form schedule.  Extra barriers: q_empty (the Q tile may be reloaded), o_free (O has been
 // read out of TMEM); every ring stage / phase is driven by a tile counter that runs across the items.
 // ---------------------------------------------------------------------------------------------------------
-template <int D>
+// TRACE: the cycle-trace instantiation (vl2_attn_args.reserved = 777 / 778 / 779); the production one carries no trace
+// registers (the D = 128 softmax loop has none to spare).
+template <int D, bool TRACE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                const AttnParams p) {
   using Cfg = AttnCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) { asm volatile("trap;"); }
@@ -382,6 +385,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 15);
   uint64_t* q_empty = bars + 16;  // MMA -> Q loader: the previous item's Q K^T MMAs have read Q
   uint64_t* o_free = bars + 17;   // softmax -> MMA: the previous item's O has been read out of TMEM
+  uint64_t* stage_free = bars + 18;   // thread 0 -> softmax: the previous item's output store has finished reading its P buffer
   float* smax = reinterpret_cast<float*>(smem + Cfg::kOffMax);
 
   const int warp = threadIdx.x >> 5;
@@ -413,8 +417,10 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
+    mbar_init(stage_free, 1);
     mbar_init(o_free, kSoftmaxThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
@@ -443,7 +449,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     if (lane == 0) {
       int gk = 0;   // K tiles loaded so far (ring stage / phase)
       for (int it = 0; item_of(it, w); ++it) {
-        const bool tl = p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
+        const bool tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
         mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
@@ -462,7 +468,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     } else if (lane == 1) {
       int gv = 0;
       for (int it = 0; item_of(it, w); ++it) {
-        const bool tl = p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
+        const bool tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         for (int j = 0; j < w.n_kv; ++j, ++gv) {
           const int st = gv & 1;
           mbar_wait(&v_empty[st], ((gv >> 1) & 1) ^ 1);
@@ -506,7 +512,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       };
       Item w;
       for (int it = 0; item_of(it, w); ++it) {
-        tl = p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
+        tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         mbar_wait(q_full, it & 1);
         VL2_TL(tl, 250);
         tl_slot = 240;
@@ -549,18 +555,27 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     // the final division by l).  Thread (r, hf) owns columns [64 hf, 64 hf + 64) of row r's scores and columns
     // [hf D/2, (hf+1) D/2) of its output; both threads of a row make identical rescale decisions from the exchanged
     // row maximum, so their partial sums l share one scale and are added once at the end.
+    // The two threads of a row live in warps w and w + 4: their exchanges go through a 64-thread named barrier per warp
+    // pair, so a pair never waits for the other three.  The item's output leaves through shared memory: each thread writes
+    // its normalised row chunk into the (free) P buffer of the item's last tile in the 128-byte-swizzle box layout and one
+    // thread issues a TMA store per 64-column atom (full lines, rows beyond S clipped by the tensor map) - the per-thread
+    // 16-byte row stores it replaces cost 1.3 k (D = 64) to 4.2 k (D = 128) cycles per item in the timeline trace.
     const int hf = warp >> 2;
+    const int pair_bar = 2 + (warp & 3);
+#define VL2_PAIR_SYNC() asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory")
     const int r = (warp & 3) * 32 + lane;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t o_taddr = tmem_base + lane_sel + Cfg::kColO + hf * (D / 2);
     constexpr float kRescaleThreshold = 8.f;
     int gt = 0;   // key tiles processed so far by this CTA: TMEM / smem stage and barrier phases run across items
 
-    const bool tr0 = p.trace && blockIdx.x == 0 && threadIdx.x == 0;
-    long long t0 = 0, acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tr_tiles = 0, tr_items = 0;
-    const long long tr_begin = tr0 ? clock64() : 0;
-#define VL2_TR(i) do { if (tr) { const long long t1 = clock64(); acc_t[i] += t1 - t0; t0 = t1; } } while (0)
+    const bool tr0 = TRACE && p.trace && blockIdx.x == 0 && threadIdx.x == 0;
+    // 32-bit cycle counters (the low clock word; a launch is far shorter than 2^32 cycles): the trace must not cost the
+    // D = 128 instantiation registers it does not have
+    unsigned t0 = 0, acc_t[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned tr_tiles = 0, tr_items = 0;
+    const unsigned tr_begin = tr0 ? (unsigned)clock64() : 0u;
+#define VL2_TR(i) do { if (tr) { const unsigned t1 = (unsigned)clock64(); acc_t[i] += t1 - t0; t0 = t1; } } while (0)
     Item w;
     for (int it = 0; item_of(it, w); ++it) {
     const bool tr = tr0 && (p.trace == 2 || (p.trace == 1 && it == 0));   // 1: the CTA's first (cold) item; 2: every item
@@ -570,14 +585,20 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     const int qi = q0 + r;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j, ++gt) {
-      if (tr) t0 = clock64();
+      if (tr) t0 = (unsigned)clock64();
       VL2_TL(tl, 8 * j);
       const int st = gt & 1;
       const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
       const int kv0 = j * BKV + hf * 64;
       const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
-      mbar_wait(&s_full[st], (gt >> 1) & 1);
+      // S_j has arrived and P V(j-2) is complete (its P buffer, this tile's, is free; both polls in flight together)
+      if (gt > 1) mbar_wait2(&s_full[st], (gt >> 1) & 1, &o_full[st], ((gt >> 1) & 1) ^ 1);
+      else mbar_wait(&s_full[st], (gt >> 1) & 1);
       tc_fence_after_sync();
+      if (it > 0 && threadIdx.x == 0 && j == 0) {   // the previous item's output store has read its staging buffer
+        bulk_wait_read_all();
+        mbar_arrive(stage_free);
+      }
       VL2_TRJ(0);   // waiting for S_j
       uint32_t sv[2][32];
 #pragma unroll
@@ -601,7 +622,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       // exchange the half-row maxima (double-buffered by tile parity: one named barrier per tile)
       float* sm = smax + st * 256;
       sm[hf * 128 + r] = fmaxf(mx0, mx1);
-      asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+      VL2_PAIR_SYNC();
       VL2_TRJ(2);   // mask + max + exchange barrier
       const float m_tile = fmaxf(sm[r], sm[128 + r]) * p.scale_log2;
       // reference maximum for this tile: keep the old one unless it is too stale
@@ -611,9 +632,9 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         m_use = (m_tile == -INFINITY) ? 0.f : m_tile;   // fully masked rows stay finite
         alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
       }
-      // P is double buffered: buffer (j & 1) was last read by P V(j-2); O (TMEM) may only be rescaled once P V(j-1)
-      // is complete
-      if (gt > 1) mbar_wait(&o_full[st], ((gt >> 1) & 1) ^ 1);
+      // P is double buffered: buffer (j & 1) was last read by P V(j-2) (waited for above) or, in the item's second tile,
+      // by the previous item's output store; O (TMEM) may only be rescaled once P V(j-1) is complete
+      if (it > 0 && j == 1) mbar_wait(stage_free, (it - 1) & 1);
       if (j > 0) {
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
@@ -658,41 +679,49 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       mbar_arrive(&p_full[st]);
       VL2_TRJ(5);   // proxy fence + arrive
     }
-    if (tr) { tr_tiles += n_kv; ++tr_items; t0 = clock64(); }
+    if (tr) { tr_tiles += n_kv; ++tr_items; t0 = (unsigned)clock64(); }
     VL2_TL(tl, 120);
     // combine the two half-row sums, then each thread normalises and stores its half of the output columns.  The
     // exchange reuses the max buffer of the item's LAST tile: the barrier below orders it after every read of that
     // tile's maxima, the next item's first tile uses the other buffer, and the buffer is only rewritten two tiles later.
     float* sl = smax + ((gt - 1) & 1) * 256;
-    asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+    VL2_PAIR_SYNC();
     sl[hf * 128 + r] = l;
-    asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxThreads) : "memory");
+    VL2_PAIR_SYNC();
     const float inv = 1.f / (sl[r] + sl[128 + r]);
     VL2_TL(tl, 121);
+    if (it > 0 && n_kv == 1) mbar_wait(stage_free, (it - 1) & 1);   // (one wait per item keeps the phase in step)
     mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
     tc_fence_after_sync();
     VL2_TL(tl, 122);
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)w.b * p.S + qi) * p.ldo + w.head * p.d_true + hf * (D / 2);
+    uint8_t* sO = sP + ((gt - 1) & 1) * Cfg::kPBytes;   // P buffer of the last tile: P V(last) has read it
 #pragma unroll
     for (int c = 0; c < D / 64; ++c) {
       uint32_t ov[32];
       tmem_ld_32x32(o_taddr + c * 32, ov);
       tmem_ld_wait();
-      if (qi < p.S) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (hf * (D / 2) + c * 32 + g * 8 >= p.d_true) break;   // head_dim < D: the zero-padded columns are not stored
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = make_uint4(
-              pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv),
-              pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv),
-              pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv),
-              pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv));
-        }
+      for (int g = 0; g < 4; ++g) {
+        const int col = hf * (D / 2) + c * 32 + g * 8;   // first of 8 output columns (within the head)
+        uint8_t* dst = sO + (col >> 6) * Cfg::kAtomBytes + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(
+            pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv),
+            pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv),
+            pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv),
+            pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv));
       }
     }
     // O has left TMEM (tcgen05.wait::ld above): the MMA warp may start the next item's first P V (accumulate = 0)
     tc_fence_before_sync();
     mbar_arrive(o_free);
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 6, %0;" ::"n"(kSoftmaxThreads) : "memory");   // every row chunk of the item is staged
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int a = 0; a < Cfg::kAtoms; ++a)
+        if (a * 64 < p.d_true) tma_store_4d(&tmap_o, sO + a * Cfg::kAtomBytes, a * 64, w.head, q0, w.b);
+      bulk_commit_group();
+    }
     VL2_TR(6);   // item epilogue: l exchange, wait for the last P V, O out of TMEM, normalise, store
     VL2_TL(tl, 123);
     }   // items
@@ -700,8 +729,10 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       for (int i = 0; i < 7; ++i) g_attn_trace[i] = acc_t[i];
       g_attn_trace[7] = tr_tiles;
       g_attn_trace[8] = tr_items;
-      g_attn_trace[9] = clock64() - tr_begin;   // whole item loop of this CTA (all items, traced or not)
+      g_attn_trace[9] = (unsigned)clock64() - tr_begin;   // whole item loop of this CTA (all items, traced or not)
     }
+    if (threadIdx.x == 0) bulk_wait_read_all();   // the last store still reads this CTA's shared memory
+#undef VL2_PAIR_SYNC
 #undef VL2_TRJ
 #undef VL2_TR
   }
@@ -749,6 +780,13 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tv, a->v, 4, dims, str, box);
     if (rc) return rc;
   }
+  CUtensorMap to;   // output rows through the same 4-D form (persistent kernel: TMA store of the staged tile)
+  {
+    uint64_t dims[4] = {dt, (uint64_t)a->Hq, (uint64_t)a->S, (uint64_t)a->B};
+    uint64_t str[3] = {dt * 2, (uint64_t)a->ldo * 2, (uint64_t)a->ldo * 2 * a->S};
+    int rc = make_tmap_bf16(&to, a->out, 4, dims, str, box);
+    if (rc) return rc;
+  }
   AttnParams p;
   p.trace = (a->reserved == 777) ? 1 : (a->reserved == 778) ? 2 : (a->reserved == 779) ? 3 : 0;
   p.out = a->out; p.ldo = a->ldo; p.d_true = a->D; p.n_batch = a->B; p.S = a->S; p.Hq = a->Hq; p.group = a->Hq / a->Hkv; p.causal = a->causal;
@@ -756,10 +794,15 @@ static int launch_attn(const vl2_attn_args* a, cudaStream_t stream) {
   VL2_SMEM_OPT_IN(attn_fwd_kernel<D>, Cfg::kSmemBytes);
   const int n_qt = (a->S + BQ - 1) / BQ;
   if (attn_persistent_enabled()) {
-    VL2_SMEM_OPT_IN(attn_fwd_persistent_kernel<D>, Cfg::kSmemBytes);
     const int n_items = n_qt * a->Hq * a->B;
     const int ctas = n_items < sm_count() ? n_items : sm_count();
-    VL2_CHECK_CUDA(launch_kernel(attn_fwd_persistent_kernel<D>, dim3(ctas), dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, p));
+    if (p.trace) {
+      VL2_SMEM_OPT_IN((attn_fwd_persistent_kernel<D, true>), Cfg::kSmemBytes);
+      VL2_CHECK_CUDA(launch_kernel(attn_fwd_persistent_kernel<D, true>, dim3(ctas), dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, to, p));
+    } else {
+      VL2_SMEM_OPT_IN((attn_fwd_persistent_kernel<D, false>), Cfg::kSmemBytes);
+      VL2_CHECK_CUDA(launch_kernel(attn_fwd_persistent_kernel<D, false>, dim3(ctas), dim3(kAttnThreads), Cfg::kSmemBytes, stream, 1, tq, tk, tv, to, p));
+    }
     VL2_CHECK_LAUNCH("attn_fwd_persistent_kernel");
     return VL2_OK;
   }

@@ -97,6 +97,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait for two barriers at once: both polls are in flight together, so a wait that is already satisfied costs one barrier
+// round trip instead of two (each poll is a few hundred cycles when eight warps hit the barrier unit at the same time).
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  uint32_t spins = 0;
+  for (;;) {
+    const bool a = mbar_try_wait(bar_a, parity_a);
+    const bool b = mbar_try_wait(bar_b, parity_b);
+    if (a && b) break;
+    if (++spins > VL2_MBAR_SPIN_LIMIT) { asm volatile("trap;"); }
+  }
+}
+
 // wait whose acquire has CLUSTER scope: for barriers other CTAs of the cluster arrive on (release.cluster) after writing
 // this CTA's shared memory through DSMEM
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -139,6 +151,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
