@@ -488,7 +488,6 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     constexpr uint32_t hi_kmaj = umma_desc_sw128_hi(1024);
     const uint32_t q_lo = umma_desc_sw128_lo(smem_u32(sQ), 16);
     const uint32_t k_lo0 = umma_desc_sw128_lo(smem_u32(sK), 16);
-    const uint32_t p_lo0 = umma_desc_sw128_lo(smem_u32(sP), 16);
     const uint32_t v_lo0 = umma_desc_sw128_lo(smem_u32(sV), Cfg::kAtomBytes);   // MN-major: LBO = next 64-wide d atom
     if (leader) {
       bool tl = false;
@@ -510,6 +509,30 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
         ++gq;
       };
+      auto issue_pv = [&](int j, int it) {
+        const int st = gp & 1;
+        mbar_wait2(&p_full[st], (gp >> 1) & 1, &v_full[st], (gp >> 1) & 1);
+        VL2_TL(tl, 128 + 8 * j + 3);
+        if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);   // the previous item's O has left TMEM
+        tc_fence_after_sync();
+        const uint32_t v_lo = v_lo0 + st * (Cfg::kTileBytes >> 4);
+        const uint32_t p_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          // A = P_j in TENSOR MEMORY, in place of S_j: keys [64 h, 64 h + 64) as 32 packed columns at S column 64 h
+          // (each softmax thread overwrote the first half of the S columns it had read); 16 keys = 8 columns.
+          // B = V, MN-major: 16 keys = 2 groups of 8 rows (1024 B each)
+          umma_bf16_ts_lohi(tmem_base + Cfg::kColO, p_tmem + (kk >> 2) * 64 + (kk & 3) * 8, v_lo + ((kk * 2048) >> 4), hi_kmaj,
+                            idesc_pv, (j | kk) != 0);
+        }
+        umma_commit(&o_full[st]);
+        umma_commit(&v_empty[st]);
+        VL2_TL(tl, 128 + 8 * j + 5);
+        ++gp;
+      };
+      // Issue order per tile: Q K^T(j+1) first (its S buffer held P_{j-1}, and P V(j-1) is ahead of it in the pipe), then
+      // P V(j) once P_j has arrived.  (Holding the MMAs back until the tile's exp2 pass begins - so that their operand
+      // fetches do not compete with the softmax warps' shared-memory phase - was measured: no gain, S_{j+1} arrives late.)
       Item w;
       for (int it = 0; item_of(it, w); ++it) {
         tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
@@ -519,8 +542,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         issue_qk();
         VL2_TL(tl, 251);
         if (w.n_kv == 1) umma_commit(q_empty);
-        for (int j = 0; j < w.n_kv; ++j, ++gp) {
-          const int st = gp & 1;
+        for (int j = 0; j < w.n_kv; ++j) {
           tl_slot = 128 + 8 * j;
           VL2_TL(tl, tl_slot + 0);
           if (j + 1 < w.n_kv) {
@@ -528,23 +550,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             if (j + 2 == w.n_kv) umma_commit(q_empty);   // last Q K^T of the item issued: Q may be overwritten once they ran
           }
           VL2_TL(tl, tl_slot + 2);
-          mbar_wait(&p_full[st], (gp >> 1) & 1);
-          VL2_TL(tl, tl_slot + 3);
-          mbar_wait(&v_full[st], (gp >> 1) & 1);
-          if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);   // the previous item's O has left TMEM
-          VL2_TL(tl, tl_slot + 4);
-          tc_fence_after_sync();
-          const uint32_t v_lo = v_lo0 + st * (Cfg::kTileBytes >> 4);
-          const uint32_t p_lo = p_lo0 + st * (Cfg::kPBytes >> 4);
-#pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            // A = P: K-major atoms of 64 keys; B = V, MN-major: 16 keys = 2 groups of 8 rows (1024 B each)
-            umma_bf16_ss_lohi(tmem_base + Cfg::kColO, p_lo + (((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4), hi_kmaj,
-                              v_lo + ((kk * 2048) >> 4), hi_kmaj, idesc_pv, (j | kk) != 0);
-          }
-          umma_commit(&o_full[st]);
-          umma_commit(&v_empty[st]);
-          VL2_TL(tl, tl_slot + 5);
+          issue_pv(j, it);
         }
       }
     }
@@ -591,9 +597,8 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
       const int kv0 = j * BKV + hf * 64;
       const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
-      // S_j has arrived and P V(j-2) is complete (its P buffer, this tile's, is free; both polls in flight together)
-      if (gt > 1) mbar_wait2(&s_full[st], (gt >> 1) & 1, &o_full[st], ((gt >> 1) & 1) ^ 1);
-      else mbar_wait(&s_full[st], (gt >> 1) & 1);
+      // S_j has arrived.  (Its TMEM columns held P_{j-2}: the tensor pipe runs Q K_j^T after P V(j-2), in issue order.)
+      mbar_wait(&s_full[st], (gt >> 1) & 1);
       tc_fence_after_sync();
       if (it > 0 && threadIdx.x == 0 && j == 0) {   // the previous item's output store has read its staging buffer
         bulk_wait_read_all();
@@ -613,15 +618,20 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           for (int i = 0; i < 32; ++i)
             sv[c][i] = (kv0 + c * 32 + i <= lim) ? sv[c][i] : 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      // row maximum of the 64 scores: 8 independent chains of three-input maxima (a single chain of 32 dependent
+      // FMNMX was ~130 cycles of pure latency per tile)
+      float mxc[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t* e = &sv[q >> 2][(q & 3) * 8];
+        mxc[q] = fmax3(fmax3(__uint_as_float(e[0]), __uint_as_float(e[1]), __uint_as_float(e[2])),
+                       fmax3(__uint_as_float(e[3]), __uint_as_float(e[4]), __uint_as_float(e[5])),
+                       fmaxf(__uint_as_float(e[6]), __uint_as_float(e[7])));
       }
+      const float mx_half = fmax3(fmax3(mxc[0], mxc[1], mxc[2]), fmax3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7]));
       // exchange the half-row maxima (double-buffered by tile parity: one named barrier per tile)
       float* sm = smax + st * 256;
-      sm[hf * 128 + r] = fmaxf(mx0, mx1);
+      sm[hf * 128 + r] = mx_half;
       VL2_PAIR_SYNC();
       VL2_TRJ(2);   // mask + max + exchange barrier
       const float m_tile = fmaxf(sm[r], sm[128 + r]) * p.scale_log2;
@@ -632,9 +642,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         m_use = (m_tile == -INFINITY) ? 0.f : m_tile;   // fully masked rows stay finite
         alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_use);
       }
-      // P is double buffered: buffer (j & 1) was last read by P V(j-2) (waited for above) or, in the item's second tile,
-      // by the previous item's output store; O (TMEM) may only be rescaled once P V(j-1) is complete
-      if (it > 0 && j == 1) mbar_wait(stage_free, (it - 1) & 1);
+      // O (TMEM) may only be rescaled once P V(j-1) is complete
       if (j > 0) {
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
@@ -652,7 +660,9 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         }
       }
       VL2_TRJ(3);   // waiting for P V(j-2) / rescale
-      // probabilities -> smem (bf16, K-major SW128 A operand): this thread's 64 columns are exactly atom `hf`
+      // probabilities -> TENSOR MEMORY (16-bit pairs), over the first half of the S columns this thread has just read:
+      // the A operand of P V comes from TMEM, so P costs no shared-memory write here and no shared-memory read in the MMA
+      // (with P in smem the kernel moved 224 KB per D = 128 tile through a 128 B/clk shared memory: 1750 cycles)
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -661,20 +671,15 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         for (int i = 0; i < 32; ++i) pr[i] = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_use));
 #pragma unroll
         for (int i = 0; i < 32; i += 4) { rs0 += pr[i]; rs1 += pr[i + 1]; rs2 += pr[i + 2]; rs3 += pr[i + 3]; }
+        uint32_t pk[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = c * 4 + g;
-          uint8_t* dst = sP + st * Cfg::kPBytes + hf * Cfg::kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) =
-              make_uint4(pack_bf16(pr[g * 8 + 0], pr[g * 8 + 1]), pack_bf16(pr[g * 8 + 2], pr[g * 8 + 3]),
-                         pack_bf16(pr[g * 8 + 4], pr[g * 8 + 5]), pack_bf16(pr[g * 8 + 6], pr[g * 8 + 7]));
-        }
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pr[2 * i], pr[2 * i + 1]);
+        tmem_st_32x32_x16(s_taddr + c * 16, pk);
       }
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
-      VL2_TRJ(4);   // exp2 + pack + st.shared
-      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      VL2_TRJ(4);   // exp2 + pack + tcgen05.st
       tc_fence_before_sync();
       mbar_arrive(&p_full[st]);
       VL2_TRJ(5);   // proxy fence + arrive
@@ -690,11 +695,12 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     VL2_PAIR_SYNC();
     const float inv = 1.f / (sl[r] + sl[128 + r]);
     VL2_TL(tl, 121);
-    if (it > 0 && n_kv == 1) mbar_wait(stage_free, (it - 1) & 1);   // (one wait per item keeps the phase in step)
-    mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
+    // the last P V is complete and the previous item's output store has read the staging tile (polls in flight together)
+    if (it > 0) mbar_wait2(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1, stage_free, (it - 1) & 1);
+    else mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
     tc_fence_after_sync();
     VL2_TL(tl, 122);
-    uint8_t* sO = sP + ((gt - 1) & 1) * Cfg::kPBytes;   // P buffer of the last tile: P V(last) has read it
+    uint8_t* sO = sP;   // output staging tile [128 rows x D], 128-byte-swizzle box layout
 #pragma unroll
     for (int c = 0; c < D / 64; ++c) {
       uint32_t ov[32];

@@ -485,8 +485,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t tmem_base = *tmem_base_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    if (elect_one()) {
+      // ===================== TMA producer (one elected lane: see the MMA issuer) =====================
       int stage = 0;
       uint32_t phase = 0;
       const bool conv = !LEAN && p.conv_C > 0;
@@ -532,10 +532,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      // ===================== MMA issuer (leader CTA only for a pair) =====================
+    // ===================== MMA issuer (leader CTA only for a pair): ONE ELECTED lane - the compiler then knows the branch
+    // is single-threaded and emits the UTCHMMAs back to back; under `lane == 0` it wrapped every MMA in an elect loop with
+    // five register -> uniform-register moves (~20 instructions and ~100 cycles per MMA, more than a 128 x 128 x 16 MMA
+    // takes to execute).  Descriptors as (lo, hi) words: one uniform add per operand per MMA (ptx.cuh). =====================
+    const bool leader = (rank == 0) && elect_one();
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_bf16(kTileM, BN2 > 0 ? BN2 : BN, 0, 0);
+      constexpr uint32_t dhi = umma_desc_sw128_hi(1024);
+      const uint32_t a_lo0 = umma_desc_sw128_lo(smem_u32(smem_a), 16);
+      const uint32_t b_lo0 = umma_desc_sw128_lo(smem_u32(smem_b), 16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -552,18 +559,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kStageBytesA);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kStageBytesB);
+          const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytesA >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (Cfg::kStageBytesB >> 4);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            if (PAIR) umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb != w.kb0) || (k != 0));
-            else umma_bf16_ss(d_tmem, da, db, idesc, (kb != w.kb0) || (k != 0));
-            if (BN2 > 0) {   // the same A k-slice into the second accumulator (TMEM column 256)
-              const uint64_t db2 = umma_desc_sw128(b_addr + Cfg::kStageBytesB1 + k * 32, 16, 1024);
-              umma_bf16_ss_pair(d_tmem + 256, da, db2, idesc2, (kb != w.kb0) || (k != 0));
-            }
+            const uint32_t acc = (kb != w.kb0) || (k != 0);
+            if (PAIR) umma_bf16_ss_pair_lohi(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, acc);
+            else umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, dhi, b_lo + 2 * k, dhi, idesc, acc);
+            if (BN2 > 0)   // the same A k-slice into the second accumulator (TMEM column 256)
+              umma_bf16_ss_pair_lohi(d_tmem + 256, a_lo + 2 * k, dhi, b_lo + (Cfg::kStageBytesB1 >> 4) + 2 * k, dhi, idesc2, acc);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
