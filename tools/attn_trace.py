@@ -25,7 +25,7 @@ for (B, S, Hq, Hkv, D, causal) in [(16, 577, 16, 16, 64, False), (1, 1776, 32, 8
         print(f"D={D} causal={causal} mode={mode} items={items} tiles={n}: "
               + ", ".join(f"{nm}={buf[i] / n:.0f}" for i, nm in enumerate(NAMES)),
               f"| per tile={sum(buf[:6]) / n:.0f} cycles; item epilogue={buf[6] / items:.0f} per item; "
-              f"traced={sum(buf[:7])} of {buf[9]} cycles in the CTA's item loop")
+              f"traced={sum(buf[:7])} of {buf[9]} cycles in the CTA's item loop; repeated (satisfied) S poll={buf[10] / n:.0f}")
     # timeline of CTA 0's second work item (reserved == 779): who waits for whom, in cycles relative to the item's first stamp
     a = AttnArgs(q=q.data_ptr(), k=k.data_ptr(), v=v.data_ptr(), out=out.data_ptr(), ldq=q.stride(0), ldk=k.stride(0),
                  ldv=v.stride(0), ldo=out.stride(0), B=B, S=S, Hq=Hq, Hkv=Hkv, D=D, causal=int(causal),

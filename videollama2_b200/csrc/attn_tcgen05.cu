@@ -15,6 +15,8 @@
 // QK^T of tile j+1 is issued before the softmax of tile j finishes, so tensor-core and MUFU work overlap.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -42,6 +44,7 @@ struct AttnCfg {
   static constexpr int kSmemBytes = (kSmemUsed > 116 * 1024) ? kSmemUsed : 116 * 1024;
   static constexpr int kTmemCols = 512;
   static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
+  static constexpr int kColP0 = 384, kColP1 = 448;      // persistent kernel: P_j as 64 columns of 16-bit pairs (A operand of P V)
 };
 
 // Debug cycle trace (vl2_attn_args.reserved == 777): block (0,0,0), softmax thread 0 accumulates the cycles it spends
@@ -359,6 +362,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // items are balanced by a closed-form schedule.  Extra barriers: q_empty (the Q tile may be reloaded), o_free (O has been
 // read out of TMEM); every ring stage / phase is driven by a tile counter that runs across the items.
 // ---------------------------------------------------------------------------------------------------------
+// O *= alpha for this thread's half of a row's output columns (lazy rescale, rare).  Out of line on purpose: the key-tile
+// loop of the persistent kernel has to stay small and straight (see there).
+template <int D>
+__device__ __noinline__ void attn_rescale_o(uint32_t o_taddr, float alpha) {
+#pragma unroll
+  for (int c = 0; c < D / 64; ++c) {
+    uint32_t ov[32];
+    tmem_ld_32x32(o_taddr + c * 32, ov);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+    tmem_st_32x32(o_taddr + c * 32, ov);
+  }
+  tmem_st_wait();
+}
+
 // TRACE: the cycle-trace instantiation (vl2_attn_args.reserved = 777 / 778 / 779); the production one carries no trace
 // registers (the D = 128 softmax loop has none to spare).
 template <int D, bool TRACE>
@@ -450,14 +469,14 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       int gk = 0;   // K tiles loaded so far (ring stage / phase)
       for (int it = 0; item_of(it, w); ++it) {
         const bool tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
-        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
+        if (it > 0) mbar_wait_parked(q_empty, (it - 1) & 1);
         mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < Cfg::kAtoms; ++a)
           tma_load_4d(sQ + a * Cfg::kAtomBytes, &tmap_q, q_full, a * 64, w.head, w.q0, w.b);
         for (int j = 0; j < w.n_kv; ++j, ++gk) {
           const int st = gk & 1;
-          mbar_wait(&k_empty[st], ((gk >> 1) & 1) ^ 1);
+          mbar_wait_parked(&k_empty[st], ((gk >> 1) & 1) ^ 1);
           VL2_TL(tl, 256 + j);
           mbar_arrive_expect_tx(&k_full[st], Cfg::kTileBytes);
 #pragma unroll
@@ -471,7 +490,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         const bool tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
         for (int j = 0; j < w.n_kv; ++j, ++gv) {
           const int st = gv & 1;
-          mbar_wait(&v_empty[st], ((gv >> 1) & 1) ^ 1);
+          mbar_wait_parked(&v_empty[st], ((gv >> 1) & 1) ^ 1);
           VL2_TL(tl, 288 + j);
           mbar_arrive_expect_tx(&v_full[st], Cfg::kTileBytes);
 #pragma unroll
@@ -495,7 +514,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       int gq = 0, gp = 0;   // S tiles issued / P V tiles issued so far (ring stages and phases run across items)
       auto issue_qk = [&]() {
         const int st = gq & 1;
-        mbar_wait(&k_full[st], (gq >> 1) & 1);
+        mbar_wait_parked(&k_full[st], (gq >> 1) & 1);
         VL2_TL(tl, tl_slot + 1);
         tc_fence_after_sync();
         const uint32_t k_lo = k_lo0 + st * (Cfg::kTileBytes >> 4);
@@ -511,43 +530,45 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       };
       auto issue_pv = [&](int j, int it) {
         const int st = gp & 1;
-        mbar_wait2(&p_full[st], (gp >> 1) & 1, &v_full[st], (gp >> 1) & 1);
         VL2_TL(tl, 128 + 8 * j + 3);
-        if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);   // the previous item's O has left TMEM
+        if (j == 0 && it > 0) mbar_wait_parked(o_free, (it - 1) & 1);   // the previous item's O has left TMEM
         tc_fence_after_sync();
         const uint32_t v_lo = v_lo0 + st * (Cfg::kTileBytes >> 4);
-        const uint32_t p_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
+        const uint32_t p_tmem = tmem_base + (st ? Cfg::kColP1 : Cfg::kColP0);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          // A = P_j in TENSOR MEMORY, in place of S_j: keys [64 h, 64 h + 64) as 32 packed columns at S column 64 h
-          // (each softmax thread overwrote the first half of the S columns it had read); 16 keys = 8 columns.
+          // A = P_j in TENSOR MEMORY: 128 keys as 64 columns of 16-bit pairs, 16 keys = 8 columns.
           // B = V, MN-major: 16 keys = 2 groups of 8 rows (1024 B each)
-          umma_bf16_ts_lohi(tmem_base + Cfg::kColO, p_tmem + (kk >> 2) * 64 + (kk & 3) * 8, v_lo + ((kk * 2048) >> 4), hi_kmaj,
-                            idesc_pv, (j | kk) != 0);
+          umma_bf16_ts_lohi(tmem_base + Cfg::kColO, p_tmem + kk * 8, v_lo + ((kk * 2048) >> 4), hi_kmaj, idesc_pv, (j | kk) != 0);
         }
         umma_commit(&o_full[st]);
         umma_commit(&v_empty[st]);
         VL2_TL(tl, 128 + 8 * j + 5);
         ++gp;
       };
-      // Issue order per tile: Q K^T(j+1) first (its S buffer held P_{j-1}, and P V(j-1) is ahead of it in the pipe), then
-      // P V(j) once P_j has arrived.  (Holding the MMAs back until the tile's exp2 pass begins - so that their operand
-      // fetches do not compete with the softmax warps' shared-memory phase - was measured: no gain, S_{j+1} arrives late.)
+      // Issue order.  P_j has its own TMEM columns, so when it arrives the S buffer it was computed from is free and
+      // Q K^T(j+2) goes into the tensor pipe AHEAD of P V(j): S_{j+2} is ready a full tile before the softmax warps need it
+      // (with Q K^T queued behind P V the chain P_j -> P V(j) -> Q K^T(j+2) -> S_{j+2} took as long as a softmax tile, and
+      // the softmax warps waited for S on every tile).
       Item w;
       for (int it = 0; item_of(it, w); ++it) {
         tl = TRACE && p.trace == 3 && blockIdx.x == 0 && it == kTlItem;
-        mbar_wait(q_full, it & 1);
+        mbar_wait_parked(q_full, it & 1);
         VL2_TL(tl, 250);
         tl_slot = 240;
         issue_qk();
         VL2_TL(tl, 251);
-        if (w.n_kv == 1) umma_commit(q_empty);
+        if (w.n_kv > 1) issue_qk();
+        if (w.n_kv <= 2) umma_commit(q_empty);   // last Q K^T of the item issued: Q may be overwritten once they ran
         for (int j = 0; j < w.n_kv; ++j) {
           tl_slot = 128 + 8 * j;
           VL2_TL(tl, tl_slot + 0);
-          if (j + 1 < w.n_kv) {
+          const int st = gp & 1;
+          mbar_wait_parked(&p_full[st], (gp >> 1) & 1);   // (S_j consumed: its buffer is free)
+          mbar_wait_parked(&v_full[st], (gp >> 1) & 1);
+          if (j + 2 < w.n_kv) {
             issue_qk();
-            if (j + 2 == w.n_kv) umma_commit(q_empty);   // last Q K^T of the item issued: Q may be overwritten once they ran
+            if (j + 3 == w.n_kv) umma_commit(q_empty);
           }
           VL2_TL(tl, tl_slot + 2);
           issue_pv(j, it);
@@ -578,7 +599,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     const bool tr0 = TRACE && p.trace && blockIdx.x == 0 && threadIdx.x == 0;
     // 32-bit cycle counters (the low clock word; a launch is far shorter than 2^32 cycles): the trace must not cost the
     // D = 128 instantiation registers it does not have
-    unsigned t0 = 0, acc_t[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned t0 = 0, acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned tr_tiles = 0, tr_items = 0;
     const unsigned tr_begin = tr0 ? (unsigned)clock64() : 0u;
 #define VL2_TR(i) do { if (tr) { const unsigned t1 = (unsigned)clock64(); acc_t[i] += t1 - t0; t0 = t1; } } while (0)
@@ -590,27 +611,38 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     const int n_kv = w.n_kv, q0 = w.q0;
     const int qi = q0 + r;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; ++j, ++gt) {
+    // One key tile.  MASK is a compile-time flag and the loop below runs the unmasked tiles first: only an item's last
+    // tile can need a mask (sequence end / causal diagonal), and with the 200-instruction masking block and the rescale
+    // block inside ONE loop body every tile paid for jumping over them - the body (~18 KB) is three times the 6 KB L0
+    // instruction cache and the whole kernel as large as the 32 KB L1.5, so each taken branch landed on a line that
+    // had to come from L2 (a fixed ~250 cycles at the top of every tile in the timeline trace).
+    auto tile = [&](const int j, auto mask_tag) {
+      constexpr bool MASK = decltype(mask_tag)::value;
       if (tr) t0 = (unsigned)clock64();
       VL2_TL(tl, 8 * j);
       const int st = gt & 1;
       const uint32_t s_taddr = tmem_base + lane_sel + (st ? Cfg::kColS1 : Cfg::kColS0) + hf * 64;
+      const uint32_t p_taddr = tmem_base + lane_sel + (st ? Cfg::kColP1 : Cfg::kColP0) + hf * 32;
       const int kv0 = j * BKV + hf * 64;
-      const bool need_mask = (j * BKV + BKV > p.S) || (p.causal && (j * BKV + BKV - 1 > q0));
-      // S_j has arrived.  (Its TMEM columns held P_{j-2}: the tensor pipe runs Q K_j^T after P V(j-2), in issue order.)
-      mbar_wait(&s_full[st], (gt >> 1) & 1);
+      // S_j has arrived; P V(j-2) has read this tile's P buffer (both polls in flight together)
+      if (gt > 1) mbar_wait2(&s_full[st], (gt >> 1) & 1, &o_full[st], ((gt >> 1) & 1) ^ 1);
+      else mbar_wait(&s_full[st], (gt >> 1) & 1);
       tc_fence_after_sync();
       if (it > 0 && threadIdx.x == 0 && j == 0) {   // the previous item's output store has read its staging buffer
         bulk_wait_read_all();
         mbar_arrive(stage_free);
       }
       VL2_TRJ(0);   // waiting for S_j
+      if (TRACE && tr0 && p.trace == 2) {   // the same poll again, now certainly satisfied: what a poll costs by itself
+        mbar_wait(&s_full[st], (gt >> 1) & 1);
+        if (tr) { const unsigned t1 = (unsigned)clock64(); acc_t[7] += t1 - t0; t0 = t1; }
+      }
       uint32_t sv[2][32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) tmem_ld_32x32(s_taddr + c * 32, sv[c]);
       tmem_ld_wait();
       VL2_TRJ(1);   // TMEM load
-      if (need_mask) {  // warp-uniform; predicated selects, no per-element branches
+      if constexpr (MASK) {  // predicated selects, no per-element branches
         const int lim = p.causal ? min(p.S - 1, qi) : (p.S - 1);   // last visible key index for this row
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -647,21 +679,12 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(&o_full[(gt - 1) & 1], ((gt - 1) >> 1) & 1);
           tc_fence_after_sync();
-#pragma unroll
-          for (int c = 0; c < D / 64; ++c) {
-            uint32_t ov[32];
-            tmem_ld_32x32(o_taddr + c * 32, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st_32x32(o_taddr + c * 32, ov);
-          }
-          tmem_st_wait();
+          attn_rescale_o<D>(o_taddr, alpha);
         }
       }
       VL2_TRJ(3);   // waiting for P V(j-2) / rescale
-      // probabilities -> TENSOR MEMORY (16-bit pairs), over the first half of the S columns this thread has just read:
-      // the A operand of P V comes from TMEM, so P costs no shared-memory write here and no shared-memory read in the MMA
+      // probabilities -> TENSOR MEMORY (16-bit pairs, this thread's 64 keys = 32 columns of the tile's P buffer): the A
+      // operand of P V comes from TMEM, so P costs no shared-memory write here and no shared-memory read in the MMA
       // (with P in smem the kernel moved 224 KB per D = 128 tile through a 128 B/clk shared memory: 1750 cycles)
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
@@ -674,7 +697,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(pr[2 * i], pr[2 * i + 1]);
-        tmem_st_32x32_x16(s_taddr + c * 16, pk);
+        tmem_st_32x32_x16(p_taddr + c * 16, pk);
       }
       l = l * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
@@ -683,6 +706,13 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       tc_fence_before_sync();
       mbar_arrive(&p_full[st]);
       VL2_TRJ(5);   // proxy fence + arrive
+    };
+    {
+      const bool last_masked = p.causal || (n_kv * BKV > p.S);
+      const int n_plain = n_kv - (last_masked ? 1 : 0);
+      int j = 0;
+      for (; j < n_plain; ++j, ++gt) tile(j, std::false_type{});
+      for (; j < n_kv; ++j, ++gt) tile(j, std::true_type{});
     }
     if (tr) { tr_tiles += n_kv; ++tr_items; t0 = (unsigned)clock64(); }
     VL2_TL(tl, 120);
@@ -735,6 +765,7 @@ attn_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       for (int i = 0; i < 7; ++i) g_attn_trace[i] = acc_t[i];
       g_attn_trace[7] = tr_tiles;
       g_attn_trace[8] = tr_items;
+      g_attn_trace[10] = acc_t[7];
       g_attn_trace[9] = (unsigned)clock64() - tr_begin;   // whole item loop of this CTA (all items, traced or not)
     }
     if (threadIdx.x == 0) bulk_wait_read_all();   // the last store still reads this CTA's shared memory

@@ -97,6 +97,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait that PARKS the thread: try_wait with a suspend-time hint, so the hardware keeps the thread asleep until the phase
+// completes (or the hint expires) instead of returning to a polling loop after the short default limit.  For the roles
+// that wait LONG by design (a producer for a free ring slot, the MMA issuer for the softmax warps, epilogue warps for a
+// whole mainloop): their polling loops kept the SM's barrier unit so busy that every other thread's poll - even one that
+// is satisfied at once - took ~200 cycles instead of ~40 (attention trace: "repeated (satisfied) S poll").
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_parked(bar, parity)) {
+    if (++spins > VL2_MBAR_SPIN_LIMIT) { asm volatile("trap;"); }
+  }
+}
+
 // Wait for two barriers at once: both polls are in flight together, so a wait that is already satisfied costs one barrier
 // round trip instead of two (each poll is a few hundred cycles when eight warps hit the barrier unit at the same time).
 __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
