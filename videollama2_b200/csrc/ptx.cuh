@@ -91,6 +91,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define VL2_MBAR_SPIN_LIMIT (1u << 24)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // First poll outside the loop: ptxas puts a YIELD in front of a polling LOOP's try_wait, and a warp that yields next to
+  // a sibling warp with a long run of ready instructions (the other half-row's exp2 pass, an epilogue) is not picked
+  // again for ~200 cycles - even when the barrier was complete all along.  The straight-line poll carries no YIELD.
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > VL2_MBAR_SPIN_LIMIT) { asm volatile("trap;"); }
@@ -123,6 +127,11 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
 // Wait for two barriers at once: both polls are in flight together, so a wait that is already satisfied costs one barrier
 // round trip instead of two (each poll is a few hundred cycles when eight warps hit the barrier unit at the same time).
 __device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  {   // first pair of polls outside the loop (no YIELD in front of it: see mbar_wait)
+    const bool a = mbar_try_wait(bar_a, parity_a);
+    const bool b = mbar_try_wait(bar_b, parity_b);
+    if (a && b) return;
+  }
   uint32_t spins = 0;
   for (;;) {
     const bool a = mbar_try_wait(bar_a, parity_a);
