@@ -1,18 +1,25 @@
 // FlashAttention-style fused attention for sm_100a (non-causal ViT heads and causal GQA decoder heads).
 //
-// One CTA = one 128-row query tile of one (batch, head).  320 threads:
+// Work item = one 128-row query tile of one (batch, head).  320 threads:
 //   warps 0..7  softmax / output warps: TWO threads per query row (warps w and w+4 share TMEM lane quarter w & 3 and
 //               take key columns [0,64) / [64,128) of every S tile), so each SM sub-partition has two warps to overlap
-//               TMEM loads, MUFU exp2 and packing; the row maximum is exchanged through smem once per tile
+//               TMEM loads, MUFU exp2 and packing; the half-row maxima are exchanged through smem once per tile
 //   warp 8      TMA producers: lane 0 loads Q and the K ring (2 stages, freed right after Q K^T), lane 1 the V ring
-//               (2 stages, freed after P V); P is double buffered so softmax(j) never waits for P V(j-1)
-//   warp 9      TMEM allocator + MMA issuer (one lane):
-//                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128, accumulator in TMEM (double buffered)
-//                 Ot_j = P_j V_j      tcgen05.mma 128xDx16,   A = P (bf16, written to smem by the softmax warps),
-//                                     B = V tile as MN-major SW128 operand (no transpose pass needed)
+//               (2 stages, freed after P V)
+//   warp 9      TMEM allocator + MMA issuer (one ELECTED lane, descriptors as (lo, hi) words: back-to-back UTCHMMAs):
+//                 S_j  = Q K_j^T      tcgen05.mma 128x128x16, A/B K-major SW128 from smem, accumulator in TMEM (2 buffers)
+//                 O   += P_j V_j      tcgen05.mma 128xDx16, B = V tile as MN-major SW128 operand (no transpose pass)
 // Online softmax state (m, l) lives in registers of the row's thread; O accumulates in TMEM over all key tiles and is
 // rescaled in place only when a row maximum grows by more than 2^8 (lazy rescale).  S is read from TMEM once per tile.
-// QK^T of tile j+1 is issued before the softmax of tile j finishes, so tensor-core and MUFU work overlap.
+//
+// Two kernels:
+//   attn_fwd_persistent_kernel (default): one CTA per SM loops over work items.  P_j goes to TENSOR MEMORY (tcgen05.st,
+//     own columns) and P V reads its A operand from there - no shared-memory write / read for P; Q K^T(j+2) is issued
+//     ahead of P V(j); the item's output tile is staged in smem and leaves through ONE TMA store per 64-column atom;
+//     the two threads of a row synchronise through a 64-thread pair barrier; unmasked and masked key tiles are separate
+//     loops.  Cycle traces (vl2_debug_attn_trace / _timeline, tools/attn_trace.py) are their own instantiation.
+//   attn_fwd_kernel (VL2_ATTN_PERSISTENT=0, the round-1 form kept for A/B runs): one CTA per item, P through a
+//     double-buffered smem tile, per-thread 16-byte output stores.
 #include <stdlib.h>
 
 #include <type_traits>

@@ -1,7 +1,8 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,Nout] = epi(A[M,K] * W[N,K]^T).
 //
-//   warp 0      TMA producer   (one lane): cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
-//   warp 1      MMA issuer     (one lane): tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, accumulators in TMEM
+//   warp 0      TMA producer   (one elected lane): cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
+//   warp 1      MMA issuer     (one elected lane, (lo, hi) descriptor words: the four UTCHMMAs of a k-block are issued back
+//               to back): tcgen05.mma.cta_group::1/2.kind::f16, 128 x BN x 16, accumulators in TMEM
 //   warp 2      TMEM allocator (2 x BN fp32 columns: the epilogue of tile i overlaps the main loop of tile i+1)
 //   warps 4..11 epilogue: tcgen05.ld (thread == accumulator row; two warps per TMEM lane quarter take alternate
 //               32-column chunks, next chunk + residual prefetched while the current one is processed, bias staged in
