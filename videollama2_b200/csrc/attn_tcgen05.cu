@@ -18,8 +18,8 @@
 //     ahead of P V(j); the item's output tile is staged in smem and leaves through ONE TMA store per 64-column atom;
 //     the two threads of a row synchronise through a 64-thread pair barrier; unmasked and masked key tiles are separate
 //     loops.  Cycle traces (vl2_debug_attn_trace / _timeline, tools/attn_trace.py) are their own instantiation.
-//   attn_fwd_kernel (VL2_ATTN_PERSISTENT=0, the round-1 form kept for A/B runs): one CTA per item, P through a
-//     double-buffered smem tile, per-thread 16-byte output stores.
+//   attn_fwd_kernel (VL2_ATTN_PERSISTENT=0, the round-1 form kept UNCHANGED for A/B runs): one CTA per item, `lane == 0`
+//     MMA issuer with descriptors rebuilt per MMA, P through a double-buffered smem tile, per-thread 16-byte output stores.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -167,28 +167,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer: one ELECTED lane (the compiler then knows the branch is single-threaded and emits
-    // back-to-back UTCHMMAs; `lane == 0` made it wrap every MMA in an elect loop), descriptors as (lo, hi) words with
-    // the low words of every ring stage computed once =====================
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
-    constexpr uint32_t hi_kmaj = umma_desc_sw128_hi(1024);
-    const uint32_t q_lo = umma_desc_sw128_lo(smem_u32(sQ), 16);
-    const uint32_t k_lo0 = umma_desc_sw128_lo(smem_u32(sK), 16);
-    const uint32_t p_lo0 = umma_desc_sw128_lo(smem_u32(sP), 16);
-    const uint32_t v_lo0 = umma_desc_sw128_lo(smem_u32(sV), Cfg::kAtomBytes);   // MN-major: LBO = next 64-wide d atom
-    if (leader) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // B (= V tile) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t k_lo = k_lo0 + st * (Cfg::kTileBytes >> 4);
+        const uint32_t k_addr = smem_u32(sK + st * Cfg::kTileBytes);
         const uint32_t d_tmem = tmem_base + (st ? Cfg::kColS1 : Cfg::kColS0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = ((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4;
-          umma_bf16_ss_lohi(d_tmem, q_lo + off, hi_kmaj, k_lo + off, hi_kmaj, idesc_qk, kk != 0);
+          const uint32_t off = (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32;
+          umma_bf16_ss(d_tmem, umma_desc_sw128(q_addr + off, 16, 1024), umma_desc_sw128(k_addr + off, 16, 1024),
+                       idesc_qk, kk != 0);
         }
         umma_commit(&s_full[st]);
         umma_commit(&k_empty[st]);   // K_j is free as soon as Q K_j^T has run (the loader can fetch K_{j+2} early)
@@ -201,13 +195,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(&p_full[st], (j >> 1) & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t v_lo = v_lo0 + st * (Cfg::kTileBytes >> 4);
-        const uint32_t p_lo = p_lo0 + st * (Cfg::kPBytes >> 4);
+        const uint32_t v_addr = smem_u32(sV + st * Cfg::kTileBytes);
+        const uint32_t p_addr = smem_u32(sP + st * Cfg::kPBytes);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
-          // A = P: K-major atoms of 64 keys; B = V, MN-major: 16 keys = 2 groups of 8 rows (1024 B each)
-          umma_bf16_ss_lohi(tmem_base + Cfg::kColO, p_lo + (((kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32) >> 4), hi_kmaj,
-                            v_lo + ((kk * 2048) >> 4), hi_kmaj, idesc_pv, (j | kk) != 0);
+          const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * Cfg::kAtomBytes + (kk & 3) * 32, 16, 1024);
+          // MN-major B: 16 keys = 2 groups of 8 rows (1024 B each); next 64-wide d atom is kAtomBytes away (LBO)
+          const uint64_t db = umma_desc_sw128(v_addr + kk * 2048, Cfg::kAtomBytes, 1024);
+          umma_bf16_ss(tmem_base + Cfg::kColO, da, db, idesc_pv, (j | kk) != 0);
         }
         umma_commit(&o_full[st]);
         umma_commit(&v_empty[st]);
